@@ -1,0 +1,237 @@
+// matvec_kernels.cu — ExpandA and the fused sign/verify core:
+//     w = [INTT] ( A_hat * [NTT] v ),   A_hat = ExpandA(rho) or a pre-expanded shared matrix.
+//
+// Reference data flow being replaced (rtl_src/combined_top.v): NTT_Y :1850-1874 ->
+// MULT_A_Y :1875-1913 -> NTTI_W :1914-1933 for signing, :921-988 for keygen, :1347-1469 for
+// verification, with A produced by gen_a_ext/sampler_a_ext/rejection_a.  The FPGA writes A
+// to BRAM_0 (combined_top.v:795-803); here A_hat lives only in shared memory:
+//   * shared-rho / shared-A mode: every persistent CTA holds the whole k*l matrix in shared
+//     memory (16/30/56 KiB) for its lifetime (expanded in the prologue by k*l threads, one
+//     Keccak state per thread, or copied once from a pre-expanded buffer); each warp then
+//     streams batch items: l forward NTTs in registers, k accumulate-reduce-INTT rounds.
+//   * per-item-rho mode: one small CTA per item; k*l threads expand the item's matrix into
+//     shared memory, then warp 0 runs the same per-item core.
+// HBM traffic per item is (l + k) KiB (+32 B of rho); A never touches HBM.
+#include <cuda_runtime.h>
+
+#include "dilithium_b200.h"
+#include "keccak.cuh"
+#include "kernels.h"
+#include "ntt_core.cuh"
+
+namespace dil {
+
+constexpr int A_STRIDE = 260;  // words per A polynomial in shared memory (pad 4: spreads the
+                               // sampler's same-index stores over 8 bank groups, keeps 16-B alignment)
+
+// ---- materialising ExpandA (keys, tests): one thread per polynomial ----
+__global__ void __launch_bounds__(64) expand_a_kernel(int32_t* __restrict__ a_hat, const uint8_t* __restrict__ rho,
+                                                      int k, int l, size_t n_polys) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_polys) return;
+    int kl = k * l;
+    size_t r = t / kl;
+    int ij = (int)(t % kl);
+    int32_t* out = a_hat + t * N;
+    expand_a_poly(rho + r * 32, ij / l, ij % l, [&](int idx, uint32_t val) { out[idx] = (int32_t)val; });
+}
+
+cudaError_t launch_expand_a(int32_t* a_hat, const uint8_t* rho, size_t n_rho, int k, int l, int sm_count, cudaStream_t st) {
+    size_t n_polys = n_rho * (size_t)(k * l);
+    if (n_polys == 0) return cudaSuccess;
+    unsigned grid = (unsigned)((n_polys + 63) / 64);
+    expand_a_kernel<<<grid, 64, 0, st>>>(a_hat, rho, k, l, n_polys);
+    return cudaGetLastError();
+}
+
+// ---- per-item core, executed by one warp ----
+// v_item: l polys (global), w_item: k polys (global), a_sm: k*l polys in shared memory (stride A_STRIDE)
+template <int K, int L, bool NTT_IN, bool INTT_OUT>
+__device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const int32_t* __restrict__ v_item,
+                                          const uint32_t* __restrict__ a_sm, uint32_t* __restrict__ scr, int lane) {
+    uint32_t yh[L][8];  // NTT-domain inputs in layout C
+    if constexpr (NTT_IN) {
+        FwdTw ftw;
+        load_fwd_tw(ftw, &TW_FWD, lane);
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            const int32_t* p = v_item + j * N + lane;
+#pragma unroll
+            for (int r = 0; r < 8; r++) yh[j][r] = (uint32_t)p[32 * r];  // layout A: 128-B line per access
+            ntt_fwd_warp(yh[j], scr, ftw, lane);
+            __syncwarp();
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            const int4* p = reinterpret_cast<const int4*>(v_item + j * N) + lane;
+            int4 lo = p[0], hi = p[32];
+            yh[j][0] = canon_signed(lo.x); yh[j][1] = canon_signed(lo.y); yh[j][2] = canon_signed(lo.z); yh[j][3] = canon_signed(lo.w);
+            yh[j][4] = canon_signed(hi.x); yh[j][5] = canon_signed(hi.y); yh[j][6] = canon_signed(hi.z); yh[j][7] = canon_signed(hi.w);
+        }
+    }
+    InvTw itw;
+    if constexpr (INTT_OUT) load_inv_tw(itw, &TW_INV, lane);
+#pragma unroll 1
+    for (int i = 0; i < K; i++) {
+        uint64_t acc[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) acc[r] = 0;
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            const uint4* ap = reinterpret_cast<const uint4*>(a_sm + (i * L + j) * A_STRIDE) + lane;
+            uint4 lo = ap[0], hi = ap[32];
+            acc[0] += (uint64_t)lo.x * yh[j][0]; acc[1] += (uint64_t)lo.y * yh[j][1];
+            acc[2] += (uint64_t)lo.z * yh[j][2]; acc[3] += (uint64_t)lo.w * yh[j][3];
+            acc[4] += (uint64_t)hi.x * yh[j][4]; acc[5] += (uint64_t)hi.y * yh[j][5];
+            acc[6] += (uint64_t)hi.z * yh[j][6]; acc[7] += (uint64_t)hi.w * yh[j][7];
+        }
+        uint32_t x[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) x[r] = reduce49(acc[r]);
+        if constexpr (INTT_OUT) {
+            ntt_inv_warp(x, scr, itw, lane);
+            __syncwarp();
+            int32_t* o = w_item + i * N + lane;
+#pragma unroll
+            for (int r = 0; r < 8; r++) o[32 * r] = (int32_t)x[r];
+        } else {
+            int4* o = reinterpret_cast<int4*>(w_item + i * N) + lane;
+            o[0] = make_int4((int)x[0], (int)x[1], (int)x[2], (int)x[3]);
+            o[32] = make_int4((int)x[4], (int)x[5], (int)x[6], (int)x[7]);
+        }
+    }
+}
+
+// ---- shared-A persistent kernel ----
+template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT>
+__global__ void __launch_bounds__(WARPS * 32) matvec_shared_kernel(int32_t* __restrict__ w, const int32_t* __restrict__ a_hat,
+                                                                   const uint8_t* __restrict__ rho,
+                                                                   const int32_t* __restrict__ v, uint32_t batch) {
+    extern __shared__ __align__(16) uint32_t smem_u32v[];
+    uint32_t* a_sm = smem_u32v;                               // K*L*A_STRIDE
+    uint32_t* scr_all = smem_u32v + K * L * A_STRIDE;         // WARPS*SCRATCH_WORDS
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if constexpr (EXPAND) {
+        for (int t = threadIdx.x; t < K * L; t += blockDim.x) {
+            uint32_t* out = a_sm + t * A_STRIDE;
+            expand_a_poly(rho, t / L, t % L, [&](int idx, uint32_t val) { out[idx] = val; });
+        }
+    } else {
+        for (int t = threadIdx.x; t < K * L * (N / 4); t += blockDim.x) {
+            int p = t >> 6, c = t & 63;
+            int4 q = __ldg(reinterpret_cast<const int4*>(a_hat) + t);
+            reinterpret_cast<uint4*>(a_sm + p * A_STRIDE)[c] =
+                make_uint4(canon_signed(q.x), canon_signed(q.y), canon_signed(q.z), canon_signed(q.w));
+        }
+    }
+    __syncthreads();
+    uint32_t* scr = scr_all + warp * SCRATCH_WORDS;
+    for (uint32_t item = blockIdx.x * WARPS + warp; item < batch; item += gridDim.x * WARPS)
+        item_core<K, L, NTT_IN, INTT_OUT>(w + (size_t)item * K * N, v + (size_t)item * L * N, a_sm, scr, lane);
+}
+
+// ---- per-item-rho kernel: one CTA per item ----
+template <int K, int L, bool NTT_IN, bool INTT_OUT>
+__global__ void __launch_bounds__(((K * L + 31) / 32) * 32) matvec_item_kernel(int32_t* __restrict__ w,
+                                                                             const uint8_t* __restrict__ rho,
+                                                                             const int32_t* __restrict__ v) {
+    extern __shared__ __align__(16) uint32_t smem_u32v[];
+    uint32_t* a_sm = smem_u32v;
+    uint32_t* scr = smem_u32v + K * L * A_STRIDE;
+    const size_t item = blockIdx.x;
+    const int t = threadIdx.x;
+    if (t < K * L) {
+        uint32_t* out = a_sm + t * A_STRIDE;
+        expand_a_poly(rho + item * 32, t / L, t % L, [&](int idx, uint32_t val) { out[idx] = val; });
+    }
+    __syncthreads();
+    if (t < 32) item_core<K, L, NTT_IN, INTT_OUT>(w + item * K * N, v + item * L * N, a_sm, scr, t);
+}
+
+template <int K, int L>
+constexpr size_t shared_smem_bytes(int warps) {
+    return (size_t)(K * L * A_STRIDE + warps * SCRATCH_WORDS) * 4;
+}
+
+template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT>
+static cudaError_t launch_shared_t(int32_t* w, const int32_t* a_hat, const uint8_t* rho, const int32_t* v, size_t batch,
+                                   int sm_count, cudaStream_t st) {
+    auto kern = matvec_shared_kernel<K, L, WARPS, EXPAND, NTT_IN, INTT_OUT>;
+    constexpr size_t smem = shared_smem_bytes<K, L>(WARPS);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    int ctas_per_sm = (int)((220 * 1024) / smem);
+    if (ctas_per_sm > 2) ctas_per_sm = 2;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    size_t want = (batch + WARPS - 1) / WARPS;
+    size_t cap = (size_t)sm_count * ctas_per_sm;
+    unsigned grid = (unsigned)(want < cap ? want : cap);
+    kern<<<grid, WARPS * 32, smem, st>>>(w, a_hat, rho, v, (uint32_t)batch);
+    return cudaGetLastError();
+}
+
+template <int K, int L, bool EXPAND>
+static cudaError_t launch_shared_flags(int32_t* w, const int32_t* a_hat, const uint8_t* rho, const int32_t* v, size_t batch,
+                                       bool ntt_in, bool intt_out, int sm_count, cudaStream_t st) {
+    constexpr int WARPS = 8;
+    if (ntt_in && intt_out) return launch_shared_t<K, L, WARPS, EXPAND, true, true>(w, a_hat, rho, v, batch, sm_count, st);
+    if (ntt_in) return launch_shared_t<K, L, WARPS, EXPAND, true, false>(w, a_hat, rho, v, batch, sm_count, st);
+    if (intt_out) return launch_shared_t<K, L, WARPS, EXPAND, false, true>(w, a_hat, rho, v, batch, sm_count, st);
+    return launch_shared_t<K, L, WARPS, EXPAND, false, false>(w, a_hat, rho, v, batch, sm_count, st);
+}
+
+template <int K, int L, bool NTT_IN, bool INTT_OUT>
+static cudaError_t launch_item_t(int32_t* w, const uint8_t* rho, const int32_t* v, size_t batch, cudaStream_t st) {
+    auto kern = matvec_item_kernel<K, L, NTT_IN, INTT_OUT>;
+    constexpr size_t smem = (size_t)(K * L * A_STRIDE + SCRATCH_WORDS) * 4;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    constexpr int threads = ((K * L + 31) / 32) * 32;
+    kern<<<(unsigned)batch, threads, smem, st>>>(w, rho, v);
+    return cudaGetLastError();
+}
+
+template <int K, int L>
+static cudaError_t launch_item_flags(int32_t* w, const uint8_t* rho, const int32_t* v, size_t batch, bool ntt_in,
+                                     bool intt_out, cudaStream_t st) {
+    if (ntt_in && intt_out) return launch_item_t<K, L, true, true>(w, rho, v, batch, st);
+    if (ntt_in) return launch_item_t<K, L, true, false>(w, rho, v, batch, st);
+    if (intt_out) return launch_item_t<K, L, false, true>(w, rho, v, batch, st);
+    return launch_item_t<K, L, false, false>(w, rho, v, batch, st);
+}
+
+cudaError_t launch_matvec_expand(int32_t* w, const uint8_t* rho, const int32_t* v, int k, int l, size_t batch,
+                                 unsigned flags, int sm_count, cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    const bool per_item = flags & DIL_RHO_PER_ITEM, ni = flags & DIL_NTT_INPUT, io = flags & DIL_INTT_OUTPUT;
+    if (per_item) {
+        if (k == 4 && l == 4) return launch_item_flags<4, 4>(w, rho, v, batch, ni, io, st);
+        if (k == 6 && l == 5) return launch_item_flags<6, 5>(w, rho, v, batch, ni, io, st);
+        if (k == 8 && l == 7) return launch_item_flags<8, 7>(w, rho, v, batch, ni, io, st);
+    } else {
+        if (k == 4 && l == 4) return launch_shared_flags<4, 4, true>(w, nullptr, rho, v, batch, ni, io, sm_count, st);
+        if (k == 6 && l == 5) return launch_shared_flags<6, 5, true>(w, nullptr, rho, v, batch, ni, io, sm_count, st);
+        if (k == 8 && l == 7) return launch_shared_flags<8, 7, true>(w, nullptr, rho, v, batch, ni, io, sm_count, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_signcore(int32_t* w, const int32_t* a_hat, const int32_t* y, int k, int l, size_t batch, int sm_count,
+                            cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    if (k == 4 && l == 4) return launch_shared_flags<4, 4, false>(w, a_hat, nullptr, y, batch, true, true, sm_count, st);
+    if (k == 6 && l == 5) return launch_shared_flags<6, 5, false>(w, a_hat, nullptr, y, batch, true, true, sm_count, st);
+    if (k == 8 && l == 7) return launch_shared_flags<8, 7, false>(w, a_hat, nullptr, y, batch, true, true, sm_count, st);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace dil

@@ -1,0 +1,139 @@
+// ntt_kernels.cu — batched forward / inverse NTT kernels (sm_100a).
+//
+// Replaces ntt()/invntt() (ref_ntt.cpp:28-47, :59-87) and ntt2x2_ref()/invntt2x2_ref()
+// (ref_ntt2x2.cpp:37-145) for batches of polynomials resident in HBM.
+//
+// Execution model: persistent CTAs, one polynomial per warp per iteration.  Every warp
+// runs its own TMA pipeline: lane 0 issues 1 KiB cp.async.bulk loads STAGES-1 polynomials
+// ahead into the warp's private ring of shared-memory slots (completion on one mbarrier
+// per slot), the warp transforms a polynomial entirely in registers + its private scratch
+// (ntt_core.cuh), writes the canonical result back into the slot and lane 0 issues a
+// cp.async.bulk store.  There is no CTA-wide barrier anywhere; HBM traffic is exactly
+// 1 KiB in + 1 KiB out per polynomial, always as whole aligned 1 KiB bursts.
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+#include "ntt_core.cuh"
+#include "tma.cuh"
+
+namespace dil {
+
+constexpr int POLY_BYTES = N * 4;
+
+template <int WARPS, int STAGES>
+struct NttSmem {
+    alignas(128) uint32_t slot[WARPS][STAGES][N];
+    alignas(16) uint32_t scratch[WARPS][SCRATCH_WORDS];
+    alignas(8) uint64_t full[WARPS][STAGES];
+};
+
+template <int WARPS, int STAGES, int MIN_CTAS, bool INVERSE>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
+ntt_tma_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ src, uint32_t n_polys) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    auto& sm = *reinterpret_cast<NttSmem<WARPS, STAGES>*>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t gwarp = blockIdx.x * WARPS + warp;
+    const uint32_t stride = gridDim.x * WARPS;
+    if (gwarp >= n_polys) return;  // warp-uniform; no CTA-wide sync below
+    const uint32_t n_my = (n_polys - gwarp + stride - 1) / stride;
+
+    FwdTw ftw;
+    InvTw itw;
+    if constexpr (INVERSE) load_inv_tw(itw, &TW_INV, lane);
+    else load_fwd_tw(ftw, &TW_FWD, lane);
+
+    uint32_t* scr = sm.scratch[warp];
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) mbar_init(smem_u32(&sm.full[warp][s]), 1);
+        fence_mbar_init();
+        // prologue: prefetch STAGES-1 polynomials
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; s++) {
+            if ((uint32_t)s < n_my) {
+                uint32_t bar = smem_u32(&sm.full[warp][s]);
+                mbar_expect_tx(bar, POLY_BYTES);
+                bulk_g2s(smem_u32(sm.slot[warp][s]), src + (size_t)(gwarp + s * stride) * N, POLY_BYTES, bar);
+            }
+        }
+    }
+    __syncwarp();
+
+    int s = 0;
+    uint32_t parity = 0;
+    for (uint32_t k = 0; k < n_my; k++) {
+        uint32_t* slot = sm.slot[warp][s];
+        mbar_wait(smem_u32(&sm.full[warp][s]), parity);
+        uint32_t x[8];
+        if constexpr (!INVERSE) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) x[r] = slot[32 * r + lane];
+            ntt_fwd_warp(x, scr, ftw, lane);
+            uint4* o = reinterpret_cast<uint4*>(slot) + lane;
+            o[0] = make_uint4(x[0], x[1], x[2], x[3]);
+            o[32] = make_uint4(x[4], x[5], x[6], x[7]);
+        } else {
+            const uint4* in = reinterpret_cast<const uint4*>(slot) + lane;
+            uint4 lo = in[0], hi = in[32];
+            x[0] = lo.x; x[1] = lo.y; x[2] = lo.z; x[3] = lo.w;
+            x[4] = hi.x; x[5] = hi.y; x[6] = hi.z; x[7] = hi.w;
+            ntt_inv_warp(x, scr, itw, lane);
+#pragma unroll
+            for (int r = 0; r < 8; r++) slot[32 * r + lane] = x[r];
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g(dst + (size_t)(gwarp + k * stride) * N, smem_u32(slot), POLY_BYTES);
+            bulk_commit();
+            // refill the slot used one iteration ago (its store has had a full iteration)
+            uint32_t kn = k + STAGES - 1;
+            if (kn < n_my) {
+                int sn = s == 0 ? STAGES - 1 : s - 1;
+                bulk_wait_read<1>();
+                uint32_t bar = smem_u32(&sm.full[warp][sn]);
+                mbar_expect_tx(bar, POLY_BYTES);
+                bulk_g2s(smem_u32(sm.slot[warp][sn]), src + (size_t)(gwarp + kn * stride) * N, POLY_BYTES, bar);
+            }
+        }
+        if (++s == STAGES) {
+            s = 0;
+            parity ^= 1;
+        }
+    }
+    if (lane == 0) bulk_wait_all<0>();  // smem must outlive the last stores
+}
+
+// ---- launch configuration ----
+constexpr int NTT_WARPS = 8;
+constexpr int NTT_STAGES = 3;
+constexpr int NTT_CTAS_PER_SM = 4;
+
+template <bool INVERSE>
+static cudaError_t launch_ntt(int32_t* dst, const int32_t* src, size_t n_polys, int sm_count, cudaStream_t st) {
+    if (n_polys == 0) return cudaSuccess;
+    using Smem = NttSmem<NTT_WARPS, NTT_STAGES>;
+    auto kern = ntt_tma_kernel<NTT_WARPS, NTT_STAGES, NTT_CTAS_PER_SM, INVERSE>;
+    static bool configured = false;  // per-process; attribute is per-function and idempotent
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    size_t want = (n_polys + NTT_WARPS - 1) / NTT_WARPS;
+    size_t cap = (size_t)sm_count * NTT_CTAS_PER_SM;
+    unsigned grid = (unsigned)(want < cap ? want : cap);
+    kern<<<grid, NTT_WARPS * 32, sizeof(Smem), st>>>(dst, src, (uint32_t)n_polys);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ntt_fwd(int32_t* dst, const int32_t* src, size_t n, int sms, cudaStream_t st) {
+    return launch_ntt<false>(dst, src, n, sms, st);
+}
+cudaError_t launch_ntt_inv(int32_t* dst, const int32_t* src, size_t n, int sms, cudaStream_t st) {
+    return launch_ntt<true>(dst, src, n, sms, st);
+}
+
+}  // namespace dil

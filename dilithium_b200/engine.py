@@ -1,0 +1,225 @@
+"""Host-side mirror of the reference's polynomial-arithmetic interface on top of the C ABI.
+
+Names follow the reference (`dilithium-256/reference_code/ref_ntt.h:30-36`, `ref_ntt2x2.h:31-33`)
+plus the north_star aliases:
+
+    Engine.ntt / invntt / pointwise_barrett / ntt2x2_ref / invntt2x2_ref
+    Engine.invntt_tomont / poly_pointwise / polyvec_matrix_pointwise
+    Engine.pointwise_acc / add / sub            (operation_module modes 2/3/4, butterfly.v:144-164)
+    Engine.expand_a / matvec_expand / signcore  (ExpandA-fused mat-vec, combined_top.v:1850-1933)
+
+Every method accepts either
+  * numpy int32 arrays (host memory): routed through the `dil_*_host` entry points, which copy
+    to the device, run the CUDA kernels and copy back; a new array is returned; or
+  * torch CUDA int32 tensors: routed through the `dil_*_dev` entry points on torch's current
+    stream, no copies, asynchronous; the result tensor is returned (in-place when `out` is
+    the input).
+PyTorch is only the owner of device memory/streams here; all arithmetic happens in
+libdilithium_b200.so.  There is no CPU implementation behind this class.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+Q = 8380417
+N = 256
+LEVEL_DIMS = {2: (4, 4), 3: (6, 5), 5: (8, 7)}  # level -> (k, l), combined_top.v:520-551
+RHO_SHARED, RHO_PER_ITEM, NTT_INPUT, INTT_OUTPUT = 0, 1, 2, 4
+
+
+class DilithiumError(RuntimeError):
+    pass
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+class Engine:
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self._lib.dil_engine_create(ctypes.byref(h), int(device))
+        if rc != 0:
+            raise DilithiumError(f"dil_engine_create(device={device}) failed: "
+                                 f"{self._lib.dil_status_string(rc).decode()} (no CPU fallback exists)")
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dil_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing ----
+    def _check(self, rc, what):
+        if rc != 0:
+            raise DilithiumError(f"{what}: {self._lib.dil_status_string(rc).decode()}: "
+                                 f"{self._lib.dil_last_error(self._h).decode()}")
+
+    @property
+    def sm_count(self):
+        return self._lib.dil_engine_sm_count(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.dil_engine_launch_count(self._h))
+
+    @staticmethod
+    def _np(a, dtype=np.int32):
+        a = np.ascontiguousarray(a, dtype=dtype)
+        return a
+
+    @staticmethod
+    def _stream():
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    @staticmethod
+    def _tcheck(t, dtype=None):
+        import torch
+        dtype = dtype or torch.int32
+        if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+            raise DilithiumError(f"expected a contiguous CUDA {dtype} tensor")
+        return ctypes.c_void_p(t.data_ptr())
+
+    @staticmethod
+    def _npolys(a):
+        n = a.size if isinstance(a, np.ndarray) else a.numel()
+        if n % N:
+            raise DilithiumError("array size is not a multiple of 256 coefficients")
+        return n // N
+
+    # ---- transforms ----
+    def _unary(self, name, a, out=None):
+        if _is_torch(a):
+            out = a.new_empty(a.shape) if out is None else out
+            rc = getattr(self._lib, f"dil_{name}_dev")(self._h, self._tcheck(out), self._tcheck(a), self._npolys(a), self._stream())
+            self._check(rc, f"dil_{name}_dev")
+            return out
+        buf = self._np(a).copy()
+        rc = getattr(self._lib, f"dil_{name}_host")(self._h, buf.ctypes.data_as(ctypes.c_void_p), self._npolys(buf))
+        self._check(rc, f"dil_{name}_host")
+        return buf
+
+    def ntt(self, a, out=None):
+        """ref_ntt.h:30  void ntt(data_t a[256]) - batched, canonical output."""
+        return self._unary("ntt", a, out)
+
+    def invntt(self, a, out=None):
+        """ref_ntt.h:36  void invntt(data_t a[256]) - batched, includes 256^-1, canonical output."""
+        return self._unary("invntt", a, out)
+
+    ntt2x2_ref = ntt          # ref_ntt2x2.h:31 (same map; the engine's schedule is radix-2x2-style)
+    invntt2x2_ref = invntt    # ref_ntt2x2.h:33
+    invntt_tomont = invntt    # north_star alias (plain domain)
+
+    # ---- coefficient-wise ----
+    def _binary(self, name, a, b, c=None):
+        if _is_torch(a):
+            c = a.new_empty(a.shape) if c is None else c
+            rc = getattr(self._lib, f"dil_{name}_dev")(self._h, self._tcheck(c), self._tcheck(a), self._tcheck(b), self._npolys(a), self._stream())
+            self._check(rc, f"dil_{name}_dev")
+            return c
+        a, b = self._np(a), self._np(b)
+        if a.shape != b.shape:
+            raise DilithiumError("shape mismatch")
+        c = np.empty_like(a) if c is None else self._np(c).copy()
+        rc = getattr(self._lib, f"dil_{name}_host")(self._h, c.ctypes.data_as(ctypes.c_void_p), a.ctypes.data_as(ctypes.c_void_p),
+                                                    b.ctypes.data_as(ctypes.c_void_p), self._npolys(a))
+        self._check(rc, f"dil_{name}_host")
+        return c
+
+    def pointwise_barrett(self, a, b, c=None):
+        """ref_ntt.h:32-34  c = a o b mod Q."""
+        return self._binary("pointwise", a, b, c)
+
+    poly_pointwise = pointwise_barrett
+
+    def pointwise_acc(self, c, a, b):
+        """butterfly.v:144-150 MULT mode: c + a o b."""
+        return self._binary("pointwise_acc", a, b, c)
+
+    def add(self, a, b, c=None):
+        return self._binary("add", a, b, c)
+
+    def sub(self, a, b, c=None):
+        return self._binary("sub", a, b, c)
+
+    # ---- mat-vec family ----
+    def polyvec_matrix_pointwise(self, a_hat, v, k, l, w=None):
+        """MULT_MODE loop nest (combined_top.v:921-958): w[b,i] = sum_j a_hat[i*l+j] o v[b,j]."""
+        if _is_torch(v):
+            batch = self._npolys(v) // l
+            w = v.new_empty((batch, k, N)) if w is None else w
+            rc = self._lib.dil_matvec_dev(self._h, self._tcheck(w), self._tcheck(a_hat), self._tcheck(v), k, l, batch, self._stream())
+            self._check(rc, "dil_matvec_dev")
+            return w
+        a_hat, v = self._np(a_hat), self._np(v)
+        batch = self._npolys(v) // l
+        w = np.empty((batch, k, N), dtype=np.int32)
+        rc = self._lib.dil_matvec_host(self._h, w.ctypes.data_as(ctypes.c_void_p), a_hat.ctypes.data_as(ctypes.c_void_p),
+                                       v.ctypes.data_as(ctypes.c_void_p), k, l, batch)
+        self._check(rc, "dil_matvec_host")
+        return w
+
+    matvec = polyvec_matrix_pointwise
+
+    def expand_a(self, rho, k, l):
+        """gen_a_ext / sampler_a_ext / rejection_a: rho[n,32] -> a_hat[n, k*l, 256]."""
+        if _is_torch(rho):
+            import torch
+            n = rho.numel() // 32
+            a = torch.empty((n, k * l, N), dtype=torch.int32, device=rho.device)
+            rc = self._lib.dil_expand_a_dev(self._h, self._tcheck(a), self._tcheck(rho, torch.uint8), n, k, l, self._stream())
+            self._check(rc, "dil_expand_a_dev")
+            return a
+        rho = self._np(rho, np.uint8).reshape(-1, 32)
+        a = np.empty((rho.shape[0], k * l, N), dtype=np.int32)
+        rc = self._lib.dil_expand_a_host(self._h, a.ctypes.data_as(ctypes.c_void_p), rho.ctypes.data_as(ctypes.c_void_p), rho.shape[0], k, l)
+        self._check(rc, "dil_expand_a_host")
+        return a
+
+    def matvec_expand(self, rho, v, k, l, per_item=False, ntt_input=False, intt_output=False, w=None):
+        """w[b] = [INTT](ExpandA(rho) * [NTT] v[b]) with A generated on chip (never in HBM)."""
+        flags = (RHO_PER_ITEM if per_item else 0) | (NTT_INPUT if ntt_input else 0) | (INTT_OUTPUT if intt_output else 0)
+        if _is_torch(v):
+            import torch
+            batch = self._npolys(v) // l
+            w = v.new_empty((batch, k, N)) if w is None else w
+            rc = self._lib.dil_matvec_expand_dev(self._h, self._tcheck(w), self._tcheck(rho, torch.uint8), self._tcheck(v), k, l, batch, flags, self._stream())
+            self._check(rc, "dil_matvec_expand_dev")
+            return w
+        rho, v = self._np(rho, np.uint8), self._np(v)
+        batch = self._npolys(v) // l
+        if rho.size != (32 * batch if per_item else 32):
+            raise DilithiumError("rho has the wrong size for this mode")
+        w = np.empty((batch, k, N), dtype=np.int32)
+        rc = self._lib.dil_matvec_expand_host(self._h, w.ctypes.data_as(ctypes.c_void_p), rho.ctypes.data_as(ctypes.c_void_p),
+                                              v.ctypes.data_as(ctypes.c_void_p), k, l, batch, flags)
+        self._check(rc, "dil_matvec_expand_host")
+        return w
+
+    def signcore(self, a_hat, y, k, l, w=None):
+        """cfg2 core in one kernel: w[b] = INTT(a_hat * NTT(y[b]))  (NTT_Y -> MULT_A_Y -> NTTI_W)."""
+        if _is_torch(y):
+            batch = self._npolys(y) // l
+            w = y.new_empty((batch, k, N)) if w is None else w
+            rc = self._lib.dil_signcore_dev(self._h, self._tcheck(w), self._tcheck(a_hat), self._tcheck(y), k, l, batch, self._stream())
+            self._check(rc, "dil_signcore_dev")
+            return w
+        a_hat, y = self._np(a_hat), self._np(y)
+        batch = self._npolys(y) // l
+        w = np.empty((batch, k, N), dtype=np.int32)
+        rc = self._lib.dil_signcore_host(self._h, w.ctypes.data_as(ctypes.c_void_p), a_hat.ctypes.data_as(ctypes.c_void_p),
+                                         y.ctypes.data_as(ctypes.c_void_p), k, l, batch)
+        self._check(rc, "dil_signcore_host")
+        return w

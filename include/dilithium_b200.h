@@ -1,0 +1,130 @@
+/*
+ * dilithium_b200.h — C ABI of the B200-native batched Dilithium polynomial-arithmetic
+ * engine (libdilithium_b200.so).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * This is the drop-in boundary for the hot path of GMUCERG/Dilithium (paths relative to
+ * the reference root).  Each entry point names the reference interface it replaces:
+ *
+ *   dil_ntt*            void ntt(data_t a[256])                 dilithium-256/reference_code/ref_ntt.h:30
+ *                       void ntt2x2_ref(data_t a[256])          dilithium-256/reference_code/ref_ntt2x2.h:31
+ *                       operation_module mode 0 (FORWARD)       rtl_src/operation_module.v:28-55
+ *   dil_invntt*         void invntt(data_t a[256])              dilithium-256/reference_code/ref_ntt.h:36
+ *                       void invntt2x2_ref(data_t a[256])       dilithium-256/reference_code/ref_ntt2x2.h:33
+ *                       operation_module mode 1 (INVERSE)       rtl_src/operation_module.v:28-55
+ *   dil_pointwise*      void pointwise_barrett(c, a, b)         dilithium-256/reference_code/ref_ntt.h:32-34
+ *   dil_pointwise_acc*  operation_module mode 2 (MULT = a*b+acc) rtl_src/butterfly.v:144-150
+ *   dil_add* / dil_sub* operation_module modes 3 / 4            rtl_src/butterfly.v:151-164
+ *   dil_matvec*         MULT_MODE loop nest ("polyvec_matrix_pointwise")
+ *                                                               rtl_src/combined_top.v:921-958, :1347-1386, :1875-1913
+ *   dil_expand_a*       gen_a_ext / sampler_a_ext / rejection_a rtl_src/gen_a_ext.v:29-409,
+ *                                                               sampler_a_ext.v:100-146, rejection_a.v:63-113
+ *   dil_matvec_expand*  ExpandA fused into the mat-vec (A never written to HBM); optional
+ *                       fused NTT on the input vector and INTT on the output vector
+ *                       (sign: NTT_Y -> MULT_A_Y -> NTTI_W, combined_top.v:1850-1933)
+ *
+ * Conventions:
+ *   - a polynomial is 256 contiguous int32 (params.h:30-35); a batch is n contiguous polys.
+ *   - inputs may be any representative in (-Q, Q); outputs are CANONICAL in [0, Q).  The
+ *     reference emits signed non-canonical residues and its own tests compare mod Q
+ *     (ref_test_ntt_ntt2x2.cpp:31-42); results here are equal to the reference's mod Q.
+ *   - arithmetic is plain-domain (no Montgomery factor), forward NTT natural -> bit-reversed
+ *     order, inverse includes the 256^-1 scaling, exactly as ref_ntt.cpp:28-87.
+ *   - caller owns every buffer; no allocation happens inside *_dev calls; dst == src
+ *     (in-place) is legal everywhere, as is c == a for pointwise (ntt2x2_test.cpp:102).
+ *   - *_dev entry points take DEVICE pointers (16-byte aligned) and a cudaStream_t passed as
+ *     void* (NULL = default stream); they enqueue work and return without synchronising.
+ *   - *_host entry points take HOST pointers, copy in, run, copy out and synchronise.
+ *   - every function returns 0 on success or a negative dil_status; there is no CPU fallback:
+ *     without a usable CUDA device dil_engine_create fails with DIL_ERR_NO_DEVICE.
+ *   - an engine handle is bound to one device; calls on one handle from several threads are
+ *     safe as long as they use different streams for overlapping buffers.
+ */
+#ifndef DILITHIUM_B200_H
+#define DILITHIUM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIL_Q 8380417
+#define DIL_N 256
+
+typedef struct dil_engine dil_engine_t;
+
+typedef enum {
+    DIL_OK = 0,
+    DIL_ERR_NO_DEVICE = -1,   /* no CUDA device / driver */
+    DIL_ERR_CUDA = -2,        /* a CUDA call failed; see dil_last_error() */
+    DIL_ERR_ARG = -3,         /* null / misaligned pointer, bad level, bad dims */
+    DIL_ERR_ALLOC = -4,       /* host or device allocation failed (host-variant staging) */
+    DIL_ERR_UNSUPPORTED = -5
+} dil_status;
+
+/* flags for dil_matvec_expand_* */
+#define DIL_RHO_SHARED   0u   /* one 32-byte rho for the whole batch               */
+#define DIL_RHO_PER_ITEM 1u   /* rho[item] : batch x 32 bytes                       */
+#define DIL_NTT_INPUT    2u   /* v is in the time domain: apply NTT before the product */
+#define DIL_INTT_OUTPUT  4u   /* apply INTT to every output polynomial              */
+
+/* ---- engine lifetime ---- */
+int dil_engine_create(dil_engine_t **out, int device);
+int dil_engine_destroy(dil_engine_t *e);
+const char *dil_status_string(int status);
+const char *dil_last_error(const dil_engine_t *e);      /* text of the last CUDA error on e */
+int dil_engine_device(const dil_engine_t *e);
+int dil_engine_sm_count(const dil_engine_t *e);
+/* (k, l) for level in {2,3,5} (combined_top.v:520-551); returns DIL_ERR_ARG otherwise */
+int dil_level_dims(int level, int *k, int *l);
+/* number of engine kernels launched on this handle since creation (bench evidence) */
+uint64_t dil_engine_launch_count(const dil_engine_t *e);
+
+/* ---- device-pointer API (hot path) ---- */
+int dil_ntt_dev(dil_engine_t *e, int32_t *dst, const int32_t *src, size_t n_polys, void *stream);
+int dil_invntt_dev(dil_engine_t *e, int32_t *dst, const int32_t *src, size_t n_polys, void *stream);
+int dil_pointwise_dev(dil_engine_t *e, int32_t *c, const int32_t *a, const int32_t *b, size_t n_polys, void *stream);
+/* c = c + a o b */
+int dil_pointwise_acc_dev(dil_engine_t *e, int32_t *c, const int32_t *a, const int32_t *b, size_t n_polys, void *stream);
+int dil_add_dev(dil_engine_t *e, int32_t *c, const int32_t *a, const int32_t *b, size_t n_polys, void *stream);
+int dil_sub_dev(dil_engine_t *e, int32_t *c, const int32_t *a, const int32_t *b, size_t n_polys, void *stream);
+/* w[b][i] = sum_j a_hat[i*l+j] o v[b][j];  a_hat: k*l polys shared by the batch,
+   v: batch*l polys, w: batch*k polys, all NTT domain */
+int dil_matvec_dev(dil_engine_t *e, int32_t *w, const int32_t *a_hat, const int32_t *v,
+                   int k, int l, size_t batch, void *stream);
+/* a_hat[r][i*l+j] = ExpandA(rho[r])_{i,j}: n_rho * k*l polys (materialised; for tests/keys) */
+int dil_expand_a_dev(dil_engine_t *e, int32_t *a_hat, const uint8_t *rho, size_t n_rho,
+                     int k, int l, void *stream);
+/* fused: w[b] = [INTT] ( ExpandA(rho) * [NTT] v[b] ); A is never written to HBM */
+int dil_matvec_expand_dev(dil_engine_t *e, int32_t *w, const uint8_t *rho, const int32_t *v,
+                          int k, int l, size_t batch, unsigned flags, void *stream);
+/* cfg2 sign core with a pre-expanded shared A: w[b] = INTT(a_hat * NTT(y[b])) in ONE kernel */
+int dil_signcore_dev(dil_engine_t *e, int32_t *w, const int32_t *a_hat, const int32_t *y,
+                     int k, int l, size_t batch, void *stream);
+
+/* ---- host-pointer API (copies inside; synchronous) ---- */
+int dil_ntt_host(dil_engine_t *e, int32_t *polys, size_t n_polys);
+int dil_invntt_host(dil_engine_t *e, int32_t *polys, size_t n_polys);
+int dil_pointwise_host(dil_engine_t *e, int32_t *c, const int32_t *a, const int32_t *b, size_t n_polys);
+int dil_pointwise_acc_host(dil_engine_t *e, int32_t *c, const int32_t *a, const int32_t *b, size_t n_polys);
+int dil_add_host(dil_engine_t *e, int32_t *c, const int32_t *a, const int32_t *b, size_t n_polys);
+int dil_sub_host(dil_engine_t *e, int32_t *c, const int32_t *a, const int32_t *b, size_t n_polys);
+int dil_matvec_host(dil_engine_t *e, int32_t *w, const int32_t *a_hat, const int32_t *v,
+                    int k, int l, size_t batch);
+int dil_expand_a_host(dil_engine_t *e, int32_t *a_hat, const uint8_t *rho, size_t n_rho, int k, int l);
+int dil_matvec_expand_host(dil_engine_t *e, int32_t *w, const uint8_t *rho, const int32_t *v,
+                           int k, int l, size_t batch, unsigned flags);
+int dil_signcore_host(dil_engine_t *e, int32_t *w, const int32_t *a_hat, const int32_t *y,
+                      int k, int l, size_t batch);
+
+/* ---- north_star aliases (plain domain, identical to the above) ---- */
+int dil_invntt_tomont_dev(dil_engine_t *e, int32_t *dst, const int32_t *src, size_t n_polys, void *stream);
+int dil_poly_pointwise_dev(dil_engine_t *e, int32_t *c, const int32_t *a, const int32_t *b, size_t n_polys, void *stream);
+int dil_polyvec_matrix_pointwise_dev(dil_engine_t *e, int32_t *w, const int32_t *a_hat, const int32_t *v,
+                                     int k, int l, size_t batch, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DILITHIUM_B200_H */
