@@ -116,12 +116,8 @@ class Oracle:
         self.lib.orc_signcore_batch_mt(_i32(w), _i32(y), _i32(a_hat), k, l, ctypes.c_size_t(y.shape[0]), threads)
         return w, y
 
-    def shake(self, data, outlen, bits=256):
-        data = np.frombuffer(bytes(data), dtype=np.uint8).copy() if len(data) else np.zeros(1, np.uint8)
-        n = len(bytes(data)) if False else None
-        out = np.empty(outlen, dtype=np.uint8)
-        fn = self.lib.orc_shake256 if bits == 256 else self.lib.orc_shake128
-        return out, fn
+    def time_signcore(self, a_hat, y, k, l, threads=1, steps=1, warmup=0):
+        return _time_signcore(self.lib.orc_signcore_batch_mt, a_hat, y, k, l, threads, steps, warmup)
 
     def shake_bytes(self, data: bytes, outlen: int, bits=256) -> bytes:
         buf = np.frombuffer(data, dtype=np.uint8).copy() if data else np.zeros(1, np.uint8)
@@ -173,8 +169,27 @@ class Oracle:
                                    _u8(c8(zp)), _u8(c8(hp)), _u8(c8(c)))
 
 
+def _time_signcore(cfn, a_hat, y, k, l, threads, steps, warmup):
+    """Wall-clock seconds per call of a C sign-core batch driver (buffers prepared outside the
+    timed region; the transforms are data-independent so y is transformed in place repeatedly)."""
+    import time
+    y = np.ascontiguousarray(y, dtype=np.int32).copy().reshape(-1, l, N)
+    a_hat = np.ascontiguousarray(a_hat, dtype=np.int32)
+    w = np.empty((y.shape[0], k, N), dtype=np.int32)
+    args = (_i32(w), _i32(y), _i32(a_hat), k, l, ctypes.c_size_t(y.shape[0]), threads)
+    for _ in range(warmup):
+        cfn(*args)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cfn(*args)
+    return (time.perf_counter() - t0) / steps
+
+
 class Ref:
     """The reference's own compiled C++ (oracle/_ref/libdilref.so)."""
+
+    def time_signcore(self, a_hat, y, k, l, threads=1, steps=1, warmup=0):
+        return _time_signcore(self.lib.ref_signcore_batch, a_hat, y, k, l, threads, steps, warmup)
 
     def __init__(self, lib):
         self.lib = lib
