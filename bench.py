@@ -196,8 +196,8 @@ def run_engine(args):
     if rank == 0:
         g0 = torch.Generator(device="cpu").manual_seed(SEED)
         rho.copy_(torch.randint(0, 256, (32,), dtype=torch.uint8, generator=g0))
-    if world > 1:
-        dist.broadcast(rho, src=0)
+    from dilithium_b200.sharding import broadcast_rho
+    broadcast_rho(rho, src=0)
     a_hat = eng.expand_a(rho, k, l)[0].contiguous()
 
     # per-rank synthetic batch (shard = contiguous item range of the global batch), pinned host copy for e2e
