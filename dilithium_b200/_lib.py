@@ -47,6 +47,12 @@ SIGNATURES = {
     "dil_expand_a_host": (c_int, [c_void, c_void, c_void, c_size, c_int, c_int]),
     "dil_matvec_expand_host": (c_int, [c_void, c_void, c_void, c_void, c_int, c_int, c_size, c_uint]),
     "dil_signcore_host": (c_int, [c_void, c_void, c_void, c_void, c_int, c_int, c_size]),
+    "dil_sign_sizes": (c_int, [c_int, ctypes.POINTER(c_size), ctypes.POINTER(c_size)]),
+    "dil_sign_key_create": (c_int, [c_void, ctypes.POINTER(c_void), c_int, c_void, c_void, c_void, c_void, c_void, c_void]),
+    "dil_sign_key_destroy": (c_int, [c_void, c_void]),
+    "dil_sign_batch_host": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void]),
+    "dil_sign_batch_dev": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void, c_void]),
+    "dil_sign_last_rounds": (ctypes.c_uint32, [c_void]),
     "dil_invntt_tomont_dev": (c_int, [c_void, c_void, c_void, c_size, c_void]),
     "dil_poly_pointwise_dev": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void]),
     "dil_polyvec_matrix_pointwise_dev": (c_int, [c_void, c_void, c_void, c_void, c_int, c_int, c_size, c_void]),

@@ -12,18 +12,8 @@
 #include <string>
 
 #include "dilithium_b200.h"
+#include "engine_priv.h"
 #include "kernels.h"
-
-struct dil_engine {
-    int device = -1;
-    int sm_count = 0;
-    std::atomic<uint64_t> launches{0};
-    std::mutex mu;           // guards staging + last_error
-    void* staging[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t staging_bytes[4] = {0, 0, 0, 0};
-    cudaStream_t host_stream = nullptr;
-    std::string last_error;
-};
 
 namespace {
 
@@ -37,18 +27,7 @@ int fail_cuda(dil_engine* e, cudaError_t err, const char* what) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = true;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
-    }
-    ~DeviceGuard() {
-        int cur = -1;
-        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
-    }
-};
+using dil::DeviceGuard;
 
 bool dims_ok(int k, int l) { return k >= 1 && k <= 8 && l >= 1 && l <= 8; }
 bool level_dims(int k, int l) { return (k == 4 && l == 4) || (k == 6 && l == 5) || (k == 8 && l == 7); }

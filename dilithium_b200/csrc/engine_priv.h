@@ -1,0 +1,35 @@
+// engine_priv.h - private definition of the engine handle (shared by capi.cu and sign_api.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <mutex>
+#include <string>
+
+struct dil_engine {
+    int device = -1;
+    int sm_count = 0;
+    std::atomic<uint64_t> launches{0};
+    std::mutex mu;           // guards staging + last_error
+    void* staging[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t staging_bytes[4] = {0, 0, 0, 0};
+    cudaStream_t host_stream = nullptr;
+    std::string last_error;
+};
+
+
+namespace dil {
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+}  // namespace dil

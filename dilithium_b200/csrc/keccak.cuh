@@ -32,17 +32,21 @@ __device__ __forceinline__ uint64_t rotl64(uint64_t x, int n) {
     return ((uint64_t)nhi << 32) | nlo;
 }
 
-__device__ __forceinline__ void keccak_f1600(uint64_t (&A)[25]) {
-    constexpr uint64_t RC[24] = {
+// round constants (keccak_cons.vhd:25-33); uniform index -> constant-cache broadcast
+static __constant__ uint64_t KECCAK_RC[24] = {
         0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
         0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
         0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
         0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
         0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
         0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+
+// 24 rounds; the round body is fully unrolled (all lane indices static), the round loop is
+// kept rolled so one permutation is ~190 instructions of code instead of ~4500.
+__device__ __forceinline__ void keccak_f1600(uint64_t (&A)[25]) {
     // rho rotation of lane x+5y
     constexpr int RHO[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < 24; r++) {
         uint64_t C[5], B[25];
 #pragma unroll
@@ -61,7 +65,7 @@ __device__ __forceinline__ void keccak_f1600(uint64_t (&A)[25]) {
         for (int y = 0; y < 5; y++)
 #pragma unroll
             for (int x = 0; x < 5; x++) A[x + 5 * y] = B[x + 5 * y] ^ (~B[(x + 1) % 5 + 5 * y] & B[(x + 2) % 5 + 5 * y]);
-        A[0] ^= RC[r];
+        A[0] ^= KECCAK_RC[r];
     }
 }
 
@@ -102,6 +106,49 @@ __device__ __forceinline__ void expand_a_poly(const uint8_t* __restrict__ rho, i
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// SHAKE-256 helpers (rate 136 B = 17 lanes) for the sign/verify pipeline.  All message
+// schedules used by the scheme are expressed as a "lane source" lane_at(idx) -> uint64 so the
+// state registers are only ever indexed with compile-time constants.
+// ---------------------------------------------------------------------------------------
+constexpr int SHAKE256_LANES = 17;
+
+// Absorb `total_bytes` bytes delivered as 64-bit little-endian lanes by lane_at(idx) (bytes
+// beyond total_bytes inside the last lane must read as zero), pad (0x1F .. 0x80) and permute
+// once more, leaving the first squeezable block in A.
+template <class LaneAt>
+__device__ __forceinline__ void shake256_absorb_lanes(uint64_t (&A)[25], size_t total_bytes, LaneAt lane_at) {
+#pragma unroll
+    for (int t = 0; t < 25; t++) A[t] = 0;
+    const size_t nfull = total_bytes / 136;
+    for (size_t b = 0; b < nfull; b++) {
+#pragma unroll
+        for (int i = 0; i < SHAKE256_LANES; i++) A[i] ^= lane_at(b * SHAKE256_LANES + i);
+        keccak_f1600(A);
+    }
+    const unsigned rem = (unsigned)(total_bytes - nfull * 136);
+    const unsigned rem_lanes = (rem + 7) >> 3;
+#pragma unroll
+    for (int i = 0; i < SHAKE256_LANES; i++) {
+        if ((unsigned)i < rem_lanes) A[i] ^= lane_at(nfull * SHAKE256_LANES + i);
+        if ((unsigned)i == (rem >> 3)) A[i] ^= 0x1FULL << (8 * (rem & 7));
+    }
+    A[16] ^= 0x80ULL << 56;
+    keccak_f1600(A);
+}
+
+// little-endian 64-bit load from an arbitrarily aligned byte string, zero beyond `len`
+__device__ __forceinline__ uint64_t load_lane_bytes(const uint8_t* __restrict__ p, size_t off, size_t len) {
+    uint64_t v = 0;
+    if (off + 8 <= len) {
+#pragma unroll
+        for (int b = 0; b < 8; b++) v |= (uint64_t)p[off + b] << (8 * b);
+    } else {
+        for (int b = 0; b < 8 && off + b < len; b++) v |= (uint64_t)p[off + b] << (8 * b);
+    }
+    return v;
 }
 
 #endif  // __CUDACC__

@@ -1,0 +1,286 @@
+// sign_api.cu — host orchestration of batched signing behind the C ABI.
+// Replaces, for a batch, what rtl_src/combined_top.v does for one signature in mode 2 with the
+// I/O order of rtl_tb/tb_sign_top.v:171-335 (inputs rho, mlen, tr, M, K, s1, s2, t0; outputs z,
+// h, c~).  Key material is expanded once per key (ExpandA + NTT of s1, s2, t0: the LOAD_RHO /
+// NTT_S1 / NTT_S2 / NTT_T0 states, combined_top.v:1560-1767); each round then runs
+// ExpandMask -> fused sign core -> w1 pack -> challenge -> tail over the active items.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "dil_params.h"
+#include "dilithium_b200.h"
+#include "engine_priv.h"
+#include "kernels.h"
+
+using dil::DeviceGuard;
+using dil::LevelParams;
+
+struct dil_sign_key {
+    LevelParams P{};
+    int device = -1;
+    int32_t* a_hat = nullptr;    // k*l polys
+    int32_t* key_hat = nullptr;  // s1_hat (l) | s2_hat (k) | t0_hat (k)
+    uint8_t* seeds = nullptr;    // tr[32] | K[32]
+    // workspace (grow-only, sized for `cap` items)
+    std::mutex mu;
+    size_t cap = 0;
+    uint64_t *mu_d = nullptr, *rhop = nullptr, *w1p = nullptr;
+    uint16_t* kappa = nullptr;
+    uint32_t *active[2] = {nullptr, nullptr}, *count = nullptr;
+    int32_t *y = nullptr, *w = nullptr, *z = nullptr;
+    int8_t* c = nullptr;
+    // host-variant staging
+    uint8_t *msgs_d = nullptr, *zp_d = nullptr, *h_d = nullptr, *ct_d = nullptr;
+    uint64_t* off_d = nullptr;
+    uint32_t* att_d = nullptr;
+    size_t msgs_cap = 0, out_cap = 0;
+    uint32_t last_rounds = 0;
+};
+
+namespace {
+
+int fail(dil_engine* e, cudaError_t err, const char* what) {
+    e->last_error = std::string(what) + ": " + cudaGetErrorString(err);
+    return DIL_ERR_CUDA;
+}
+#define CK(expr)                                                   \
+    do {                                                           \
+        cudaError_t err_ = (expr);                                 \
+        if (err_ != cudaSuccess) return fail(e, err_, #expr);      \
+    } while (0)
+
+// little-endian fixed-width bit stream -> values (decoder.v:89-143)
+void bits_get(uint32_t* v, const uint8_t* in, int n, int width) {
+    size_t bit = 0;
+    for (int i = 0; i < n; i++) {
+        uint32_t x = 0;
+        for (int b = 0; b < width; b++, bit++) x |= (uint32_t)((in[bit >> 3] >> (bit & 7)) & 1u) << b;
+        v[i] = x;
+    }
+}
+
+template <class T>
+cudaError_t dmalloc(T** p, size_t count) {
+    return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+}
+
+void free_ws(dil_sign_key* k) {
+    void* ptrs[] = {k->mu_d, k->rhop, k->w1p, k->kappa, k->active[0], k->active[1], k->count, k->y, k->w, k->z, k->c};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    k->mu_d = k->rhop = k->w1p = nullptr;
+    k->kappa = nullptr;
+    k->active[0] = k->active[1] = k->count = nullptr;
+    k->y = k->w = k->z = nullptr;
+    k->c = nullptr;
+    k->cap = 0;
+}
+
+int ensure_ws(dil_engine* e, dil_sign_key* k, size_t n) {
+    if (n <= k->cap) return DIL_OK;
+    free_ws(k);
+    const LevelParams& P = k->P;
+    cudaError_t err = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+    A(dmalloc(&k->mu_d, n * 8));
+    A(dmalloc(&k->rhop, n * 8));
+    A(dmalloc(&k->w1p, n * (size_t)(P.k * P.w1_bytes / 8)));
+    A(dmalloc(&k->kappa, n));
+    A(dmalloc(&k->active[0], n));
+    A(dmalloc(&k->active[1], n));
+    A(dmalloc(&k->count, 4));
+    A(dmalloc(&k->y, n * (size_t)P.l * 256));
+    A(dmalloc(&k->w, n * (size_t)P.k * 256));
+    A(dmalloc(&k->z, n * (size_t)P.l * 256));
+    A(dmalloc(&k->c, n * 256));
+    if (err != cudaSuccess) {
+        free_ws(k);
+        e->last_error = std::string("sign workspace: ") + cudaGetErrorString(err);
+        return DIL_ERR_ALLOC;
+    }
+    k->cap = n;
+    return DIL_OK;
+}
+
+// the round loop; all pointers are device pointers
+int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uint64_t* d_off, size_t n, uint8_t* d_zp,
+                uint8_t* d_h, uint8_t* d_ct, uint32_t* d_att, cudaStream_t st) {
+    const LevelParams& P = k->P;
+    int rc = ensure_ws(e, k, n);
+    if (rc) return rc;
+    uint64_t launches = 0;
+    CK(dil::launch_iota(k->active[0], (uint32_t)n, st));
+    CK(dil::launch_sign_init(k->mu_d, k->rhop, k->kappa, k->seeds, k->seeds + 32, d_msgs, d_off, (uint32_t)n, st));
+    launches += 2;
+    uint32_t n_active = (uint32_t)n, rounds = 0;
+    int cur = 0;
+    while (n_active > 0) {
+        if (++rounds > 2000) {
+            e->last_error = "sign: rejection loop did not terminate";
+            return DIL_ERR_CUDA;
+        }
+        CK(cudaMemsetAsync(k->count, 0, 4, st));
+        CK(dil::launch_expand_mask(P.level, k->y, k->rhop, k->kappa, k->active[cur], n_active, st));
+        CK(dil::launch_signcore(k->w, k->a_hat, k->y, P.k, P.l, n_active, e->sm_count, st));
+        CK(dil::launch_pack_w1(P.level, reinterpret_cast<uint32_t*>(k->w1p), k->w, n_active, st));
+        CK(dil::launch_challenge(P.level, k->c, reinterpret_cast<uint64_t*>(d_ct), k->mu_d, k->w1p, k->active[cur], n_active, st));
+        CK(dil::launch_sign_tail(P.level, k->z, d_h, d_att, k->kappa, k->active[cur ^ 1], k->count, k->key_hat, k->y, k->w,
+                                 k->c, k->active[cur], n_active, e->sm_count, st));
+        launches += 5;
+        uint32_t next = 0;
+        CK(cudaMemcpyAsync(&next, k->count, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        n_active = next;
+        cur ^= 1;
+    }
+    CK(dil::launch_pack_z(P.level, d_zp, k->z, (uint32_t)n, st));
+    launches += 1;
+    e->launches += launches;
+    k->last_rounds = rounds;
+    return DIL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dil_sign_sizes(int level, size_t* z_bytes, size_t* h_bytes) {
+    if (level != 2 && level != 3 && level != 5) return DIL_ERR_ARG;
+    LevelParams P = dil::level_params(level);
+    if (z_bytes) *z_bytes = (size_t)P.l * P.z_bytes;
+    if (h_bytes) *h_bytes = (size_t)P.omega + P.k;
+    return DIL_OK;
+}
+
+int dil_sign_key_create(dil_engine_t* e, dil_sign_key_t** out, int level, const uint8_t* rho, const uint8_t* key,
+                        const uint8_t* tr, const uint8_t* s1p, const uint8_t* s2p, const uint8_t* t0p) {
+    if (!e || !out || !rho || !key || !tr || !s1p || !s2p || !t0p) return DIL_ERR_ARG;
+    if (level != 2 && level != 3 && level != 5) return DIL_ERR_ARG;
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(e->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    dil_sign_key* k = new (std::nothrow) dil_sign_key();
+    if (!k) return DIL_ERR_ALLOC;
+    k->P = dil::level_params(level);
+    k->device = e->device;
+    const LevelParams& P = k->P;
+    const int nkey = P.l + 2 * P.k;
+    // unpack s1, s2 (eta - x, 3 or 4 bits) and t0 (2^12 - x, 13 bits): decoder.v:89-143
+    std::vector<int32_t> polys((size_t)nkey * 256);
+    std::vector<uint32_t> tmp(256);
+    const int sw = P.eta == 2 ? 3 : 4;
+    for (int p = 0; p < P.l + P.k; p++) {
+        const uint8_t* src = p < P.l ? s1p + (size_t)p * P.s_bytes : s2p + (size_t)(p - P.l) * P.s_bytes;
+        bits_get(tmp.data(), src, 256, sw);
+        for (int i = 0; i < 256; i++) polys[(size_t)p * 256 + i] = P.eta - (int32_t)tmp[i];
+    }
+    for (int p = 0; p < P.k; p++) {
+        bits_get(tmp.data(), t0p + (size_t)p * 416, 256, 13);
+        for (int i = 0; i < 256; i++) polys[(size_t)(P.l + P.k + p) * 256 + i] = (1 << 12) - (int32_t)tmp[i];
+    }
+    cudaStream_t st = e->host_stream;
+    cudaError_t err = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+    uint8_t seeds[96];
+    std::memcpy(seeds, tr, 32);
+    std::memcpy(seeds + 32, key, 32);
+    std::memcpy(seeds + 64, rho, 32);
+    A(dmalloc(&k->a_hat, (size_t)P.k * P.l * 256));
+    A(dmalloc(&k->key_hat, (size_t)nkey * 256));
+    A(dmalloc(&k->seeds, 96));
+    if (err == cudaSuccess) {
+        A(cudaMemcpyAsync(k->seeds, seeds, 96, cudaMemcpyHostToDevice, st));
+        A(cudaMemcpyAsync(k->key_hat, polys.data(), polys.size() * 4, cudaMemcpyHostToDevice, st));
+        A(dil::launch_expand_a(k->a_hat, k->seeds + 64, 1, P.k, P.l, e->sm_count, st));
+        A(dil::launch_ntt_fwd(k->key_hat, k->key_hat, nkey, e->sm_count, st));
+        A(cudaStreamSynchronize(st));
+    }
+    if (err != cudaSuccess) {
+        if (k->a_hat) cudaFree(k->a_hat);
+        if (k->key_hat) cudaFree(k->key_hat);
+        if (k->seeds) cudaFree(k->seeds);
+        delete k;
+        return fail(e, err, "dil_sign_key_create");
+    }
+    e->launches += 2;
+    *out = k;
+    return DIL_OK;
+}
+
+int dil_sign_key_destroy(dil_engine_t* e, dil_sign_key_t* k) {
+    if (!k) return DIL_OK;
+    DeviceGuard dg(k->device);
+    free_ws(k);
+    void* ptrs[] = {k->a_hat, k->key_hat, k->seeds, k->msgs_d, k->zp_d, k->h_d, k->ct_d, k->off_d, k->att_d};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    (void)e;
+    delete k;
+    return DIL_OK;
+}
+
+uint32_t dil_sign_last_rounds(const dil_sign_key_t* k) { return k ? k->last_rounds : 0; }
+
+int dil_sign_batch_dev(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* d_msgs, const uint64_t* d_offsets, size_t n,
+                       uint8_t* d_z, uint8_t* d_h, uint8_t* d_ctilde, uint32_t* d_attempts, void* stream) {
+    if (!e || !k) return DIL_ERR_ARG;
+    if (n == 0) return DIL_OK;
+    if (!d_msgs || !d_offsets || !d_z || !d_h || !d_ctilde || !d_attempts || n > 0x7FFFFFFFu) return DIL_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_ctilde) & 7u) || (reinterpret_cast<uintptr_t>(d_z) & 3u)) return DIL_ERR_ARG;
+    std::lock_guard<std::mutex> g(k->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    return sign_rounds(e, k, d_msgs, d_offsets, n, d_z, d_h, d_ctilde, d_attempts, (cudaStream_t)stream);
+}
+
+int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs, const uint64_t* offsets, size_t n,
+                        uint8_t* z, uint8_t* h, uint8_t* ctilde, uint32_t* attempts) {
+    if (!e || !k) return DIL_ERR_ARG;
+    if (n == 0) return DIL_OK;
+    if (!msgs || !offsets || !z || !h || !ctilde || n > 0x7FFFFFFFu) return DIL_ERR_ARG;
+    std::lock_guard<std::mutex> g(k->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    const LevelParams& P = k->P;
+    cudaStream_t st = e->host_stream;
+    const size_t mbytes = offsets[n] > 0 ? offsets[n] : 1;
+    const size_t zb = (size_t)P.l * P.z_bytes, hb = (size_t)P.omega + P.k;
+    if (mbytes > k->msgs_cap) {
+        if (k->msgs_d) cudaFree(k->msgs_d);
+        k->msgs_d = nullptr;
+        k->msgs_cap = 0;
+        CK(dmalloc(&k->msgs_d, mbytes));
+        k->msgs_cap = mbytes;
+    }
+    if (n > k->out_cap) {
+        void* ptrs[] = {k->zp_d, k->h_d, k->ct_d, k->off_d, k->att_d};
+        for (void* p : ptrs)
+            if (p) cudaFree(p);
+        k->zp_d = k->h_d = k->ct_d = nullptr;
+        k->off_d = nullptr;
+        k->att_d = nullptr;
+        k->out_cap = 0;
+        CK(dmalloc(&k->zp_d, n * zb));
+        CK(dmalloc(&k->h_d, n * hb));
+        CK(dmalloc(&k->ct_d, n * 32));
+        CK(dmalloc(&k->off_d, n + 1));
+        CK(dmalloc(&k->att_d, n));
+        k->out_cap = n;
+    }
+    CK(cudaMemcpyAsync(k->msgs_d, msgs, offsets[n], cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(k->off_d, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    int rc = sign_rounds(e, k, k->msgs_d, k->off_d, n, k->zp_d, k->h_d, k->ct_d, k->att_d, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(z, k->zp_d, n * zb, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h, k->h_d, n * hb, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctilde, k->ct_d, n * 32, cudaMemcpyDeviceToHost, st));
+    if (attempts) CK(cudaMemcpyAsync(attempts, k->att_d, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return DIL_OK;
+}
+
+}  // extern "C"

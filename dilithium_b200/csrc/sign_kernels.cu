@@ -1,0 +1,540 @@
+// sign_kernels.cu — device side of batched deterministic signing (Dilithium round 3.1), the
+// caller of the polynomial-arithmetic hot path.
+//
+// Reference data flow (rtl_src/combined_top.v, mode 2): LOAD_MU (expandmask_ext.v:131-185:
+// mu = SHAKE256(tr||M), rho' = SHAKE256(K||mu)) -> per attempt kappa: GENY (expandmask_ext.v:98,
+// :284-294, rejection_y.v:76-99) -> NTT_Y -> MULT_A_Y -> NTTI_W (:1850-1933) -> DECOMP
+// (decomp_map1.v, coeff_decomposer.v:80-88) + c~ = SHAKE256(mu||w1) (gen_c.v:163-191) -> GEN_C /
+// SampleInBall (gen_c.v:192-222) -> NTT_C, c*s1, c*s2, c*t0, INTTs, norm checks
+// (:2011-2179, norm_check.v:84-105), MAKEHINT (makehint.v:99-102), restart on reject (:2217-2228).
+//
+// The FPGA runs one signature at a time with speculative pipelining; here every kernel
+// processes all still-active signatures of the batch for one attempt ("round"), and rejected
+// items are compacted into the next round's active list.
+#include <cuda_runtime.h>
+
+#include "dil_params.h"
+#include "keccak.cuh"
+#include "kernels.h"
+#include "ntt_core.cuh"
+
+namespace dil {
+
+// ---------------------------------------------------------------------------------------
+// S0: mu = SHAKE256(tr || M)[0:64], rho' = SHAKE256(K || mu)[0:64]; one thread per item
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) sign_init_kernel(uint64_t* __restrict__ mu, uint64_t* __restrict__ rhop,
+                                                        uint16_t* __restrict__ kappa, const uint8_t* __restrict__ tr,
+                                                        const uint8_t* __restrict__ key, const uint8_t* __restrict__ msgs,
+                                                        const uint64_t* __restrict__ offsets, uint32_t n) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint8_t* m = msgs + offsets[t];
+    const size_t mlen = (size_t)(offsets[t + 1] - offsets[t]);
+    uint64_t A[25];
+    shake256_absorb_lanes(A, 32 + mlen, [&](size_t idx) -> uint64_t {
+        if (idx < 4) return load_lane_bytes(tr, idx * 8, 32);
+        return load_lane_bytes(m, (idx - 4) * 8, mlen);
+    });
+    uint64_t muv[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        muv[i] = A[i];
+        mu[(size_t)t * 8 + i] = A[i];
+    }
+    // K (4 lanes) || mu (8 lanes) = 96 bytes: one block
+#pragma unroll
+    for (int i = 0; i < 25; i++) A[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) A[i] = load_lane_bytes(key, i * 8, 32);
+#pragma unroll
+    for (int i = 0; i < 8; i++) A[4 + i] = muv[i];
+    A[12] = 0x1F;
+    A[16] = 0x80ULL << 56;
+    keccak_f1600(A);
+#pragma unroll
+    for (int i = 0; i < 8; i++) rhop[(size_t)t * 8 + i] = A[i];
+    kappa[t] = 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// S1: ExpandMask.  One thread per polynomial y[a][j] = SHAKE256(rho' || u16le(l*kappa + j)),
+// squeezed into a per-warp shared staging area, then the warp unpacks the 32 polynomials
+// cooperatively so that HBM sees coalesced 1 KiB polynomial writes.
+// ---------------------------------------------------------------------------------------
+template <int L, int GAMMA1_BITS>
+__global__ void __launch_bounds__(128) expand_mask_kernel(int32_t* __restrict__ y, const uint64_t* __restrict__ rhop,
+                                                          const uint16_t* __restrict__ kappa, const uint32_t* __restrict__ active,
+                                                          uint32_t n_active) {
+    constexpr int ZB = 32 * (GAMMA1_BITS + 1);       // packed bytes per poly: 576 / 640
+    constexpr int ROW = ZB + 16;                      // row stride in shared memory
+    constexpr int LANES = ZB / 8;                     // 72 / 80 lanes of output needed
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* stage = sm_raw + (size_t)warp * 32 * ROW;
+    const uint32_t n_polys = n_active * L;
+    const uint32_t wbase = (blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+    const uint32_t gid = wbase + lane;
+    if (wbase >= n_polys) return;
+    if (gid < n_polys) {
+        const uint32_t a = gid / L, j = gid % L;
+        const uint32_t item = active[a];
+        const uint32_t nonce = (uint32_t)L * kappa[item] + j;
+        uint64_t A[25];
+#pragma unroll
+        for (int i = 0; i < 25; i++) A[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) A[i] = rhop[(size_t)item * 8 + i];
+        A[8] = (uint64_t)(nonce & 0xFFFF) | (0x1FULL << 16);
+        A[16] = 0x80ULL << 56;
+        uint64_t* row = reinterpret_cast<uint64_t*>(stage + (size_t)lane * ROW);
+#pragma unroll
+        for (int blk = 0; blk < (LANES + 16) / 17; blk++) {
+            keccak_f1600(A);
+#pragma unroll
+            for (int i = 0; i < 17; i++)
+                if (blk * 17 + i < LANES) row[blk * 17 + i] = A[i];
+        }
+    }
+    __syncwarp();
+    // cooperative unpack: lane handles coefficients 8*lane .. 8*lane+7 of polynomial p
+    constexpr int BITS = GAMMA1_BITS + 1;             // 18 / 20
+    constexpr int CHUNK = BITS;                       // bytes per 8 coefficients
+    constexpr int32_t G1 = 1 << GAMMA1_BITS;
+    for (int p = 0; p < 32 && wbase + p < n_polys; p++) {
+        const unsigned char* src = stage + (size_t)p * ROW + lane * CHUNK;
+        uint64_t lo, mid;
+        uint32_t hi;
+        if constexpr (BITS == 18) {  // 18 bytes, 2-byte aligned
+            const uint16_t* h = reinterpret_cast<const uint16_t*>(src);
+            lo = (uint64_t)h[0] | ((uint64_t)h[1] << 16) | ((uint64_t)h[2] << 32) | ((uint64_t)h[3] << 48);
+            mid = (uint64_t)h[4] | ((uint64_t)h[5] << 16) | ((uint64_t)h[6] << 32) | ((uint64_t)h[7] << 48);
+            hi = h[8];
+        } else {                     // 20 bytes, 4-byte aligned
+            const uint32_t* h = reinterpret_cast<const uint32_t*>(src);
+            lo = (uint64_t)h[0] | ((uint64_t)h[1] << 32);
+            mid = (uint64_t)h[2] | ((uint64_t)h[3] << 32);
+            hi = h[4];
+        }
+        int32_t v[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int pos = c * BITS;
+            uint64_t bits;
+            if (pos + BITS <= 64) bits = lo >> pos;
+            else if (pos < 64) bits = (lo >> pos) | (mid << (64 - pos));
+            else if (pos + BITS <= 128) bits = mid >> (pos - 64);
+            else if (pos < 128) bits = (mid >> (pos - 64)) | ((uint64_t)hi << (128 - pos));
+            else bits = hi >> (pos - 128);
+            v[c] = G1 - (int32_t)((uint32_t)bits & ((1u << BITS) - 1));
+        }
+        int4* dst = reinterpret_cast<int4*>(y + (size_t)(wbase + p) * N) + 2 * lane;
+        dst[0] = make_int4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_int4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Decompose (decomp_map1.v / coeff_decomposer.v:80-88): a = a1*2*gamma2 + a0,
+// -gamma2 < a0 <= gamma2, with the wrap-around row mapped to a1 = 0.
+// ---------------------------------------------------------------------------------------
+template <int32_t GAMMA2>
+__device__ __forceinline__ void decompose(int32_t a, int32_t& a1, int32_t& a0) {
+    int32_t t = (a + 127) >> 7;
+    if constexpr (GAMMA2 == (Q_I - 1) / 32) {
+        t = (t * 1025 + (1 << 21)) >> 22;
+        t &= 15;
+    } else {
+        t = (t * 11275 + (1 << 23)) >> 24;
+        t ^= ((43 - t) >> 31) & t;
+    }
+    a1 = t;
+    a0 = a - t * 2 * GAMMA2;
+    a0 -= (((Q_I - 1) / 2 - a0) >> 31) & Q_I;
+}
+
+// S3: w1 = HighBits(w), bit-packed (encoder.v:96-133: 6 bits for gamma2=(Q-1)/88, else 4).
+// One thread per 16 coefficients -> 12 or 8 bytes.
+template <int32_t GAMMA2>
+__global__ void __launch_bounds__(256) pack_w1_kernel(uint32_t* __restrict__ w1p, const int32_t* __restrict__ w, size_t n_groups) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_groups) return;
+    const int4* src = reinterpret_cast<const int4*>(w) + t * 4;
+    int32_t h[16];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        int4 v = src[q];
+        int32_t a0;
+        decompose<GAMMA2>(v.x, h[4 * q + 0], a0);
+        decompose<GAMMA2>(v.y, h[4 * q + 1], a0);
+        decompose<GAMMA2>(v.z, h[4 * q + 2], a0);
+        decompose<GAMMA2>(v.w, h[4 * q + 3], a0);
+    }
+    if constexpr (GAMMA2 == (Q_I - 1) / 32) {
+        uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            o0 |= (uint32_t)h[c] << (4 * c);
+            o1 |= (uint32_t)h[8 + c] << (4 * c);
+        }
+        w1p[t * 2] = o0;
+        w1p[t * 2 + 1] = o1;
+    } else {
+        uint64_t lo = 0;
+        uint32_t hi = 0;
+#pragma unroll
+        for (int c = 0; c < 10; c++) lo |= (uint64_t)h[c] << (6 * c);           // bits 0..59
+        lo |= (uint64_t)h[10] << 60;                                              // bits 60..65
+        hi = ((uint32_t)h[10] >> 4) | ((uint32_t)h[11] << 2) | ((uint32_t)h[12] << 8) | ((uint32_t)h[13] << 14) |
+             ((uint32_t)h[14] << 20) | ((uint32_t)h[15] << 26);
+        w1p[t * 3] = (uint32_t)lo;
+        w1p[t * 3 + 1] = (uint32_t)(lo >> 32);
+        w1p[t * 3 + 2] = hi;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// S4: c~ = SHAKE256(mu || w1_packed)[0:32]; c = SampleInBall(c~) (gen_c.v:163-222, :317-343).
+// One thread per active item; c is written as 256 int8 in {-1,0,1}.
+// ---------------------------------------------------------------------------------------
+template <int K, int W1_BYTES, int TAU>
+__global__ void __launch_bounds__(128) challenge_kernel(int8_t* __restrict__ c_out, uint64_t* __restrict__ ctilde,
+                                                        const uint64_t* __restrict__ mu, const uint64_t* __restrict__ w1p,
+                                                        const uint32_t* __restrict__ active, uint32_t n_active) {
+    uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_active) return;
+    const uint32_t item = active[a];
+    constexpr int W1_LANES = K * W1_BYTES / 8;
+    const uint64_t* m = mu + (size_t)item * 8;
+    const uint64_t* w = w1p + (size_t)a * W1_LANES;
+    uint64_t A[25];
+    shake256_absorb_lanes(A, 64 + K * W1_BYTES, [&](size_t idx) -> uint64_t { return idx < 8 ? m[idx] : w[idx - 8]; });
+    uint64_t ct[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        ct[i] = A[i];
+        ctilde[(size_t)item * 4 + i] = A[i];
+    }
+    // SampleInBall: SHAKE256(c~): first 8 bytes = sign bits, then rejection bytes
+#pragma unroll
+    for (int i = 0; i < 25; i++) A[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) A[i] = ct[i];
+    A[4] = 0x1F;
+    A[16] = 0x80ULL << 56;
+    keccak_f1600(A);
+    uint64_t signs = A[0];
+    __align__(8) uint8_t buf[136];
+    __align__(4) int8_t c[N];
+#pragma unroll
+    for (int i = 0; i < 17; i++) reinterpret_cast<uint64_t*>(buf)[i] = A[i];
+    for (int i = 0; i < N; i++) c[i] = 0;
+    int pos = 8;
+    for (int i = N - TAU; i < N; i++) {
+        int b;
+        do {
+            if (pos == 136) {
+                keccak_f1600(A);
+#pragma unroll
+                for (int q = 0; q < 17; q++) reinterpret_cast<uint64_t*>(buf)[q] = A[q];
+                pos = 0;
+            }
+            b = buf[pos++];
+        } while (b > i);
+        c[i] = c[b];
+        c[b] = (signs & 1) ? -1 : 1;
+        signs >>= 1;
+    }
+    uint32_t* dst = reinterpret_cast<uint32_t*>(c_out + (size_t)a * N);
+    for (int i = 0; i < N / 4; i++) dst[i] = reinterpret_cast<const uint32_t*>(c)[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// S5: signature tail, one warp per active item.
+//   c_hat = NTT(c); z = y + INTT(c_hat o s1_hat); ||z|| < gamma1 - beta
+//   r0 = LowBits(w) - INTT(c_hat o s2_hat); ||r0|| < gamma2 - beta
+//   ct0 = INTT(c_hat o t0_hat); ||ct0|| < gamma2; h = MakeHint(r0 + ct0, HighBits(w)); #h <= omega
+// Key polynomials (s1_hat | s2_hat | t0_hat, NTT domain) live in shared memory per persistent CTA.
+// Rejected items are appended to the next round's active list.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t centre(uint32_t a) { return (int32_t)a - (int32_t)((a > (Q - 1) / 2) ? Q : 0); }
+
+template <int K, int L, int32_t GAMMA1, int32_t GAMMA2, int BETA, int OMEGA, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) sign_tail_kernel(
+    int32_t* __restrict__ z_out, uint8_t* __restrict__ h_out, uint32_t* __restrict__ attempts, uint16_t* __restrict__ kappa,
+    uint32_t* __restrict__ next_active, uint32_t* __restrict__ next_count, const int32_t* __restrict__ key_hat,
+    const int32_t* __restrict__ y, const int32_t* __restrict__ w, const int8_t* __restrict__ c,
+    const uint32_t* __restrict__ active, uint32_t n_active) {
+    extern __shared__ __align__(16) uint32_t sm_words[];
+    constexpr int NKEY = L + 2 * K;
+    uint32_t* key_sm = sm_words;                       // NKEY * 256
+    uint32_t* scr_all = sm_words + NKEY * N;           // WARPS * SCRATCH_WORDS
+    uint32_t* hm_all = scr_all + WARPS * SCRATCH_WORDS;  // WARPS * K * 8 hint masks
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t = threadIdx.x; t < NKEY * (N / 4); t += blockDim.x) {
+        int4 q = __ldg(reinterpret_cast<const int4*>(key_hat) + t);
+        reinterpret_cast<uint4*>(key_sm)[t] = make_uint4(canon_signed(q.x), canon_signed(q.y), canon_signed(q.z), canon_signed(q.w));
+    }
+    __syncthreads();
+    uint32_t* scr = scr_all + warp * SCRATCH_WORDS;
+    uint32_t* hm = hm_all + warp * K * 8;
+    FwdTw ftw;
+    InvTw itw;
+    load_inv_tw(itw, &TW_INV, lane);
+
+    for (uint32_t a = blockIdx.x * WARPS + warp; a < n_active; a += gridDim.x * WARPS) {
+        const uint32_t item = active[a];
+        // c_hat in layout C
+        uint32_t ch[8];
+        {
+            load_fwd_tw(ftw, &TW_FWD, lane);
+            const int8_t* cp = c + (size_t)a * N + lane;
+#pragma unroll
+            for (int r = 0; r < 8; r++) ch[r] = (uint32_t)(int32_t)cp[32 * r];
+            ntt_fwd_warp(ch, scr, ftw, lane);
+            __syncwarp();
+        }
+        auto mul_inv = [&](uint32_t (&x)[8], int p) {   // x = INTT(c_hat o key[p]) in layout A
+            const uint4* kp = reinterpret_cast<const uint4*>(key_sm + p * N) + lane;
+            uint4 lo = kp[0], hi = kp[32];
+            x[0] = mul_full(ch[0], lo.x); x[1] = mul_full(ch[1], lo.y); x[2] = mul_full(ch[2], lo.z); x[3] = mul_full(ch[3], lo.w);
+            x[4] = mul_full(ch[4], hi.x); x[5] = mul_full(ch[5], hi.y); x[6] = mul_full(ch[6], hi.z); x[7] = mul_full(ch[7], hi.w);
+            ntt_inv_warp(x, scr, itw, lane);
+            __syncwarp();
+        };
+        bool bad = false;
+        // z = y + c*s1
+        int32_t* zo = z_out + (size_t)item * L * N + lane;
+        const int32_t* yi = y + (size_t)a * L * N + lane;
+#pragma unroll 1
+        for (int j = 0; j < L; j++) {
+            uint32_t x[8];
+            mul_inv(x, j);
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                int32_t z = yi[j * N + 32 * r] + centre(x[r]);
+                bad |= (z >= GAMMA1 - BETA) || (z <= -(GAMMA1 - BETA));
+                zo[j * N + 32 * r] = z;
+            }
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        uint32_t nh = 0;
+        if (!bad) {
+            const int32_t* wi = w + (size_t)a * K * N + lane;
+#pragma unroll 1
+            for (int i = 0; i < K; i++) {
+                uint32_t x[8];
+                int32_t r0[8], w1[8];
+                mul_inv(x, L + i);                      // c*s2_i
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    int32_t a0;
+                    decompose<GAMMA2>(wi[i * N + 32 * r], w1[r], a0);
+                    r0[r] = a0 - centre(x[r]);
+                    bad |= (r0[r] >= GAMMA2 - BETA) || (r0[r] <= -(GAMMA2 - BETA));
+                }
+                mul_inv(x, L + K + i);                  // c*t0_i
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    int32_t ct0 = centre(x[r]);
+                    bad |= (ct0 >= GAMMA2) || (ct0 <= -GAMMA2);
+                    int32_t v = r0[r] + ct0;
+                    bool hint = (v > GAMMA2) || (v < -GAMMA2) || (v == -GAMMA2 && w1[r] != 0);
+                    uint32_t mask = __ballot_sync(0xffffffffu, hint);
+                    nh += __popc(mask);
+                    if (lane == 0) hm[i * 8 + r] = mask;
+                }
+            }
+            bad = __any_sync(0xffffffffu, bad) || nh > OMEGA;
+        }
+        __syncwarp();
+        if (!bad) {
+            // hint encoding: omega position bytes (ascending inside each polynomial), then k running counts
+            uint8_t* ho = h_out + (size_t)item * (OMEGA + K);
+            for (int t = lane; t < OMEGA + K; t += 32) ho[t] = 0;
+            __syncwarp();
+            uint32_t run = 0;
+            for (int i = 0; i < K; i++) {
+                for (int r = 0; r < 8; r++) {
+                    uint32_t mask = hm[i * 8 + r];
+                    if ((mask >> lane) & 1u) ho[run + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)(32 * r + lane);
+                    run += __popc(mask);
+                }
+                if (lane == 0) ho[OMEGA + i] = (uint8_t)run;
+            }
+            if (lane == 0) attempts[item] = (uint32_t)kappa[item] + 1;
+        } else if (lane == 0) {
+            kappa[item] += 1;
+            next_active[atomicAdd(next_count, 1u)] = item;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// final packing of z (encoder.v:96-133: gamma1 - z, 18 or 20 bits); thread per 8 coefficients
+// ---------------------------------------------------------------------------------------
+template <int GAMMA1_BITS>
+__global__ void __launch_bounds__(256) pack_z_kernel(uint8_t* __restrict__ zp, const int32_t* __restrict__ z, size_t n_groups) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_groups) return;
+    constexpr int BITS = GAMMA1_BITS + 1;
+    const int4* src = reinterpret_cast<const int4*>(z) + t * 2;
+    int4 a = src[0], b = src[1];
+    const int32_t G1 = 1 << GAMMA1_BITS;
+    uint32_t v[8] = {(uint32_t)(G1 - a.x), (uint32_t)(G1 - a.y), (uint32_t)(G1 - a.z), (uint32_t)(G1 - a.w),
+                     (uint32_t)(G1 - b.x), (uint32_t)(G1 - b.y), (uint32_t)(G1 - b.z), (uint32_t)(G1 - b.w)};
+    uint64_t lo = 0, mid = 0;
+    uint32_t hi = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const int pos = c * BITS;
+        uint64_t x = v[c] & ((1u << BITS) - 1);
+        if (pos < 64) {
+            lo |= x << pos;
+            if (pos + BITS > 64) mid |= x >> (64 - pos);
+        } else if (pos < 128) {
+            mid |= x << (pos - 64);
+            if (pos + BITS > 128) hi |= (uint32_t)(x >> (128 - pos));
+        } else {
+            hi |= (uint32_t)x << (pos - 128);
+        }
+    }
+    uint8_t* dst = zp + t * BITS;
+    if constexpr (BITS == 18) {
+        uint16_t* d = reinterpret_cast<uint16_t*>(dst);
+#pragma unroll
+        for (int q = 0; q < 4; q++) d[q] = (uint16_t)(lo >> (16 * q));
+#pragma unroll
+        for (int q = 0; q < 4; q++) d[4 + q] = (uint16_t)(mid >> (16 * q));
+        d[8] = (uint16_t)hi;
+    } else {
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+        d[0] = (uint32_t)lo; d[1] = (uint32_t)(lo >> 32); d[2] = (uint32_t)mid; d[3] = (uint32_t)(mid >> 32); d[4] = hi;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------
+cudaError_t launch_sign_init(uint64_t* mu, uint64_t* rhop, uint16_t* kappa, const uint8_t* tr, const uint8_t* key,
+                             const uint8_t* msgs, const uint64_t* offsets, uint32_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    sign_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(mu, rhop, kappa, tr, key, msgs, offsets, n);
+    return cudaGetLastError();
+}
+
+template <int L, int G1B>
+static cudaError_t launch_expand_mask_t(int32_t* y, const uint64_t* rhop, const uint16_t* kappa, const uint32_t* active,
+                                        uint32_t n_active, cudaStream_t st) {
+    constexpr int ROW = 32 * (G1B + 1) + 16;
+    constexpr size_t smem = (size_t)4 * 32 * ROW;
+    auto kern = expand_mask_kernel<L, G1B>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    uint32_t n_polys = n_active * L;
+    kern<<<(n_polys + 127) / 128, 128, smem, st>>>(y, rhop, kappa, active, n_active);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_expand_mask(int level, int32_t* y, const uint64_t* rhop, const uint16_t* kappa, const uint32_t* active,
+                               uint32_t n_active, cudaStream_t st) {
+    if (n_active == 0) return cudaSuccess;
+    switch (level) {
+        case 2: return launch_expand_mask_t<4, 17>(y, rhop, kappa, active, n_active, st);
+        case 3: return launch_expand_mask_t<5, 19>(y, rhop, kappa, active, n_active, st);
+        case 5: return launch_expand_mask_t<7, 19>(y, rhop, kappa, active, n_active, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_pack_w1(int level, uint32_t* w1p, const int32_t* w, uint32_t n_active, cudaStream_t st) {
+    if (n_active == 0) return cudaSuccess;
+    const LevelParams P = level_params(level);
+    size_t n_groups = (size_t)n_active * P.k * (N / 16);
+    unsigned grid = (unsigned)((n_groups + 255) / 256);
+    if (level == 2) pack_w1_kernel<(Q_I - 1) / 88><<<grid, 256, 0, st>>>(w1p, w, n_groups);
+    else pack_w1_kernel<(Q_I - 1) / 32><<<grid, 256, 0, st>>>(w1p, w, n_groups);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_challenge(int level, int8_t* c, uint64_t* ctilde, const uint64_t* mu, const uint64_t* w1p,
+                             const uint32_t* active, uint32_t n_active, cudaStream_t st) {
+    if (n_active == 0) return cudaSuccess;
+    unsigned grid = (n_active + 127) / 128;
+    switch (level) {
+        case 2: challenge_kernel<4, 192, 39><<<grid, 128, 0, st>>>(c, ctilde, mu, w1p, active, n_active); break;
+        case 3: challenge_kernel<6, 128, 49><<<grid, 128, 0, st>>>(c, ctilde, mu, w1p, active, n_active); break;
+        case 5: challenge_kernel<8, 128, 60><<<grid, 128, 0, st>>>(c, ctilde, mu, w1p, active, n_active); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA>
+static cudaError_t launch_sign_tail_t(int32_t* z_out, uint8_t* h_out, uint32_t* attempts, uint16_t* kappa,
+                                      uint32_t* next_active, uint32_t* next_count, const int32_t* key_hat, const int32_t* y,
+                                      const int32_t* w, const int8_t* c, const uint32_t* active, uint32_t n_active,
+                                      int sm_count, cudaStream_t st) {
+    constexpr int WARPS = 8;
+    constexpr size_t smem = (size_t)((L + 2 * K) * N + WARPS * SCRATCH_WORDS + WARPS * K * 8) * 4;
+    auto kern = sign_tail_kernel<K, L, G1, G2, BETA, OMEGA, WARPS>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    unsigned want = (n_active + WARPS - 1) / WARPS;
+    unsigned cap = (unsigned)sm_count * 2;
+    kern<<<want < cap ? want : cap, WARPS * 32, smem, st>>>(z_out, h_out, attempts, kappa, next_active, next_count, key_hat, y,
+                                                           w, c, active, n_active);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sign_tail(int level, int32_t* z_out, uint8_t* h_out, uint32_t* attempts, uint16_t* kappa,
+                             uint32_t* next_active, uint32_t* next_count, const int32_t* key_hat, const int32_t* y,
+                             const int32_t* w, const int8_t* c, const uint32_t* active, uint32_t n_active, int sm_count,
+                             cudaStream_t st) {
+    if (n_active == 0) return cudaSuccess;
+    switch (level) {
+        case 2:
+            return launch_sign_tail_t<4, 4, 1 << 17, (Q_I - 1) / 88, 78, 80>(z_out, h_out, attempts, kappa, next_active, next_count,
+                                                                            key_hat, y, w, c, active, n_active, sm_count, st);
+        case 3:
+            return launch_sign_tail_t<6, 5, 1 << 19, (Q_I - 1) / 32, 196, 55>(z_out, h_out, attempts, kappa, next_active, next_count,
+                                                                             key_hat, y, w, c, active, n_active, sm_count, st);
+        case 5:
+            return launch_sign_tail_t<8, 7, 1 << 19, (Q_I - 1) / 32, 120, 75>(z_out, h_out, attempts, kappa, next_active, next_count,
+                                                                             key_hat, y, w, c, active, n_active, sm_count, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_pack_z(int level, uint8_t* zp, const int32_t* z, uint32_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const LevelParams P = level_params(level);
+    size_t n_groups = (size_t)n * P.l * (N / 8);
+    unsigned grid = (unsigned)((n_groups + 255) / 256);
+    if (P.gamma1_bits == 17) pack_z_kernel<17><<<grid, 256, 0, st>>>(zp, z, n_groups);
+    else pack_z_kernel<19><<<grid, 256, 0, st>>>(zp, z, n_groups);
+    return cudaGetLastError();
+}
+
+}  // namespace dil
+
+namespace dil {
+__global__ void iota_kernel(uint32_t* dst, uint32_t n) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) dst[t] = t;
+}
+cudaError_t launch_iota(uint32_t* dst, uint32_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    iota_kernel<<<(n + 255) / 256, 256, 0, st>>>(dst, n);
+    return cudaGetLastError();
+}
+}  // namespace dil

@@ -223,3 +223,61 @@ class Engine:
                                          y.ctypes.data_as(ctypes.c_void_p), k, l, batch)
         self._check(rc, "dil_signcore_host")
         return w
+
+
+class SignKey:
+    """Expanded signing key on the device (ExpandA + NTT of s1, s2, t0 done once; LOAD_RHO / NTT_S1 /
+    NTT_S2 / NTT_T0 of combined_top.v:1560-1767).  Inputs are bit-packed exactly as the reference's
+    KAT files / rtl_tb/tb_sign_top.v:171-284 feed them."""
+
+    def __init__(self, engine, level, rho, key, tr, s1_packed, s2_packed, t0_packed):
+        self.engine, self.level = engine, int(level)
+        lib = engine._lib
+        zb, hb = ctypes.c_size_t(), ctypes.c_size_t()
+        engine._check(lib.dil_sign_sizes(self.level, ctypes.byref(zb), ctypes.byref(hb)), "dil_sign_sizes")
+        self.z_bytes, self.h_bytes = zb.value, hb.value
+        bufs = [np.ascontiguousarray(x, dtype=np.uint8) for x in (rho, key, tr, s1_packed, s2_packed, t0_packed)]
+        h = ctypes.c_void_p()
+        rc = lib.dil_sign_key_create(engine._h, ctypes.byref(h), self.level, *[b.ctypes.data_as(ctypes.c_void_p) for b in bufs])
+        engine._check(rc, "dil_sign_key_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.engine, "_h", None):
+            self.engine._lib.dil_sign_key_destroy(self.engine._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def last_rounds(self):
+        return int(self.engine._lib.dil_sign_last_rounds(self._h))
+
+    def sign(self, msgs):
+        """Sign a list of byte strings (host path, dil_sign_batch_host).
+        Returns (z[n, z_bytes], h[n, h_bytes], ctilde[n, 32], attempts[n])."""
+        n = len(msgs)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(m) for m in msgs])
+        blob = np.frombuffer(b"".join(msgs), dtype=np.uint8).copy() if off[-1] else np.zeros(1, np.uint8)
+        z = np.empty((n, self.z_bytes), dtype=np.uint8)
+        h = np.empty((n, self.h_bytes), dtype=np.uint8)
+        c = np.empty((n, 32), dtype=np.uint8)
+        att = np.zeros(n, dtype=np.uint32)
+        P = ctypes.c_void_p
+        rc = self.engine._lib.dil_sign_batch_host(self.engine._h, self._h, blob.ctypes.data_as(P), off.ctypes.data_as(P), n,
+                                                  z.ctypes.data_as(P), h.ctypes.data_as(P), c.ctypes.data_as(P), att.ctypes.data_as(P))
+        self.engine._check(rc, "dil_sign_batch_host")
+        return z, h, c, att
+
+    def sign_dev(self, d_msgs, d_offsets, n, d_z, d_h, d_c, d_att):
+        """Device-resident variant (torch CUDA uint8 / int64-as-uint64 / int32 tensors) on torch's current stream."""
+        rc = self.engine._lib.dil_sign_batch_dev(self.engine._h, self._h, ctypes.c_void_p(d_msgs.data_ptr()),
+                                                 ctypes.c_void_p(d_offsets.data_ptr()), n, ctypes.c_void_p(d_z.data_ptr()),
+                                                 ctypes.c_void_p(d_h.data_ptr()), ctypes.c_void_p(d_c.data_ptr()),
+                                                 ctypes.c_void_p(d_att.data_ptr()), self.engine._stream())
+        self.engine._check(rc, "dil_sign_batch_dev")

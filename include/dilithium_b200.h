@@ -118,6 +118,25 @@ int dil_matvec_expand_host(dil_engine_t *e, int32_t *w, const uint8_t *rho, cons
 int dil_signcore_host(dil_engine_t *e, int32_t *w, const int32_t *a_hat, const int32_t *y,
                       int k, int l, size_t batch);
 
+/* ---- batched deterministic signing (the caller of the hot path) ----
+ * Replaces, for a whole batch, the sign mode of the reference's top level
+ * (rtl_src/combined_top.v:31-41 mode 2, FSMs :1535-2229) with the I/O of rtl_tb/tb_sign_top.v:171-335:
+ * inputs rho, tr, K, s1, s2, t0 (bit-packed exactly as the KAT files / decoder.v:89-143) and
+ * messages; outputs per signature z (l * 576|640 bytes, gamma1 - z packed), h (omega + k bytes),
+ * c~ (32 bytes) and the number of attempts.  Round-3.1, deterministic (rho' = SHAKE256(K || mu)).
+ * msgs = all messages concatenated; offsets[i]..offsets[i+1] delimit message i (n+1 entries). */
+typedef struct dil_sign_key dil_sign_key_t;
+int dil_sign_sizes(int level, size_t *z_bytes, size_t *h_bytes);
+int dil_sign_key_create(dil_engine_t *e, dil_sign_key_t **out, int level, const uint8_t *rho, const uint8_t *key,
+                        const uint8_t *tr, const uint8_t *s1_packed, const uint8_t *s2_packed, const uint8_t *t0_packed);
+int dil_sign_key_destroy(dil_engine_t *e, dil_sign_key_t *k);
+int dil_sign_batch_host(dil_engine_t *e, dil_sign_key_t *k, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                        uint8_t *z, uint8_t *h, uint8_t *ctilde, uint32_t *attempts);
+/* device pointers (d_ctilde 8-byte aligned); synchronises the stream once per rejection round */
+int dil_sign_batch_dev(dil_engine_t *e, dil_sign_key_t *k, const uint8_t *d_msgs, const uint64_t *d_offsets, size_t n,
+                       uint8_t *d_z, uint8_t *d_h, uint8_t *d_ctilde, uint32_t *d_attempts, void *stream);
+uint32_t dil_sign_last_rounds(const dil_sign_key_t *k);   /* rejection rounds of the last batch */
+
 /* ---- north_star aliases (plain domain, identical to the above) ---- */
 int dil_invntt_tomont_dev(dil_engine_t *e, int32_t *dst, const int32_t *src, size_t n_polys, void *stream);
 int dil_poly_pointwise_dev(dil_engine_t *e, int32_t *c, const int32_t *a, const int32_t *b, size_t n_polys, void *stream);
