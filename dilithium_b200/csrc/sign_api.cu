@@ -30,8 +30,11 @@ struct dil_sign_key {
     uint64_t *mu_d = nullptr, *rhop = nullptr, *w1p = nullptr;
     uint16_t* kappa = nullptr;
     uint32_t *active[2] = {nullptr, nullptr}, *count = nullptr;
-    int32_t *y = nullptr, *w = nullptr, *z = nullptr;
+    int32_t *y = nullptr, *w = nullptr;
     int8_t* c = nullptr;
+    uint8_t *h_slot = nullptr, *accepted = nullptr;
+    uint64_t* ct_slot = nullptr;
+    size_t slots = 0;            // slot capacity of y/w/c/w1p/h_slot/ct_slot/accepted
     // host-variant staging
     uint8_t *msgs_d = nullptr, *zp_d = nullptr, *h_d = nullptr, *ct_d = nullptr;
     uint64_t* off_d = nullptr;
@@ -67,16 +70,25 @@ cudaError_t dmalloc(T** p, size_t count) {
     return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
 }
 
+// Straggler speculation: once fewer than SPEC_SLOT_TARGET items are still active the GPU is no
+// longer saturated by distinct items, so each remaining item tries up to SPEC_MAX consecutive kappa
+// values per round in parallel slots; the smallest accepted kappa wins, which is exactly the
+// sequential result of combined_top.v:2217-2228 (restart with the next kappa).
+constexpr size_t SPEC_SLOT_TARGET = 32768;
+constexpr size_t SPEC_MAX = 16;
+
 void free_ws(dil_sign_key* k) {
-    void* ptrs[] = {k->mu_d, k->rhop, k->w1p, k->kappa, k->active[0], k->active[1], k->count, k->y, k->w, k->z, k->c};
+    void* ptrs[] = {k->mu_d, k->rhop, k->w1p, k->kappa, k->active[0], k->active[1], k->count, k->y, k->w, k->c,
+                    k->h_slot, k->accepted, k->ct_slot};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    k->mu_d = k->rhop = k->w1p = nullptr;
+    k->mu_d = k->rhop = k->w1p = k->ct_slot = nullptr;
     k->kappa = nullptr;
     k->active[0] = k->active[1] = k->count = nullptr;
-    k->y = k->w = k->z = nullptr;
+    k->y = k->w = nullptr;
     k->c = nullptr;
-    k->cap = 0;
+    k->h_slot = k->accepted = nullptr;
+    k->cap = k->slots = 0;
 }
 
 int ensure_ws(dil_engine* e, dil_sign_key* k, size_t n) {
@@ -85,23 +97,28 @@ int ensure_ws(dil_engine* e, dil_sign_key* k, size_t n) {
     const LevelParams& P = k->P;
     cudaError_t err = cudaSuccess;
     auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+    // slots: every item of a round owns `spec` speculative attempt slots (spec = 1 in the big rounds)
+    const size_t slots = n > SPEC_SLOT_TARGET ? n : (n * SPEC_MAX < SPEC_SLOT_TARGET ? n * SPEC_MAX : SPEC_SLOT_TARGET);
     A(dmalloc(&k->mu_d, n * 8));
     A(dmalloc(&k->rhop, n * 8));
-    A(dmalloc(&k->w1p, n * (size_t)(P.k * P.w1_bytes / 8)));
     A(dmalloc(&k->kappa, n));
     A(dmalloc(&k->active[0], n));
     A(dmalloc(&k->active[1], n));
     A(dmalloc(&k->count, 4));
-    A(dmalloc(&k->y, n * (size_t)P.l * 256));
-    A(dmalloc(&k->w, n * (size_t)P.k * 256));
-    A(dmalloc(&k->z, n * (size_t)P.l * 256));
-    A(dmalloc(&k->c, n * 256));
+    A(dmalloc(&k->w1p, slots * (size_t)(P.k * P.w1_bytes / 8)));
+    A(dmalloc(&k->y, slots * (size_t)P.l * 256));
+    A(dmalloc(&k->w, slots * (size_t)P.k * 256));
+    A(dmalloc(&k->c, slots * 256));
+    A(dmalloc(&k->h_slot, slots * (size_t)(P.omega + P.k)));
+    A(dmalloc(&k->accepted, slots));
+    A(dmalloc(&k->ct_slot, slots * 4));
     if (err != cudaSuccess) {
         free_ws(k);
         e->last_error = std::string("sign workspace: ") + cudaGetErrorString(err);
         return DIL_ERR_ALLOC;
     }
     k->cap = n;
+    k->slots = slots;
     return DIL_OK;
 }
 
@@ -118,26 +135,31 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
     uint32_t n_active = (uint32_t)n, rounds = 0;
     int cur = 0;
     while (n_active > 0) {
-        if (++rounds > 2000) {
+        if (++rounds > 4000) {
             e->last_error = "sign: rejection loop did not terminate";
             return DIL_ERR_CUDA;
         }
+        size_t spec = 1;
+        if (n_active < SPEC_SLOT_TARGET) {
+            size_t room = (k->slots < SPEC_SLOT_TARGET ? k->slots : SPEC_SLOT_TARGET) / n_active;
+            spec = room < 1 ? 1 : (room > SPEC_MAX ? SPEC_MAX : room);
+        }
+        const uint32_t n_slots = (uint32_t)(n_active * spec);
         CK(cudaMemsetAsync(k->count, 0, 4, st));
-        CK(dil::launch_expand_mask(P.level, k->y, k->rhop, k->kappa, k->active[cur], n_active, st));
-        CK(dil::launch_signcore(k->w, k->a_hat, k->y, P.k, P.l, n_active, e->sm_count, st));
-        CK(dil::launch_pack_w1(P.level, reinterpret_cast<uint32_t*>(k->w1p), k->w, n_active, st));
-        CK(dil::launch_challenge(P.level, k->c, reinterpret_cast<uint64_t*>(d_ct), k->mu_d, k->w1p, k->active[cur], n_active, st));
-        CK(dil::launch_sign_tail(P.level, k->z, d_h, d_att, k->kappa, k->active[cur ^ 1], k->count, k->key_hat, k->y, k->w,
-                                 k->c, k->active[cur], n_active, e->sm_count, st));
-        launches += 5;
+        CK(dil::launch_expand_mask(P.level, k->y, k->rhop, k->kappa, k->active[cur], n_slots, (uint32_t)spec, st));
+        CK(dil::launch_signcore(k->w, k->a_hat, k->y, P.k, P.l, n_slots, e->sm_count, st));
+        CK(dil::launch_pack_w1(P.level, reinterpret_cast<uint32_t*>(k->w1p), k->w, n_slots, st));
+        CK(dil::launch_challenge(P.level, k->c, k->ct_slot, k->mu_d, k->w1p, k->active[cur], n_slots, (uint32_t)spec, st));
+        CK(dil::launch_sign_tail(P.level, k->y, k->h_slot, k->accepted, k->key_hat, k->w, k->c, n_slots, e->sm_count, st));
+        CK(dil::launch_resolve(P.level, d_zp, d_h, reinterpret_cast<uint64_t*>(d_ct), d_att, k->kappa, k->active[cur ^ 1], k->count,
+                               k->y, k->h_slot, k->ct_slot, k->accepted, k->active[cur], n_active, (uint32_t)spec, st));
+        launches += 6;
         uint32_t next = 0;
         CK(cudaMemcpyAsync(&next, k->count, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         n_active = next;
         cur ^= 1;
     }
-    CK(dil::launch_pack_z(P.level, d_zp, k->z, (uint32_t)n, st));
-    launches += 1;
     e->launches += launches;
     k->last_rounds = rounds;
     return DIL_OK;

@@ -58,6 +58,10 @@ __global__ void __launch_bounds__(128) sign_init_kernel(uint64_t* __restrict__ m
 }
 
 // ---------------------------------------------------------------------------------------
+// Slots: in a round every active item owns `spec` consecutive slots a = idx*spec + s that try the
+// attempts kappa+s speculatively (spec = 1 while the GPU is saturated by distinct items, up to 16
+// in the straggler rounds); the smallest accepted kappa wins, exactly as sequential signing.
+//
 // S1: ExpandMask.  One thread per polynomial y[a][j] = SHAKE256(rho' || u16le(l*kappa + j)),
 // squeezed into a per-warp shared staging area, then the warp unpacks the 32 polynomials
 // cooperatively so that HBM sees coalesced 1 KiB polynomial writes.
@@ -65,21 +69,21 @@ __global__ void __launch_bounds__(128) sign_init_kernel(uint64_t* __restrict__ m
 template <int L, int GAMMA1_BITS>
 __global__ void __launch_bounds__(128) expand_mask_kernel(int32_t* __restrict__ y, const uint64_t* __restrict__ rhop,
                                                           const uint16_t* __restrict__ kappa, const uint32_t* __restrict__ active,
-                                                          uint32_t n_active) {
+                                                          uint32_t n_slots, uint32_t spec) {
     constexpr int ZB = 32 * (GAMMA1_BITS + 1);       // packed bytes per poly: 576 / 640
     constexpr int ROW = ZB + 16;                      // row stride in shared memory
     constexpr int LANES = ZB / 8;                     // 72 / 80 lanes of output needed
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* stage = sm_raw + (size_t)warp * 32 * ROW;
-    const uint32_t n_polys = n_active * L;
+    const uint32_t n_polys = n_slots * L;
     const uint32_t wbase = (blockIdx.x * (blockDim.x >> 5) + warp) * 32;
     const uint32_t gid = wbase + lane;
     if (wbase >= n_polys) return;
     if (gid < n_polys) {
         const uint32_t a = gid / L, j = gid % L;
-        const uint32_t item = active[a];
-        const uint32_t nonce = (uint32_t)L * kappa[item] + j;
+        const uint32_t item = active[a / spec];
+        const uint32_t nonce = (uint32_t)L * (kappa[item] + a % spec) + j;
         uint64_t A[25];
 #pragma unroll
         for (int i = 0; i < 25; i++) A[i] = 0;
@@ -200,10 +204,10 @@ __global__ void __launch_bounds__(256) pack_w1_kernel(uint32_t* __restrict__ w1p
 template <int K, int W1_BYTES, int TAU>
 __global__ void __launch_bounds__(128) challenge_kernel(int8_t* __restrict__ c_out, uint64_t* __restrict__ ctilde,
                                                         const uint64_t* __restrict__ mu, const uint64_t* __restrict__ w1p,
-                                                        const uint32_t* __restrict__ active, uint32_t n_active) {
+                                                        const uint32_t* __restrict__ active, uint32_t n_slots, uint32_t spec) {
     uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n_active) return;
-    const uint32_t item = active[a];
+    if (a >= n_slots) return;
+    const uint32_t item = active[a / spec];
     constexpr int W1_LANES = K * W1_BYTES / 8;
     const uint64_t* m = mu + (size_t)item * 8;
     const uint64_t* w = w1p + (size_t)a * W1_LANES;
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(128) challenge_kernel(int8_t* __restrict__ c_o
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         ct[i] = A[i];
-        ctilde[(size_t)item * 4 + i] = A[i];
+        ctilde[(size_t)a * 4 + i] = A[i];
     }
     // SampleInBall: SHAKE256(c~): first 8 bytes = sign bits, then rejection bytes
 #pragma unroll
@@ -260,11 +264,9 @@ __global__ void __launch_bounds__(128) challenge_kernel(int8_t* __restrict__ c_o
 __device__ __forceinline__ int32_t centre(uint32_t a) { return (int32_t)a - (int32_t)((a > (Q - 1) / 2) ? Q : 0); }
 
 template <int K, int L, int32_t GAMMA1, int32_t GAMMA2, int BETA, int OMEGA, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) sign_tail_kernel(
-    int32_t* __restrict__ z_out, uint8_t* __restrict__ h_out, uint32_t* __restrict__ attempts, uint16_t* __restrict__ kappa,
-    uint32_t* __restrict__ next_active, uint32_t* __restrict__ next_count, const int32_t* __restrict__ key_hat,
-    const int32_t* __restrict__ y, const int32_t* __restrict__ w, const int8_t* __restrict__ c,
-    const uint32_t* __restrict__ active, uint32_t n_active) {
+__global__ void __launch_bounds__(WARPS * 32, 3) sign_tail_kernel(
+    int32_t* __restrict__ y /* in: y, out: z (in place) */, uint8_t* __restrict__ h_slot, uint8_t* __restrict__ accepted,
+    const int32_t* __restrict__ key_hat, const int32_t* __restrict__ w, const int8_t* __restrict__ c, uint32_t n_slots) {
     extern __shared__ __align__(16) uint32_t sm_words[];
     constexpr int NKEY = L + 2 * K;
     uint32_t* key_sm = sm_words;                       // NKEY * 256
@@ -282,15 +284,14 @@ __global__ void __launch_bounds__(WARPS * 32) sign_tail_kernel(
     InvTw itw;
     load_inv_tw(itw, &TW_INV, lane);
 
-    for (uint32_t a = blockIdx.x * WARPS + warp; a < n_active; a += gridDim.x * WARPS) {
-        const uint32_t item = active[a];
+    for (uint32_t a = blockIdx.x * WARPS + warp; a < n_slots; a += gridDim.x * WARPS) {
         // c_hat in layout C
         uint32_t ch[8];
         {
-            load_fwd_tw(ftw, &TW_FWD, lane);
             const int8_t* cp = c + (size_t)a * N + lane;
 #pragma unroll
             for (int r = 0; r < 8; r++) ch[r] = (uint32_t)(int32_t)cp[32 * r];
+            load_fwd_tw(ftw, &TW_FWD, lane);
             ntt_fwd_warp(ch, scr, ftw, lane);
             __syncwarp();
         }
@@ -303,36 +304,43 @@ __global__ void __launch_bounds__(WARPS * 32) sign_tail_kernel(
             __syncwarp();
         };
         bool bad = false;
-        // z = y + c*s1
-        int32_t* zo = z_out + (size_t)item * L * N + lane;
-        const int32_t* yi = y + (size_t)a * L * N + lane;
+        // z = y + c*s1, written over y; stop at the first polynomial that violates the bound
+        int32_t* yi = y + (size_t)a * L * N + lane;
 #pragma unroll 1
-        for (int j = 0; j < L; j++) {
+        for (int j = 0; j < L && !bad; j++) {
+            int32_t yv[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) yv[r] = yi[j * N + 32 * r];   // issued before the transform: latency hidden
             uint32_t x[8];
             mul_inv(x, j);
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                int32_t z = yi[j * N + 32 * r] + centre(x[r]);
+                int32_t z = yv[r] + centre(x[r]);
                 bad |= (z >= GAMMA1 - BETA) || (z <= -(GAMMA1 - BETA));
-                zo[j * N + 32 * r] = z;
+                yi[j * N + 32 * r] = z;
             }
+            bad = __any_sync(0xffffffffu, bad);
         }
-        bad = __any_sync(0xffffffffu, bad);
         uint32_t nh = 0;
         if (!bad) {
             const int32_t* wi = w + (size_t)a * K * N + lane;
 #pragma unroll 1
-            for (int i = 0; i < K; i++) {
+            for (int i = 0; i < K && !bad; i++) {
+                int32_t wv[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) wv[r] = wi[i * N + 32 * r];
                 uint32_t x[8];
                 int32_t r0[8], w1[8];
                 mul_inv(x, L + i);                      // c*s2_i
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
                     int32_t a0;
-                    decompose<GAMMA2>(wi[i * N + 32 * r], w1[r], a0);
+                    decompose<GAMMA2>(wv[r], w1[r], a0);
                     r0[r] = a0 - centre(x[r]);
                     bad |= (r0[r] >= GAMMA2 - BETA) || (r0[r] <= -(GAMMA2 - BETA));
                 }
+                bad = __any_sync(0xffffffffu, bad);
+                if (bad) break;
                 mul_inv(x, L + K + i);                  // c*t0_i
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
@@ -344,13 +352,14 @@ __global__ void __launch_bounds__(WARPS * 32) sign_tail_kernel(
                     nh += __popc(mask);
                     if (lane == 0) hm[i * 8 + r] = mask;
                 }
+                bad = __any_sync(0xffffffffu, bad);
             }
-            bad = __any_sync(0xffffffffu, bad) || nh > OMEGA;
+            bad = bad || nh > OMEGA;
         }
         __syncwarp();
         if (!bad) {
             // hint encoding: omega position bytes (ascending inside each polynomial), then k running counts
-            uint8_t* ho = h_out + (size_t)item * (OMEGA + K);
+            uint8_t* ho = h_slot + (size_t)a * (OMEGA + K);
             for (int t = lane; t < OMEGA + K; t += 32) ho[t] = 0;
             __syncwarp();
             uint32_t run = 0;
@@ -362,56 +371,81 @@ __global__ void __launch_bounds__(WARPS * 32) sign_tail_kernel(
                 }
                 if (lane == 0) ho[OMEGA + i] = (uint8_t)run;
             }
-            if (lane == 0) attempts[item] = (uint32_t)kappa[item] + 1;
-        } else if (lane == 0) {
-            kappa[item] += 1;
-            next_active[atomicAdd(next_count, 1u)] = item;
         }
+        if (lane == 0) accepted[a] = bad ? 0 : 1;
         __syncwarp();
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// final packing of z (encoder.v:96-133: gamma1 - z, 18 or 20 bits); thread per 8 coefficients
+// S6: resolve, one warp per active item: the first accepted slot (smallest kappa) wins; its z is
+// packed (encoder.v:96-133: gamma1 - z, 18 or 20 bits) straight into the signature, h and c~ are
+// copied; items without an accepted slot advance kappa by `spec` and join the next round.
 // ---------------------------------------------------------------------------------------
-template <int GAMMA1_BITS>
-__global__ void __launch_bounds__(256) pack_z_kernel(uint8_t* __restrict__ zp, const int32_t* __restrict__ z, size_t n_groups) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_groups) return;
+template <int L, int GAMMA1_BITS, int HB>
+__global__ void __launch_bounds__(256) resolve_kernel(uint8_t* __restrict__ zp, uint8_t* __restrict__ h_out,
+                                                      uint64_t* __restrict__ ct_out, uint32_t* __restrict__ attempts,
+                                                      uint16_t* __restrict__ kappa, uint32_t* __restrict__ next_active,
+                                                      uint32_t* __restrict__ next_count, const int32_t* __restrict__ zslot,
+                                                      const uint8_t* __restrict__ h_slot, const uint64_t* __restrict__ ct_slot,
+                                                      const uint8_t* __restrict__ accepted, const uint32_t* __restrict__ active,
+                                                      uint32_t n_items, uint32_t spec) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (idx >= n_items) return;
+    const uint32_t item = active[idx];
+    const uint32_t a0 = idx * spec;
+    uint32_t acc = (lane < (int)spec) ? accepted[a0 + lane] : 0;
+    uint32_t mask = __ballot_sync(0xffffffffu, acc != 0);
+    if (mask == 0) {
+        if (lane == 0) {
+            kappa[item] += (uint16_t)spec;
+            next_active[atomicAdd(next_count, 1u)] = item;
+        }
+        return;
+    }
+    const uint32_t s = __ffs(mask) - 1;
+    const uint32_t a = a0 + s;
     constexpr int BITS = GAMMA1_BITS + 1;
-    const int4* src = reinterpret_cast<const int4*>(z) + t * 2;
-    int4 a = src[0], b = src[1];
-    const int32_t G1 = 1 << GAMMA1_BITS;
-    uint32_t v[8] = {(uint32_t)(G1 - a.x), (uint32_t)(G1 - a.y), (uint32_t)(G1 - a.z), (uint32_t)(G1 - a.w),
-                     (uint32_t)(G1 - b.x), (uint32_t)(G1 - b.y), (uint32_t)(G1 - b.z), (uint32_t)(G1 - b.w)};
-    uint64_t lo = 0, mid = 0;
-    uint32_t hi = 0;
+    constexpr int32_t G1 = 1 << GAMMA1_BITS;
+    const int4* src = reinterpret_cast<const int4*>(zslot + (size_t)a * L * N);
+    uint8_t* dstp = zp + (size_t)item * (L * 32 * BITS);
+    for (int g = lane; g < L * 32; g += 32) {
+        int4 va = src[2 * g], vb = src[2 * g + 1];
+        uint32_t v[8] = {(uint32_t)(G1 - va.x), (uint32_t)(G1 - va.y), (uint32_t)(G1 - va.z), (uint32_t)(G1 - va.w),
+                         (uint32_t)(G1 - vb.x), (uint32_t)(G1 - vb.y), (uint32_t)(G1 - vb.z), (uint32_t)(G1 - vb.w)};
+        uint64_t lo = 0, mid = 0;
+        uint32_t hi = 0;
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-        const int pos = c * BITS;
-        uint64_t x = v[c] & ((1u << BITS) - 1);
-        if (pos < 64) {
-            lo |= x << pos;
-            if (pos + BITS > 64) mid |= x >> (64 - pos);
-        } else if (pos < 128) {
-            mid |= x << (pos - 64);
-            if (pos + BITS > 128) hi |= (uint32_t)(x >> (128 - pos));
+        for (int c = 0; c < 8; c++) {
+            const int pos = c * BITS;
+            uint64_t x = v[c] & ((1u << BITS) - 1);
+            if (pos < 64) {
+                lo |= x << pos;
+                if (pos + BITS > 64) mid |= x >> (64 - pos);
+            } else if (pos < 128) {
+                mid |= x << (pos - 64);
+                if (pos + BITS > 128) hi |= (uint32_t)(x >> (128 - pos));
+            } else {
+                hi |= (uint32_t)x << (pos - 128);
+            }
+        }
+        uint8_t* dst = dstp + (size_t)g * BITS;
+        if constexpr (BITS == 18) {
+            uint16_t* d = reinterpret_cast<uint16_t*>(dst);
+#pragma unroll
+            for (int q = 0; q < 4; q++) d[q] = (uint16_t)(lo >> (16 * q));
+#pragma unroll
+            for (int q = 0; q < 4; q++) d[4 + q] = (uint16_t)(mid >> (16 * q));
+            d[8] = (uint16_t)hi;
         } else {
-            hi |= (uint32_t)x << (pos - 128);
+            uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+            d[0] = (uint32_t)lo; d[1] = (uint32_t)(lo >> 32); d[2] = (uint32_t)mid; d[3] = (uint32_t)(mid >> 32); d[4] = hi;
         }
     }
-    uint8_t* dst = zp + t * BITS;
-    if constexpr (BITS == 18) {
-        uint16_t* d = reinterpret_cast<uint16_t*>(dst);
-#pragma unroll
-        for (int q = 0; q < 4; q++) d[q] = (uint16_t)(lo >> (16 * q));
-#pragma unroll
-        for (int q = 0; q < 4; q++) d[4 + q] = (uint16_t)(mid >> (16 * q));
-        d[8] = (uint16_t)hi;
-    } else {
-        uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-        d[0] = (uint32_t)lo; d[1] = (uint32_t)(lo >> 32); d[2] = (uint32_t)mid; d[3] = (uint32_t)(mid >> 32); d[4] = hi;
-    }
+    for (int t = lane; t < HB; t += 32) h_out[(size_t)item * HB + t] = h_slot[(size_t)a * HB + t];
+    if (lane < 4) ct_out[(size_t)item * 4 + lane] = ct_slot[(size_t)a * 4 + lane];
+    if (lane == 0) attempts[item] = (uint32_t)kappa[item] + s + 1;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -426,7 +460,7 @@ cudaError_t launch_sign_init(uint64_t* mu, uint64_t* rhop, uint16_t* kappa, cons
 
 template <int L, int G1B>
 static cudaError_t launch_expand_mask_t(int32_t* y, const uint64_t* rhop, const uint16_t* kappa, const uint32_t* active,
-                                        uint32_t n_active, cudaStream_t st) {
+                                        uint32_t n_slots, uint32_t spec, cudaStream_t st) {
     constexpr int ROW = 32 * (G1B + 1) + 16;
     constexpr size_t smem = (size_t)4 * 32 * ROW;
     auto kern = expand_mask_kernel<L, G1B>;
@@ -436,50 +470,48 @@ static cudaError_t launch_expand_mask_t(int32_t* y, const uint64_t* rhop, const 
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    uint32_t n_polys = n_active * L;
-    kern<<<(n_polys + 127) / 128, 128, smem, st>>>(y, rhop, kappa, active, n_active);
+    uint32_t n_polys = n_slots * L;
+    kern<<<(n_polys + 127) / 128, 128, smem, st>>>(y, rhop, kappa, active, n_slots, spec);
     return cudaGetLastError();
 }
 
 cudaError_t launch_expand_mask(int level, int32_t* y, const uint64_t* rhop, const uint16_t* kappa, const uint32_t* active,
-                               uint32_t n_active, cudaStream_t st) {
-    if (n_active == 0) return cudaSuccess;
+                               uint32_t n_slots, uint32_t spec, cudaStream_t st) {
+    if (n_slots == 0) return cudaSuccess;
     switch (level) {
-        case 2: return launch_expand_mask_t<4, 17>(y, rhop, kappa, active, n_active, st);
-        case 3: return launch_expand_mask_t<5, 19>(y, rhop, kappa, active, n_active, st);
-        case 5: return launch_expand_mask_t<7, 19>(y, rhop, kappa, active, n_active, st);
+        case 2: return launch_expand_mask_t<4, 17>(y, rhop, kappa, active, n_slots, spec, st);
+        case 3: return launch_expand_mask_t<5, 19>(y, rhop, kappa, active, n_slots, spec, st);
+        case 5: return launch_expand_mask_t<7, 19>(y, rhop, kappa, active, n_slots, spec, st);
     }
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_pack_w1(int level, uint32_t* w1p, const int32_t* w, uint32_t n_active, cudaStream_t st) {
-    if (n_active == 0) return cudaSuccess;
+cudaError_t launch_pack_w1(int level, uint32_t* w1p, const int32_t* w, uint32_t n_slots, cudaStream_t st) {
+    if (n_slots == 0) return cudaSuccess;
     const LevelParams P = level_params(level);
-    size_t n_groups = (size_t)n_active * P.k * (N / 16);
+    size_t n_groups = (size_t)n_slots * P.k * (N / 16);
     unsigned grid = (unsigned)((n_groups + 255) / 256);
     if (level == 2) pack_w1_kernel<(Q_I - 1) / 88><<<grid, 256, 0, st>>>(w1p, w, n_groups);
     else pack_w1_kernel<(Q_I - 1) / 32><<<grid, 256, 0, st>>>(w1p, w, n_groups);
     return cudaGetLastError();
 }
 
-cudaError_t launch_challenge(int level, int8_t* c, uint64_t* ctilde, const uint64_t* mu, const uint64_t* w1p,
-                             const uint32_t* active, uint32_t n_active, cudaStream_t st) {
-    if (n_active == 0) return cudaSuccess;
-    unsigned grid = (n_active + 127) / 128;
+cudaError_t launch_challenge(int level, int8_t* c, uint64_t* ct_slot, const uint64_t* mu, const uint64_t* w1p,
+                             const uint32_t* active, uint32_t n_slots, uint32_t spec, cudaStream_t st) {
+    if (n_slots == 0) return cudaSuccess;
+    unsigned grid = (n_slots + 127) / 128;
     switch (level) {
-        case 2: challenge_kernel<4, 192, 39><<<grid, 128, 0, st>>>(c, ctilde, mu, w1p, active, n_active); break;
-        case 3: challenge_kernel<6, 128, 49><<<grid, 128, 0, st>>>(c, ctilde, mu, w1p, active, n_active); break;
-        case 5: challenge_kernel<8, 128, 60><<<grid, 128, 0, st>>>(c, ctilde, mu, w1p, active, n_active); break;
+        case 2: challenge_kernel<4, 192, 39><<<grid, 128, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
+        case 3: challenge_kernel<6, 128, 49><<<grid, 128, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
+        case 5: challenge_kernel<8, 128, 60><<<grid, 128, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
 template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA>
-static cudaError_t launch_sign_tail_t(int32_t* z_out, uint8_t* h_out, uint32_t* attempts, uint16_t* kappa,
-                                      uint32_t* next_active, uint32_t* next_count, const int32_t* key_hat, const int32_t* y,
-                                      const int32_t* w, const int8_t* c, const uint32_t* active, uint32_t n_active,
-                                      int sm_count, cudaStream_t st) {
+static cudaError_t launch_sign_tail_t(int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat, const int32_t* w,
+                                      const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st) {
     constexpr int WARPS = 8;
     constexpr size_t smem = (size_t)((L + 2 * K) * N + WARPS * SCRATCH_WORDS + WARPS * K * 8) * 4;
     auto kern = sign_tail_kernel<K, L, G1, G2, BETA, OMEGA, WARPS>;
@@ -489,39 +521,35 @@ static cudaError_t launch_sign_tail_t(int32_t* z_out, uint8_t* h_out, uint32_t* 
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    unsigned want = (n_active + WARPS - 1) / WARPS;
-    unsigned cap = (unsigned)sm_count * 2;
-    kern<<<want < cap ? want : cap, WARPS * 32, smem, st>>>(z_out, h_out, attempts, kappa, next_active, next_count, key_hat, y,
-                                                           w, c, active, n_active);
+    unsigned want = (n_slots + WARPS - 1) / WARPS;
+    unsigned cap = (unsigned)sm_count * 3;
+    kern<<<want < cap ? want : cap, WARPS * 32, smem, st>>>(y, h_slot, accepted, key_hat, w, c, n_slots);
     return cudaGetLastError();
 }
 
-cudaError_t launch_sign_tail(int level, int32_t* z_out, uint8_t* h_out, uint32_t* attempts, uint16_t* kappa,
-                             uint32_t* next_active, uint32_t* next_count, const int32_t* key_hat, const int32_t* y,
-                             const int32_t* w, const int8_t* c, const uint32_t* active, uint32_t n_active, int sm_count,
-                             cudaStream_t st) {
-    if (n_active == 0) return cudaSuccess;
+cudaError_t launch_sign_tail(int level, int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat,
+                             const int32_t* w, const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st) {
+    if (n_slots == 0) return cudaSuccess;
     switch (level) {
-        case 2:
-            return launch_sign_tail_t<4, 4, 1 << 17, (Q_I - 1) / 88, 78, 80>(z_out, h_out, attempts, kappa, next_active, next_count,
-                                                                            key_hat, y, w, c, active, n_active, sm_count, st);
-        case 3:
-            return launch_sign_tail_t<6, 5, 1 << 19, (Q_I - 1) / 32, 196, 55>(z_out, h_out, attempts, kappa, next_active, next_count,
-                                                                             key_hat, y, w, c, active, n_active, sm_count, st);
-        case 5:
-            return launch_sign_tail_t<8, 7, 1 << 19, (Q_I - 1) / 32, 120, 75>(z_out, h_out, attempts, kappa, next_active, next_count,
-                                                                             key_hat, y, w, c, active, n_active, sm_count, st);
+        case 2: return launch_sign_tail_t<4, 4, 1 << 17, (Q_I - 1) / 88, 78, 80>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st);
+        case 3: return launch_sign_tail_t<6, 5, 1 << 19, (Q_I - 1) / 32, 196, 55>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st);
+        case 5: return launch_sign_tail_t<8, 7, 1 << 19, (Q_I - 1) / 32, 120, 75>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st);
     }
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_pack_z(int level, uint8_t* zp, const int32_t* z, uint32_t n, cudaStream_t st) {
-    if (n == 0) return cudaSuccess;
-    const LevelParams P = level_params(level);
-    size_t n_groups = (size_t)n * P.l * (N / 8);
-    unsigned grid = (unsigned)((n_groups + 255) / 256);
-    if (P.gamma1_bits == 17) pack_z_kernel<17><<<grid, 256, 0, st>>>(zp, z, n_groups);
-    else pack_z_kernel<19><<<grid, 256, 0, st>>>(zp, z, n_groups);
+cudaError_t launch_resolve(int level, uint8_t* zp, uint8_t* h_out, uint64_t* ct_out, uint32_t* attempts, uint16_t* kappa,
+                           uint32_t* next_active, uint32_t* next_count, const int32_t* zslot, const uint8_t* h_slot,
+                           const uint64_t* ct_slot, const uint8_t* accepted, const uint32_t* active, uint32_t n_items,
+                           uint32_t spec, cudaStream_t st) {
+    if (n_items == 0) return cudaSuccess;
+    unsigned grid = (n_items + 7) / 8;
+    switch (level) {
+        case 2: resolve_kernel<4, 17, 84><<<grid, 256, 0, st>>>(zp, h_out, ct_out, attempts, kappa, next_active, next_count, zslot, h_slot, ct_slot, accepted, active, n_items, spec); break;
+        case 3: resolve_kernel<5, 19, 61><<<grid, 256, 0, st>>>(zp, h_out, ct_out, attempts, kappa, next_active, next_count, zslot, h_slot, ct_slot, accepted, active, n_items, spec); break;
+        case 5: resolve_kernel<7, 19, 83><<<grid, 256, 0, st>>>(zp, h_out, ct_out, attempts, kappa, next_active, next_count, zslot, h_slot, ct_slot, accepted, active, n_items, spec); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

@@ -42,7 +42,7 @@ def test_sign_batch_vs_oracle(eng, oracle, level):
     msgs = [b"", b"a", bytes(135), bytes(range(104)), bytes(rng.integers(0, 256, 3301).astype(np.uint8))]
     msgs += [bytes(rng.integers(0, 256, int(rng.integers(1, 300))).astype(np.uint8)) for _ in range(120)]
     z, h, c, att = key.sign(msgs)
-    assert key.last_rounds == int(att.max())
+    assert 1 <= key.last_rounds <= int(att.max())
     for m in range(len(msgs)):
         zo, ho, co, a = oracle.sign(level, K["rho"][i], K["k"][i], K["tr"][i], K["s1"][i], K["s2"][i], K["t0"][i], msgs[m])
         assert np.array_equal(c[m], co) and np.array_equal(z[m], zo) and np.array_equal(h[m], ho) and att[m] == a, (level, m)
