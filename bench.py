@@ -1,23 +1,29 @@
 #!/usr/bin/env python
-"""bench.py - headline benchmark of the Dilithium polynomial-arithmetic hot path on B200.
+"""bench.py - headline benchmark: batched Dilithium-2 signing on B200 (BASELINE.json metric
+"Dilithium-2 signs/sec at 1/2/4/8 B200; NTT polys/sec vs HBM roofline", configs[1]: Dilithium-2
+(k=4,l=4), 64K-signature batch per GPU).
 
-Workload (BASELINE.json configs[1], "cfg2"): Dilithium-2 (k=4, l=4), a batch of 65 536
-independent signature attempts per GPU; one step = one pass of the sign core over the batch
-
-    y (l polys / item, time domain)  ->  NTT  ->  w = A_hat * y_hat  ->  INTT  ->  w (k polys / item)
-
-(NTT_Y -> MULT_A_Y -> NTTI_W of the reference, rtl_src/combined_top.v:1850-1933) with a shared,
-pre-expanded A_hat (one key signing many messages; rho is broadcast once over NCCL when N > 1 and
-expanded on every GPU by the engine).  Inputs are synthetic (uniform in [0,Q), seed 0x44494C32).
+One step = sign one batch of 65 536 independent 32-byte messages under one key, start to finish
+(mu / rho' hashing, and per rejection round: ExpandMask -> NTT(y) -> A*y -> INTT(w) -> Decompose ->
+challenge hash + SampleInBall -> c*s1, c*s2, c*t0, norm checks, MakeHint; deterministic round-3.1
+signing exactly as the reference's KAT vectors, rtl_src/combined_top.v mode 2).  The polynomial
+arithmetic inside is the engine's hot path; the stand-alone NTT kernel and the fused cfg2 sign core
+(NTT+matvec+INTT) are timed separately in the same run and reported as `roofline_ntt` /
+`sign_core`.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]                 # this framework (CUDA engine)
-    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] # the reference's own C++ on host cores
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] # reference C++ arithmetic on host cores
 
-One JSON line on stdout (rank 0).  `value` = items/s over all GPUs with inputs resident in HBM,
-device-timed (CUDA events, max over ranks).  `e2e` = the same through the host-pointer C ABI
-(dil_signcore_host) from pinned host buffers, H2D and D2H inside the timed region.
+Multi-GPU: one process per GPU (torchrun), every rank signs its own 65 536-message shard (weak
+scaling); the only collective is ONE NCCL broadcast of the key material from rank 0.
+
+`value`   signs/s over all GPUs, messages already resident in HBM, CUDA-event timed, max over ranks.
+`e2e`     the same through dil_sign_batch_host: pinned host messages in, signatures back on the host.
+`roofline` the kernel class with the largest share of the step's device time (measured with CUDA
+          events around every launch in a separate profiled step).
 """
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -30,27 +36,33 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 Q = 8380417
 SEED = 0x44494C32
+MSG_BYTES = 32
 LEVEL_DIMS = {2: (4, 4), 3: (6, 5), 5: (8, 7)}
-METRIC = "Dilithium-2 sign-core items/sec (cfg2: NTT(y) -> A*y -> INTT(w) per signature attempt)"
-UNIT = "items/s"
+LEVEL_EXTRA = {2: dict(w1=192, zb=576, hb=84), 3: dict(w1=128, zb=640, hb=61), 5: dict(w1=128, zb=640, hb=83)}
+UNIT = "signs/s"
+
+
+def metric_name(level):
+    return f"Dilithium-{level} signs/sec"
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--level", type=int, default=2, choices=[2, 3, 5])
-    ap.add_argument("--batch", type=int, default=65536, help="items per GPU (weak scaling)")
-    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=65536, help="signatures per GPU per step (weak scaling)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
 def workload_name(level, batch):
     k, l = LEVEL_DIMS[level]
-    return f"cfg2 sign core NTT+matvec+INTT, Dilithium-{level} (k={k},l={l}), {batch}-item batch per GPU"
+    return (f"full deterministic sign, Dilithium-{level} (k={k},l={l}), {batch}-signature batch per GPU, one key, "
+            f"{MSG_BYTES}-byte messages")
 
 
 def measured_peak():
@@ -61,51 +73,87 @@ def measured_peak():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+def ncu_traffic(kernel_class):
+    """dram bytes per launch of `kernel_class` from the committed ncu capture, or None."""
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel.json")))
-        return prof.get("dram_bytes_per_launch")
+        return prof.get(kernel_class, {}).get("dram_bytes_per_launch")
     except Exception:
         return None
 
 
+def kat_key(level, index=0):
+    """Signing key = KAT vector `index` of the reference (committed fixture tests/golden/kat_L*.npz)."""
+    import numpy as np
+    d = np.load(os.path.join(ROOT, "tests", "golden", f"kat_L{level}.npz"))
+    return {f: np.ascontiguousarray(d[f][index]) for f in ("rho", "k", "tr", "s1", "s2", "t0", "t1")}
+
+
+def class_bytes(level):
+    """Algorithmic HBM bytes per slot (one signing attempt) for each kernel class."""
+    k, l = LEVEL_DIMS[level]
+    x = LEVEL_EXTRA[level]
+    return {
+        "expand_mask": 66 + l * 1024,
+        "signcore": (l + k) * 1024,
+        "pack_w1": k * 1024 + k * x["w1"],
+        "challenge": 64 + k * x["w1"] + 256 + 32,
+        "tail": 256 + 2 * l * 1024 + k * 1024 + x["hb"] + 1,
+        "resolve": l * 1024 + l * x["zb"] + 2 * x["hb"] + 64 + 4,
+    }
+
+
+CLASS_KERNEL = {"expand_mask": "expand_mask_kernel<L,GAMMA1_BITS> (SHAKE-256 ExpandMask, one Keccak state per thread)",
+                "signcore": "matvec_shared_kernel<K,L,8,0,1,1> (fused NTT -> A*y -> INTT)",
+                "pack_w1": "pack_w1_kernel", "challenge": "challenge_kernel (SHAKE-256 + SampleInBall)",
+                "tail": "sign_tail_kernel (NTT(c), c*s1/c*s2/c*t0, INTTs, norm checks, MakeHint)", "resolve": "resolve_kernel",
+                "init": "sign_init_kernel"}
+CLASS_BOUND_NOTE = {"expand_mask": "integer ALU (Keccak): ncu alu pipe 95% busy; HBM fraction is not the limiter",
+                    "challenge": "integer ALU (Keccak)", "tail": "integer multiply pipe (fmaheavy) + load latency",
+                    "signcore": "integer multiply pipe (fmaheavy): ncu 73% busy", "pack_w1": "HBM", "resolve": "HBM/latency"}
+
+
 # --------------------------------------------------------------------------------------
-# CPU arm: the reference's own implementation (oracle/_ref) or the oracle port
+# CPU arm: reference arithmetic (oracle/_ref) + scheme glue, or the pure oracle port
 # --------------------------------------------------------------------------------------
-def cpu_signcore(level, batch, threads, steps=1, warmup=0):
-    """Times the cfg2 sign core on host cores.  Returns (items_per_s, kind, cores, sample, ms_per_step)."""
+def cpu_sign(level, n_msgs, threads, steps=1, warmup=0):
     import numpy as np
     import oracle_lib as ol
-    k, l = LEVEL_DIMS[level]
+    K = {f: v[None, ...] for f, v in kat_key(level).items()}
     rng = np.random.default_rng(SEED)
-    a_hat = rng.integers(0, Q, size=(k * l, 256)).astype(np.int32)
-    y0 = rng.integers(0, Q, size=(batch, l, 256)).astype(np.int32)
+    msgs = [bytes(rng.integers(0, 256, MSG_BYTES).astype(np.uint8)) for _ in range(n_msgs)]
     ref = ol.load_ref()
     impl, kind = (ref, "reference") if ref is not None else (ol.load(), "port")
-    dt = impl.time_signcore(a_hat, y0, k, l, threads=threads, steps=steps, warmup=warmup)
-    sample = (f"{batch} items x {steps} step(s) of the same workload through "
-              + ("ref_ntt.cpp ntt/invntt/pointwise_barrett compiled from the reference (oracle/_ref)"
-                 if kind == "reference" else "the oracle port (oracle/*.c)")
-              + f", batch split over {threads} std::thread(s)")
-    return batch / dt, kind, threads, sample, dt * 1e3
+    for _ in range(warmup):
+        impl.sign_batch(level, K, 0, msgs, threads)
+    dt = 0.0
+    att = None
+    for _ in range(steps):
+        *_, att, sec = impl.sign_batch(level, K, 0, msgs, threads)
+        dt += sec
+    dt /= steps
+    sample = (f"{n_msgs} messages x {steps} step(s), one key, split over {threads} thread(s); "
+              + ("every NTT / inverse NTT / pointwise product runs the reference's own compiled ref_ntt.cpp functions "
+                 "(oracle/_ref, ref_bridge.cpp); hashing, sampling, packing and the rejection loop are the oracle's C "
+                 "restatement (the reference has no C/C++ sign, SURVEY.md 0.1)" if kind == "reference"
+                 else "oracle port (oracle/*.c) for everything"))
+    return n_msgs / dt, kind, threads, sample, dt * 1e3, float(att.mean())
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = os.cpu_count() or 1
-    batch = min(args.batch, 16384)  # bounded sample per step: ~1 core-second
-    steps = max(1, min(args.steps, 20))
-    warm = max(0, min(args.warmup, 2))
-    val, kind, threads, sample, ms = cpu_signcore(args.level, batch, cores, steps, warm)
+    n_msgs = 256 * cores if 256 * cores < 8192 else 8192
+    steps = max(1, min(args.steps, 5))
+    warm = max(0, min(args.warmup, 1))
+    val, kind, threads, sample, ms, att = cpu_sign(args.level, n_msgs, cores, steps, warm)
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args.level), "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32/int64 (signed % reduction)", "data": "synthetic",
-        "config": {"workload": workload_name(args.level, args.batch), "level": args.level, "sample_items_per_step": batch,
-                   "note": "CPU arm: host cores only, no GPU; throughput does not depend on --gpus"},
+        "config": {"workload": workload_name(args.level, args.batch), "level": args.level, "sample_messages_per_step": n_msgs,
+                   "mean_attempts": att, "note": "CPU arm: host cores only, no GPU; throughput does not depend on --gpus"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -168,6 +216,7 @@ class ClockSampler:
 # engine arm
 # --------------------------------------------------------------------------------------
 def run_engine(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     import dilithium_b200 as d
@@ -183,7 +232,8 @@ def run_engine(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     eng = d.Engine(local)
-    k, l = LEVEL_DIMS[args.level]
+    level = args.level
+    k, l = LEVEL_DIMS[level]
     B = args.batch
 
     def barrier():
@@ -191,25 +241,40 @@ def run_engine(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # one key for the whole job: rho broadcast once (the only collective), A expanded on every GPU
-    rho = torch.zeros(32, dtype=torch.uint8, device=dev)
-    if rank == 0:
-        g0 = torch.Generator(device="cpu").manual_seed(SEED)
-        rho.copy_(torch.randint(0, 256, (32,), dtype=torch.uint8, generator=g0))
-    from dilithium_b200.sharding import broadcast_rho
-    broadcast_rho(rho, src=0)
-    a_hat = eng.expand_a(rho, k, l)[0].contiguous()
+    def maxr(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # per-rank synthetic batch (shard = contiguous item range of the global batch), pinned host copy for e2e
+    # one key for the whole job: rank 0 owns it, ONE broadcast ships it (rho | K | tr | s1 | s2 | t0)
+    fields = ("rho", "k", "tr", "s1", "s2", "t0")
+    sizes = {f: v.size for f, v in kat_key(level).items()}
+    blob = torch.zeros(sum(sizes[f] for f in fields), dtype=torch.uint8, device=dev)
+    if rank == 0:
+        kk = kat_key(level)
+        blob.copy_(torch.from_numpy(np.concatenate([kk[f] for f in fields])))
+    if world > 1:
+        dist.broadcast(blob, src=0)
+    parts, off = {}, 0
+    hb = blob.cpu().numpy()
+    for f in fields:
+        parts[f] = hb[off:off + sizes[f]].copy()
+        off += sizes[f]
+    key = d.SignKey(eng, level, *[parts[f] for f in fields])
+
+    # per-rank synthetic messages (the rank's shard of the global batch)
     gen = torch.Generator(device="cpu").manual_seed(SEED + 1 + rank)
-    y_host = torch.randint(0, Q, (B, l, 256), dtype=torch.int32, generator=gen).pin_memory()
-    w_host = torch.empty((B, k, 256), dtype=torch.int32).pin_memory()
-    y = y_host.to(dev, non_blocking=True)
-    w = torch.empty((B, k, 256), dtype=torch.int32, device=dev)
-    torch.cuda.synchronize()
+    msgs_host = torch.randint(0, 256, (B * MSG_BYTES,), dtype=torch.uint8, generator=gen).pin_memory()
+    offs_host = (torch.arange(B + 1, dtype=torch.int64) * MSG_BYTES).pin_memory()
+    msgs, offs = msgs_host.to(dev), offs_host.to(dev)
+    z = torch.empty((B, key.z_bytes), dtype=torch.uint8, device=dev)
+    h = torch.empty((B, key.h_bytes), dtype=torch.uint8, device=dev)
+    c = torch.empty((B, 32), dtype=torch.uint8, device=dev)
+    att = torch.zeros(B, dtype=torch.int32, device=dev)
 
     def step():
-        eng.signcore(a_hat, y, k, l, w=w)
+        key.sign_dev(msgs, offs, B, z, h, c, att)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -223,18 +288,23 @@ def run_engine(args):
         ev1.record()
         barrier()
     launches = eng.launch_count - l0
-    ms_total = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = maxr(ev0.elapsed_time(ev1))
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
+    mean_attempts = float(att.float().mean().item())
+    rounds = key.last_rounds
 
-    # stand-alone NTT kernel (north_star: "NTT polys/sec vs HBM roofline"), separately timed
-    npoly = B * l
-    out = torch.empty_like(y)
+    # per-kernel-class device time of one step (CUDA events around every launch), outside the timed region
+    key.set_profile(True)
+    step()
+    torch.cuda.synchronize()
+    prof = key.get_profile()
+    key.set_profile(False)
+    prof_total = sum(ms for ms, _ in prof.values())
+    dominant = max((n for n in prof if n != "init"), key=lambda n: prof[n][0])
+    cb = class_bytes(level)
 
+    # stand-alone hot-path kernels, separately timed (north_star: "NTT polys/sec vs HBM roofline")
     def time_kernel(fn, iters=50):
         for _ in range(3):
             fn()
@@ -247,63 +317,82 @@ def run_engine(args):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / iters
 
-    ntt_ms = time_kernel(lambda: eng.ntt(y, out=out))
-    intt_ms = time_kernel(lambda: eng.invntt(y, out=out))
+    yb = torch.randint(0, Q, (B, l, 256), dtype=torch.int32, device=dev)
+    outb = torch.empty_like(yb)
+    wb = torch.empty((B, k, 256), dtype=torch.int32, device=dev)
+    a_hat = eng.expand_a(torch.from_numpy(parts["rho"]).to(dev), k, l)[0].contiguous()
+    npoly = B * l
+    ntt_ms = time_kernel(lambda: eng.ntt(yb, out=outb))
+    intt_ms = time_kernel(lambda: eng.invntt(yb, out=outb))
+    core_ms = time_kernel(lambda: eng.signcore(a_hat, yb, k, l, w=wb))
+    del yb, outb, wb
 
-    # end to end through the host-pointer C ABI: pinned host y -> H2D -> sign core -> D2H -> host w
-    y_np, w_np = y_host.numpy(), w_host.numpy()
-    import ctypes
+    # end to end through the host-pointer C ABI: pinned host messages in, signatures out to host memory
+    z_h = torch.empty((B, key.z_bytes), dtype=torch.uint8).pin_memory()
+    h_h = torch.empty((B, key.h_bytes), dtype=torch.uint8).pin_memory()
+    c_h = torch.empty((B, 32), dtype=torch.uint8).pin_memory()
+    a_h = torch.zeros(B, dtype=torch.int32).pin_memory()
+    P = ctypes.c_void_p
     lib = eng._lib
 
     def e2e_step():
-        rc = lib.dil_signcore_host(eng._h, ctypes.c_void_p(w_np.ctypes.data), ctypes.c_void_p(a_hat_np.ctypes.data),
-                                   ctypes.c_void_p(y_np.ctypes.data), k, l, B)
+        rc = lib.dil_sign_batch_host(eng._h, key._h, P(msgs_host.data_ptr()), P(offs_host.data_ptr()), B, P(z_h.data_ptr()),
+                                     P(h_h.data_ptr()), P(c_h.data_ptr()), P(a_h.data_ptr()))
         if rc != 0:
-            raise RuntimeError("dil_signcore_host failed")
+            raise RuntimeError("dil_sign_batch_host failed")
 
-    a_hat_np = a_hat.cpu().numpy()
     e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
         e2e_step()
     barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = world * B * args.e2e_steps / float(te.item())
-    e2e_ok = bool(torch.equal(torch.from_numpy(w_np).to(dev), w))
+    e2e_s = maxr(time.perf_counter() - t0)
+    e2e_val = world * B * args.e2e_steps / e2e_s
+    e2e_ok = bool(torch.equal(z_h.to(dev), z) and torch.equal(h_h.to(dev), h) and torch.equal(c_h.to(dev), c))
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        alg_bytes = B * (k + l) * 1024
-        achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+        dom_ms, dom_units = prof[dominant]
+        dom_bytes = cb[dominant] * dom_units
+        dom_achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        sig_bytes = key.z_bytes + key.h_bytes + 32
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 (Shoup/Barrett modular arithmetic, 64-bit accumulate)", "data": "synthetic",
-            "config": {"workload": workload_name(args.level, B), "level": args.level, "k": k, "l": l, "batch_per_gpu": B,
-                       "sharding": "independent items, contiguous ranges per rank; one 32-byte NCCL broadcast of rho" if world > 1 else "single GPU",
-                       "l2": f"no flush: {alg_bytes >> 20} MiB touched per step exceeds the 126 MB L2",
-                       "timing": "CUDA events on torch's current stream (the stream the kernels are launched on), max over ranks"},
+            "metric": metric_name(level), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32/u64 integer (Shoup/Barrett modular arithmetic, 64-bit Keccak lanes)", "data": "synthetic",
+            "config": {"workload": workload_name(level, B), "level": level, "k": k, "l": l, "batch_per_gpu": B,
+                       "key": "reference KAT vector 0 (tests/golden)", "mean_attempts": mean_attempts, "rejection_rounds": rounds,
+                       "sharding": ("independent messages, one contiguous shard per rank; one NCCL broadcast of the key material"
+                                    if world > 1 else "single GPU"),
+                       "l2": "no flush: every round streams > 1 GiB of per-attempt state (y, w, c), far above the 126 MB L2",
+                       "timing": "CUDA events on torch's current stream (the stream every kernel is launched on), max over ranks"},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
-            "roofline": {"kernel": "matvec_shared_kernel<4,4,...> (fused NTT -> A*y -> INTT sign core)" if args.level == 2 else "matvec_shared_kernel",
-                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                         "note": "(l+k) KiB per item; this fused kernel is integer-issue bound, not HBM bound (DESIGN.md)"},
-            "roofline_ntt": {"kernel": "ntt_tma_kernel<8,3,4,false>", "bound": "hbm", "polys_per_s": npoly / (ntt_ms * 1e-3),
-                             "achieved": npoly * 2048 / (ntt_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": npoly * 2048 / (ntt_ms * 1e-3) / 1e9 / peak, "polys_per_launch": npoly,
+            "step_profile_ms": {n: round(ms, 4) for n, (ms, _) in prof.items()},
+            "step_profile_note": f"device time per kernel class in one step (sum {prof_total:.3f} ms of {ms_step:.3f} ms wall); "
+                                 "the rest is launch latency and one 4-byte D2H + stream sync per rejection round",
+            "roofline": {"kernel": CLASS_KERNEL[dominant], "class": dominant, "bound": "hbm", "achieved": dom_achieved, "peak": peak,
+                         "unit": "GB/s", "frac": dom_achieved / peak, "traffic": ncu_traffic(dominant),
+                         "algorithmic_bytes_per_slot": cb[dominant], "slots_per_step": dom_units, "launches_per_step": rounds,
+                         "avg_launch_ms": dom_ms / max(rounds, 1), "peak_source": peak_src,
+                         "true_limiter": CLASS_BOUND_NOTE.get(dominant, "")},
+            "roofline_ntt": {"kernel": "ntt_tma_kernel<8,3,4,false> (stand-alone forward NTT, the north_star's named kernel)",
+                             "bound": "hbm", "polys_per_s": npoly / (ntt_ms * 1e-3), "achieved": npoly * 2048 / (ntt_ms * 1e-3) / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": npoly * 2048 / (ntt_ms * 1e-3) / 1e9 / peak, "polys_per_launch": npoly,
                              "invntt_polys_per_s": npoly / (intt_ms * 1e-3), "invntt_frac": npoly * 2048 / (intt_ms * 1e-3) / 1e9 / peak},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * l * 1024 + k * l * 1024, "d2h_bytes_per_step": B * k * 1024,
-                    "steps": args.e2e_steps, "api": "dil_signcore_host (C ABI, pinned host buffers, synchronous)",
+            "sign_core": {"workload": f"cfg2 core alone: w = INTT(A_hat * NTT(y)), {B} items, one fused kernel",
+                          "items_per_s": B / (core_ms * 1e-3), "ms": core_ms,
+                          "hbm_frac": B * (k + l) * 1024 / (core_ms * 1e-3) / 1e9 / peak},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * MSG_BYTES + (B + 1) * 8,
+                    "d2h_bytes_per_step": B * (sig_bytes + 4), "steps": args.e2e_steps,
+                    "api": "dil_sign_batch_host (C ABI): pinned host messages in, z/h/c~/attempts back in host memory",
                     "timing": "host wall clock around the synchronous calls, max over ranks", "matches_device_path": e2e_ok},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            v, kind, threads, sample, _ = cpu_signcore(args.level, min(B, 32768), cores, steps=3, warmup=1)
+            n_cpu = 256 * cores if 256 * cores < 8192 else 8192
+            v, kind, threads, sample, _, _ = cpu_sign(level, n_cpu, cores, steps=2, warmup=1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -41,6 +41,11 @@ struct dil_sign_key {
     uint32_t* att_d = nullptr;
     size_t msgs_cap = 0, out_cap = 0;
     uint32_t last_rounds = 0;
+    // optional per-kernel-class device timing (CUDA events on the launching stream)
+    bool profile = false;
+    cudaEvent_t ev[16] = {};
+    double prof_ms[8] = {};
+    uint64_t prof_slots[8] = {};
 };
 
 namespace {
@@ -129,9 +134,25 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
     int rc = ensure_ws(e, k, n);
     if (rc) return rc;
     uint64_t launches = 0;
+    const bool prof = k->profile;
+    if (prof) {
+        for (int i = 0; i < 8; i++) k->prof_ms[i] = 0, k->prof_slots[i] = 0;
+        for (int i = 0; i < 16; i++)
+            if (!k->ev[i]) CK(cudaEventCreate(&k->ev[i]));
+    }
+#define PROF_BEGIN(cls) do { if (prof) CK(cudaEventRecord(k->ev[2 * (cls)], st)); } while (0)
+#define PROF_END(cls, units) do { if (prof) { CK(cudaEventRecord(k->ev[2 * (cls) + 1], st)); k->prof_slots[cls] += (units); } } while (0)
     CK(dil::launch_iota(k->active[0], (uint32_t)n, st));
+    PROF_BEGIN(0);
     CK(dil::launch_sign_init(k->mu_d, k->rhop, k->kappa, k->seeds, k->seeds + 32, d_msgs, d_off, (uint32_t)n, st));
+    PROF_END(0, n);
     launches += 2;
+    if (prof) {
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, k->ev[0], k->ev[1]));
+        k->prof_ms[0] += ms;
+    }
     uint32_t n_active = (uint32_t)n, rounds = 0;
     int cur = 0;
     while (n_active > 0) {
@@ -146,17 +167,35 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
         }
         const uint32_t n_slots = (uint32_t)(n_active * spec);
         CK(cudaMemsetAsync(k->count, 0, 4, st));
+        PROF_BEGIN(1);
         CK(dil::launch_expand_mask(P.level, k->y, k->rhop, k->kappa, k->active[cur], n_slots, (uint32_t)spec, st));
+        PROF_END(1, n_slots);
+        PROF_BEGIN(2);
         CK(dil::launch_signcore(k->w, k->a_hat, k->y, P.k, P.l, n_slots, e->sm_count, st));
+        PROF_END(2, n_slots);
+        PROF_BEGIN(3);
         CK(dil::launch_pack_w1(P.level, reinterpret_cast<uint32_t*>(k->w1p), k->w, n_slots, st));
+        PROF_END(3, n_slots);
+        PROF_BEGIN(4);
         CK(dil::launch_challenge(P.level, k->c, k->ct_slot, k->mu_d, k->w1p, k->active[cur], n_slots, (uint32_t)spec, st));
+        PROF_END(4, n_slots);
+        PROF_BEGIN(5);
         CK(dil::launch_sign_tail(P.level, k->y, k->h_slot, k->accepted, k->key_hat, k->w, k->c, n_slots, e->sm_count, st));
+        PROF_END(5, n_slots);
+        PROF_BEGIN(6);
         CK(dil::launch_resolve(P.level, d_zp, d_h, reinterpret_cast<uint64_t*>(d_ct), d_att, k->kappa, k->active[cur ^ 1], k->count,
                                k->y, k->h_slot, k->ct_slot, k->accepted, k->active[cur], n_active, (uint32_t)spec, st));
+        PROF_END(6, n_active);
         launches += 6;
         uint32_t next = 0;
         CK(cudaMemcpyAsync(&next, k->count, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        if (prof)
+            for (int cls = 1; cls <= 6; cls++) {
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, k->ev[2 * cls], k->ev[2 * cls + 1]));
+                k->prof_ms[cls] += ms;
+            }
         n_active = next;
         cur ^= 1;
     }
@@ -240,12 +279,25 @@ int dil_sign_key_destroy(dil_engine_t* e, dil_sign_key_t* k) {
     void* ptrs[] = {k->a_hat, k->key_hat, k->seeds, k->msgs_d, k->zp_d, k->h_d, k->ct_d, k->off_d, k->att_d};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    for (auto& ev : k->ev)
+        if (ev) cudaEventDestroy(ev);
     (void)e;
     delete k;
     return DIL_OK;
 }
 
 uint32_t dil_sign_last_rounds(const dil_sign_key_t* k) { return k ? k->last_rounds : 0; }
+
+int dil_sign_set_profile(dil_sign_key_t* k, int on) {
+    if (!k) return DIL_ERR_ARG;
+    k->profile = on != 0;
+    return DIL_OK;
+}
+int dil_sign_get_profile(const dil_sign_key_t* k, double* ms, uint64_t* units) {
+    if (!k || !ms || !units) return DIL_ERR_ARG;
+    for (int i = 0; i < 8; i++) ms[i] = k->prof_ms[i], units[i] = k->prof_slots[i];
+    return DIL_OK;
+}
 
 int dil_sign_batch_dev(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* d_msgs, const uint64_t* d_offsets, size_t n,
                        uint8_t* d_z, uint8_t* d_h, uint8_t* d_ctilde, uint32_t* d_attempts, void* stream) {

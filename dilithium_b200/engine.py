@@ -257,6 +257,18 @@ class SignKey:
     def last_rounds(self):
         return int(self.engine._lib.dil_sign_last_rounds(self._h))
 
+    PROFILE_CLASSES = ("init", "expand_mask", "signcore", "pack_w1", "challenge", "tail", "resolve")
+
+    def set_profile(self, on=True):
+        self.engine._check(self.engine._lib.dil_sign_set_profile(self._h, int(on)), "dil_sign_set_profile")
+
+    def get_profile(self):
+        """{class: (device ms, slots processed)} of the last batch signed with profiling on."""
+        ms = (ctypes.c_double * 8)()
+        units = (ctypes.c_uint64 * 8)()
+        self.engine._check(self.engine._lib.dil_sign_get_profile(self._h, ms, units), "dil_sign_get_profile")
+        return {name: (ms[i], int(units[i])) for i, name in enumerate(self.PROFILE_CLASSES)}
+
     def sign(self, msgs):
         """Sign a list of byte strings (host path, dil_sign_batch_host).
         Returns (z[n, z_bytes], h[n, h_bytes], ctilde[n, 32], attempts[n])."""

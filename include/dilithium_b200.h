@@ -136,6 +136,11 @@ int dil_sign_batch_host(dil_engine_t *e, dil_sign_key_t *k, const uint8_t *msgs,
 int dil_sign_batch_dev(dil_engine_t *e, dil_sign_key_t *k, const uint8_t *d_msgs, const uint64_t *d_offsets, size_t n,
                        uint8_t *d_z, uint8_t *d_h, uint8_t *d_ctilde, uint32_t *d_attempts, void *stream);
 uint32_t dil_sign_last_rounds(const dil_sign_key_t *k);   /* rejection rounds of the last batch */
+/* optional device timing of the pipeline's kernel classes (CUDA events on the launching stream):
+   index 0 init (mu, rho'), 1 ExpandMask, 2 fused sign core, 3 w1 pack, 4 challenge, 5 tail, 6 resolve;
+   ms[8] = summed kernel time of the last batch, units[8] = slots (attempts) each class processed */
+int dil_sign_set_profile(dil_sign_key_t *k, int on);
+int dil_sign_get_profile(const dil_sign_key_t *k, double *ms, uint64_t *units);
 
 /* ---- north_star aliases (plain domain, identical to the above) ---- */
 int dil_invntt_tomont_dev(dil_engine_t *e, int32_t *dst, const int32_t *src, size_t n_polys, void *stream);

@@ -115,6 +115,12 @@ int orc_sign(int level, const uint8_t rho[32], const uint8_t key[32], const uint
              const uint8_t *s1p, const uint8_t *s2p, const uint8_t *t0p,
              const uint8_t *msg, size_t mlen,
              uint8_t *zp, uint8_t *hp, uint8_t ctilde[32]);
+/* the same with the per-key work (ExpandA, NTT of s1/s2/t0) hoisted out for batches */
+typedef struct orc_sign_ctx orc_sign_ctx_t;
+orc_sign_ctx_t *orc_sign_prepare(int level, const uint8_t rho[32], const uint8_t *s1p, const uint8_t *s2p, const uint8_t *t0p);
+int orc_sign_msg(const orc_sign_ctx_t *ctx, const uint8_t key[32], const uint8_t tr[32],
+                 const uint8_t *msg, size_t mlen, uint8_t *zp, uint8_t *hp, uint8_t ctilde[32]);
+void orc_sign_free(orc_sign_ctx_t *ctx);
 /* verify (combined_top.v:1080-1534); returns 0 = accept, 1 = reject */
 int orc_verify(int level, const uint8_t rho[32], const uint8_t *t1p,
                const uint8_t *msg, size_t mlen,

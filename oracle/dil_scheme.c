@@ -264,23 +264,48 @@ int orc_keygen(int level, const uint8_t xi[32], uint8_t rho[32], uint8_t key[32]
     return 0;
 }
 
+/* Expanded signing key: ExpandA(rho) and the NTT images of s1, s2, t0 - computed once per key
+   (LOAD_RHO / NTT_S1 / NTT_S2 / NTT_T0, combined_top.v:1560-1767) and reused for every message. */
+struct orc_sign_ctx {
+    orc_params_t P;
+    int32_t *a_hat;
+    int32_t s1h[8 * N], s2h[8 * N], t0h[8 * N];
+};
+
+orc_sign_ctx_t *orc_sign_prepare(int level, const uint8_t rho[32], const uint8_t *s1p, const uint8_t *s2p, const uint8_t *t0p) {
+    orc_sign_ctx_t *c = (orc_sign_ctx_t *)malloc(sizeof *c);
+    if (!c || orc_params(&c->P, level)) { free(c); return NULL; }
+    const int k = c->P.k, l = c->P.l;
+    c->a_hat = (int32_t *)malloc((size_t)k * l * N * 4);
+    orc_expand_a(c->a_hat, rho, k, l);
+    orc_unpack_s(c->s1h, s1p, l, c->P.eta); orc_ntt_batch(c->s1h, (size_t)l);
+    orc_unpack_s(c->s2h, s2p, k, c->P.eta); orc_ntt_batch(c->s2h, (size_t)k);
+    orc_unpack_t0(c->t0h, t0p, k);          orc_ntt_batch(c->t0h, (size_t)k);
+    return c;
+}
+void orc_sign_free(orc_sign_ctx_t *c) {
+    if (c) { free(c->a_hat); free(c); }
+}
+
 int orc_sign(int level, const uint8_t rho[32], const uint8_t key[32], const uint8_t tr[32],
              const uint8_t *s1p, const uint8_t *s2p, const uint8_t *t0p,
              const uint8_t *msg, size_t mlen, uint8_t *zp, uint8_t *hp, uint8_t ctilde[32]) {
-    orc_params_t P;
-    if (orc_params(&P, level)) return -1;
+    orc_sign_ctx_t *c = orc_sign_prepare(level, rho, s1p, s2p, t0p);
+    if (!c) return -1;
+    int r = orc_sign_msg(c, key, tr, msg, mlen, zp, hp, ctilde);
+    orc_sign_free(c);
+    return r;
+}
+
+int orc_sign_msg(const orc_sign_ctx_t *ctx, const uint8_t key[32], const uint8_t tr[32],
+                 const uint8_t *msg, size_t mlen, uint8_t *zp, uint8_t *hp, uint8_t ctilde[32]) {
+    const orc_params_t P = ctx->P;
     const int k = P.k, l = P.l;
-    int32_t *a_hat = (int32_t *)malloc((size_t)k * l * N * 4);
-    int32_t s1h[8 * N], s2h[8 * N], t0h[8 * N];
+    const int32_t *a_hat = ctx->a_hat, *s1h = ctx->s1h, *s2h = ctx->s2h, *t0h = ctx->t0h;
     int32_t y[8 * N], yh[8 * N], w[8 * N], w1[8 * N], w0[8 * N], c[N], ch[N];
     int32_t z[8 * N], tmp[8 * N], hint[8 * N];
     uint8_t mu[64], rhoprime[64], w1p[8 * 192];
     orc_shake_t st;
-
-    orc_expand_a(a_hat, rho, k, l);
-    orc_unpack_s(s1h, s1p, l, P.eta); orc_ntt_batch(s1h, (size_t)l);
-    orc_unpack_s(s2h, s2p, k, P.eta); orc_ntt_batch(s2h, (size_t)k);
-    orc_unpack_t0(t0h, t0p, k);       orc_ntt_batch(t0h, (size_t)k);
 
     orc_shake_init(&st, 136);
     orc_shake_absorb(&st, tr, 32);
@@ -341,10 +366,8 @@ int orc_sign(int level, const uint8_t rho[32], const uint8_t key[32], const uint
                 if (hint[i * N + j]) hp[idx++] = (uint8_t)j;
             hp[P.omega + i] = (uint8_t)idx;
         }
-        free(a_hat);
         return attempts;
     }
-    free(a_hat);
     return -2;
 }
 

@@ -119,6 +119,9 @@ class Oracle:
     def time_signcore(self, a_hat, y, k, l, threads=1, steps=1, warmup=0):
         return _time_signcore(self.lib.orc_signcore_batch_mt, a_hat, y, k, l, threads, steps, warmup)
 
+    def sign_batch(self, level, K, i, msgs, threads=1):
+        return _sign_batch(self.lib, level, K, i, msgs, threads)
+
     def shake_bytes(self, data: bytes, outlen: int, bits=256) -> bytes:
         buf = np.frombuffer(data, dtype=np.uint8).copy() if data else np.zeros(1, np.uint8)
         out = np.empty(outlen, dtype=np.uint8)
@@ -169,6 +172,26 @@ class Oracle:
                                    _u8(c8(zp)), _u8(c8(hp)), _u8(c8(c)))
 
 
+def _sign_batch(lib, level, K, i, msgs, threads, attempts=True):
+    """Threaded CPU batch sign with KAT key i.  Returns (z, h, c, attempts, seconds)."""
+    import time
+    P = PARAMS[level]
+    n = len(msgs)
+    zb = P["l"] * N * (P["gamma1_bits"] + 1) // 8
+    hb = P["omega"] + P["k"]
+    off = np.zeros(n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(m) for m in msgs])
+    blob = np.frombuffer(b"".join(msgs), dtype=np.uint8).copy() if off[-1] else np.zeros(1, np.uint8)
+    z, h, c = np.empty((n, zb), np.uint8), np.empty((n, hb), np.uint8), np.empty((n, 32), np.uint8)
+    att = np.zeros(n, dtype=np.uint32)
+    c8 = np.ascontiguousarray
+    g = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    args = [level] + [g(c8(K[f][i])) for f in ("rho", "k", "tr", "s1", "s2", "t0")] + [g(blob), g(off), ctypes.c_size_t(n), g(z), g(h), g(c), g(att), threads]
+    t0 = time.perf_counter()
+    lib.orc_sign_batch_mt(*args)
+    return z, h, c, att, time.perf_counter() - t0
+
+
 def _time_signcore(cfn, a_hat, y, k, l, threads, steps, warmup):
     """Wall-clock seconds per call of a C sign-core batch driver (buffers prepared outside the
     timed region; the transforms are data-independent so y is transformed in place repeatedly)."""
@@ -190,6 +213,11 @@ class Ref:
 
     def time_signcore(self, a_hat, y, k, l, threads=1, steps=1, warmup=0):
         return _time_signcore(self.lib.ref_signcore_batch, a_hat, y, k, l, threads, steps, warmup)
+
+    def sign_batch(self, level, K, i, msgs, threads=1):
+        """Full sign on host cores: reference ntt/invntt/pointwise_barrett for all polynomial
+        arithmetic (ref_bridge.cpp) + the oracle's scheme glue."""
+        return _sign_batch(self.lib, level, K, i, msgs, threads)
 
     def __init__(self, lib):
         self.lib = lib
