@@ -55,6 +55,10 @@ SIGNATURES = {
     "dil_sign_last_rounds": (ctypes.c_uint32, [c_void]),
     "dil_sign_set_profile": (c_int, [c_void, c_int]),
     "dil_sign_get_profile": (c_int, [c_void, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
+    "dil_verify_key_create": (c_int, [c_void, ctypes.POINTER(c_void), c_int, c_void, c_void]),
+    "dil_verify_key_destroy": (c_int, [c_void, c_void]),
+    "dil_verify_batch_host": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void]),
+    "dil_verify_batch_dev": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void, c_void]),
     "dil_invntt_tomont_dev": (c_int, [c_void, c_void, c_void, c_size, c_void]),
     "dil_poly_pointwise_dev": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void]),
     "dil_polyvec_matrix_pointwise_dev": (c_int, [c_void, c_void, c_void, c_void, c_int, c_int, c_size, c_void]),

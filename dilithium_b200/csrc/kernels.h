@@ -36,5 +36,16 @@ cudaError_t launch_resolve(int level, uint8_t* zp, uint8_t* h_out, uint64_t* ct_
                            const uint64_t* ct_slot, const uint8_t* accepted, const uint32_t* active, uint32_t n_items,
                            uint32_t spec, cudaStream_t st);
 cudaError_t launch_iota(uint32_t* dst, uint32_t n, cudaStream_t st);
+// ---- verify pipeline ----
+cudaError_t launch_verify_core(int32_t* w, const int32_t* a_ext, const int32_t* v, int level, size_t batch, int sm_count,
+                               cudaStream_t st);
+cudaError_t launch_verify_mu(uint64_t* mu, const uint8_t* tr, const uint8_t* msgs, const uint64_t* offsets, uint32_t n, cudaStream_t st);
+cudaError_t launch_tr(uint64_t* tr, const uint8_t* rho, const uint8_t* t1p, uint32_t t1_bytes, cudaStream_t st);
+cudaError_t launch_unpack_z(int level, int32_t* v, uint32_t* bad, const uint8_t* zp, uint32_t n, cudaStream_t st);
+cudaError_t launch_verify_prep(int level, int32_t* v, uint32_t* hmask, uint32_t* bad, const uint8_t* h, const uint64_t* ctilde,
+                               uint32_t n, cudaStream_t st);
+cudaError_t launch_usehint_pack(int level, uint32_t* w1p, const int32_t* w, const uint32_t* hmask, uint32_t n, cudaStream_t st);
+cudaError_t launch_verify_hash(int level, uint8_t* ok, const uint64_t* mu, const uint64_t* w1p, const uint64_t* ctilde,
+                               const uint32_t* bad, uint32_t n, cudaStream_t st);
 
 }  // namespace dil

@@ -234,4 +234,17 @@ cudaError_t launch_signcore(int32_t* w, const int32_t* a_hat, const int32_t* y, 
     return cudaErrorInvalidValue;
 }
 
+
+// verification core: k x (l+1) matrix [A_hat | -t1_hat*2^13], inputs [z_0..z_{l-1}, c] in the time domain
+cudaError_t launch_verify_core(int32_t* w, const int32_t* a_ext, const int32_t* v, int level, size_t batch, int sm_count,
+                               cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    switch (level) {
+        case 2: return launch_shared_t<4, 5, 8, false, true, true>(w, a_ext, nullptr, v, batch, sm_count, st);
+        case 3: return launch_shared_t<6, 6, 8, false, true, true>(w, a_ext, nullptr, v, batch, sm_count, st);
+        case 5: return launch_shared_t<8, 8, 8, false, true, true>(w, a_ext, nullptr, v, batch, sm_count, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 }  // namespace dil

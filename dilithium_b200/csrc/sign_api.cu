@@ -358,3 +358,194 @@ int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs,
 }
 
 }  // extern "C"
+
+// =======================================================================================
+// Verification API (combined_top.v mode 1; I/O order of rtl_tb/tb_verify_top.v:144-249:
+// rho, c~, z, t1, mlen, M, h -> one accept/reject word)
+// =======================================================================================
+struct dil_verify_key {
+    LevelParams P{};
+    int device = -1;
+    int32_t* a_ext = nullptr;   // k x (l+1) polys: [A_hat | -NTT(t1 * 2^13)]
+    uint8_t* seeds = nullptr;   // tr[32] | rho[32] | t1_packed
+    std::mutex mu;
+    size_t cap = 0;
+    uint64_t *mu_d = nullptr, *w1p = nullptr;
+    int32_t *v = nullptr, *w = nullptr;
+    uint32_t *hmask = nullptr, *bad = nullptr;
+    // host-variant staging
+    uint8_t *msgs_d = nullptr, *z_d = nullptr, *h_d = nullptr, *ct_d = nullptr, *ok_d = nullptr;
+    uint64_t* off_d = nullptr;
+    size_t msgs_cap = 0, io_cap = 0;
+};
+
+namespace {
+void vfree(void* p) { if (p) cudaFree(p); }
+void free_vws(dil_verify_key* k) {
+    vfree(k->mu_d); vfree(k->w1p); vfree(k->v); vfree(k->w); vfree(k->hmask); vfree(k->bad);
+    k->mu_d = k->w1p = nullptr; k->v = k->w = nullptr; k->hmask = k->bad = nullptr; k->cap = 0;
+}
+int ensure_vws(dil_engine* e, dil_verify_key* k, size_t n) {
+    if (n <= k->cap) return DIL_OK;
+    free_vws(k);
+    const LevelParams& P = k->P;
+    cudaError_t err = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+    A(dmalloc(&k->mu_d, n * 8));
+    A(dmalloc(&k->w1p, n * (size_t)(P.k * P.w1_bytes / 8)));
+    A(dmalloc(&k->v, n * (size_t)(P.l + 1) * 256));
+    A(dmalloc(&k->w, n * (size_t)P.k * 256));
+    A(dmalloc(&k->hmask, n * (size_t)P.k * 8));
+    A(dmalloc(&k->bad, n));
+    if (err != cudaSuccess) {
+        free_vws(k);
+        e->last_error = std::string("verify workspace: ") + cudaGetErrorString(err);
+        return DIL_ERR_ALLOC;
+    }
+    k->cap = n;
+    return DIL_OK;
+}
+int verify_run(dil_engine* e, dil_verify_key* k, const uint8_t* d_msgs, const uint64_t* d_off, size_t n, const uint8_t* d_z,
+               const uint8_t* d_h, const uint8_t* d_ct, uint8_t* d_ok, cudaStream_t st) {
+    const LevelParams& P = k->P;
+    int rc = ensure_vws(e, k, n);
+    if (rc) return rc;
+    const uint32_t nn = (uint32_t)n;
+    CK(cudaMemsetAsync(k->bad, 0, n * 4, st));
+    CK(dil::launch_verify_mu(k->mu_d, k->seeds, d_msgs, d_off, nn, st));
+    CK(dil::launch_unpack_z(P.level, k->v, k->bad, d_z, nn, st));
+    CK(dil::launch_verify_prep(P.level, k->v, k->hmask, k->bad, d_h, reinterpret_cast<const uint64_t*>(d_ct), nn, st));
+    CK(dil::launch_verify_core(k->w, k->a_ext, k->v, P.level, n, e->sm_count, st));
+    CK(dil::launch_usehint_pack(P.level, reinterpret_cast<uint32_t*>(k->w1p), k->w, k->hmask, nn, st));
+    CK(dil::launch_verify_hash(P.level, d_ok, k->mu_d, k->w1p, reinterpret_cast<const uint64_t*>(d_ct), k->bad, nn, st));
+    e->launches += 6;
+    return DIL_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int dil_verify_key_create(dil_engine_t* e, dil_verify_key_t** out, int level, const uint8_t* rho, const uint8_t* t1p) {
+    if (!e || !out || !rho || !t1p) return DIL_ERR_ARG;
+    if (level != 2 && level != 3 && level != 5) return DIL_ERR_ARG;
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(e->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    dil_verify_key* k = new (std::nothrow) dil_verify_key();
+    if (!k) return DIL_ERR_ALLOC;
+    k->P = dil::level_params(level);
+    k->device = e->device;
+    const LevelParams& P = k->P;
+    const int K = P.k, L = P.l;
+    // -t1 * 2^13 mod Q (decoder.v:96-100 delivers t1 * 2^13), unpacked on the host
+    std::vector<int32_t> t1neg((size_t)K * 256);
+    std::vector<uint32_t> tmp(256);
+    for (int p = 0; p < K; p++) {
+        bits_get(tmp.data(), t1p + (size_t)p * 320, 256, 10);
+        for (int i = 0; i < 256; i++) {
+            int64_t v = ((int64_t)tmp[i] << dil::D_BITS) % dil::Q_I;
+            t1neg[(size_t)p * 256 + i] = (int32_t)((dil::Q_I - v) % dil::Q_I);
+        }
+    }
+    cudaStream_t st = e->host_stream;
+    cudaError_t err = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+    int32_t* a_tmp = nullptr;
+    const size_t t1_bytes = (size_t)K * 320;
+    std::vector<uint8_t> seeds(64 + t1_bytes);
+    std::memcpy(seeds.data() + 32, rho, 32);
+    std::memcpy(seeds.data() + 64, t1p, t1_bytes);
+    A(dmalloc(&k->a_ext, (size_t)K * (L + 1) * 256));
+    A(dmalloc(&a_tmp, (size_t)K * L * 256));
+    A(dmalloc(&k->seeds, seeds.size()));
+    if (err == cudaSuccess) {
+        A(cudaMemcpyAsync(k->seeds, seeds.data(), seeds.size(), cudaMemcpyHostToDevice, st));
+        A(dil::launch_tr(reinterpret_cast<uint64_t*>(k->seeds), k->seeds + 32, k->seeds + 64, (uint32_t)t1_bytes, st));
+        A(dil::launch_expand_a(a_tmp, k->seeds + 32, 1, K, L, e->sm_count, st));
+        // rows of A_hat into the first l columns of a_ext, -t1*2^13 into column l, then NTT that column
+        A(cudaMemcpy2DAsync(k->a_ext, (size_t)(L + 1) * 1024, a_tmp, (size_t)L * 1024, (size_t)L * 1024, K, cudaMemcpyDeviceToDevice, st));
+        A(cudaMemcpy2DAsync(k->a_ext + (size_t)L * 256, (size_t)(L + 1) * 1024, t1neg.data(), 1024, 1024, K, cudaMemcpyHostToDevice, st));
+        for (int i = 0; i < K; i++) {
+            int32_t* col = k->a_ext + ((size_t)i * (L + 1) + L) * 256;
+            A(dil::launch_ntt_fwd(col, col, 1, e->sm_count, st));
+        }
+        A(cudaStreamSynchronize(st));
+    }
+    if (a_tmp) cudaFree(a_tmp);
+    if (err != cudaSuccess) {
+        vfree(k->a_ext); vfree(k->seeds);
+        delete k;
+        return fail(e, err, "dil_verify_key_create");
+    }
+    e->launches += 2 + K;
+    *out = k;
+    return DIL_OK;
+}
+
+int dil_verify_key_destroy(dil_engine_t* e, dil_verify_key_t* k) {
+    (void)e;
+    if (!k) return DIL_OK;
+    DeviceGuard dg(k->device);
+    free_vws(k);
+    vfree(k->a_ext); vfree(k->seeds); vfree(k->msgs_d); vfree(k->z_d); vfree(k->h_d); vfree(k->ct_d); vfree(k->ok_d); vfree(k->off_d);
+    delete k;
+    return DIL_OK;
+}
+
+int dil_verify_batch_dev(dil_engine_t* e, dil_verify_key_t* k, const uint8_t* d_msgs, const uint64_t* d_offsets, size_t n,
+                         const uint8_t* d_z, const uint8_t* d_h, const uint8_t* d_ctilde, uint8_t* d_ok, void* stream) {
+    if (!e || !k) return DIL_ERR_ARG;
+    if (n == 0) return DIL_OK;
+    if (!d_msgs || !d_offsets || !d_z || !d_h || !d_ctilde || !d_ok || n > 0x7FFFFFFFu) return DIL_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_ctilde) & 7u) || (reinterpret_cast<uintptr_t>(d_z) & 3u)) return DIL_ERR_ARG;
+    std::lock_guard<std::mutex> g(k->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    return verify_run(e, k, d_msgs, d_offsets, n, d_z, d_h, d_ctilde, d_ok, (cudaStream_t)stream);
+}
+
+int dil_verify_batch_host(dil_engine_t* e, dil_verify_key_t* k, const uint8_t* msgs, const uint64_t* offsets, size_t n,
+                          const uint8_t* z, const uint8_t* h, const uint8_t* ctilde, uint8_t* ok) {
+    if (!e || !k) return DIL_ERR_ARG;
+    if (n == 0) return DIL_OK;
+    if (!msgs || !offsets || !z || !h || !ctilde || !ok || n > 0x7FFFFFFFu) return DIL_ERR_ARG;
+    std::lock_guard<std::mutex> g(k->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    const LevelParams& P = k->P;
+    cudaStream_t st = e->host_stream;
+    const size_t mbytes = offsets[n] > 0 ? offsets[n] : 1;
+    const size_t zb = (size_t)P.l * P.z_bytes, hb = (size_t)P.omega + P.k;
+    if (mbytes > k->msgs_cap) {
+        vfree(k->msgs_d);
+        k->msgs_d = nullptr;
+        k->msgs_cap = 0;
+        CK(dmalloc(&k->msgs_d, mbytes));
+        k->msgs_cap = mbytes;
+    }
+    if (n > k->io_cap) {
+        vfree(k->z_d); vfree(k->h_d); vfree(k->ct_d); vfree(k->ok_d); vfree(k->off_d);
+        k->z_d = k->h_d = k->ct_d = k->ok_d = nullptr;
+        k->off_d = nullptr;
+        k->io_cap = 0;
+        CK(dmalloc(&k->z_d, n * zb));
+        CK(dmalloc(&k->h_d, n * hb));
+        CK(dmalloc(&k->ct_d, n * 32));
+        CK(dmalloc(&k->ok_d, n));
+        CK(dmalloc(&k->off_d, n + 1));
+        k->io_cap = n;
+    }
+    CK(cudaMemcpyAsync(k->msgs_d, msgs, offsets[n], cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(k->off_d, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(k->z_d, z, n * zb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(k->h_d, h, n * hb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(k->ct_d, ctilde, n * 32, cudaMemcpyHostToDevice, st));
+    int rc = verify_run(e, k, k->msgs_d, k->off_d, n, k->z_d, k->h_d, k->ct_d, k->ok_d, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ok, k->ok_d, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return DIL_OK;
+}
+
+}  // extern "C"

@@ -566,3 +566,273 @@ cudaError_t launch_iota(uint32_t* dst, uint32_t n, cudaStream_t st) {
     return cudaGetLastError();
 }
 }  // namespace dil
+
+// =======================================================================================
+// Verification (rtl_src/combined_top.v:1080-1534, I/O order rtl_tb/tb_verify_top.v:144-249):
+//   w' = INTT( A_hat * NTT(z) - NTT(c) o NTT(t1 * 2^13) ),  w1' = UseHint(h, w'),
+//   accept iff SHAKE256(mu || pack(w1')) == c~   (and ||z|| < gamma1 - beta, h well formed).
+// The core is the same fused kernel as signing with one extra column: inputs [z_0..z_{l-1}, c],
+// matrix [A_hat | -t1_hat * 2^13] of shape k x (l+1)  (matvec_kernels.cu, launch_verify_core).
+// =======================================================================================
+namespace dil {
+
+// mu = SHAKE256(tr || M); one thread per item
+__global__ void __launch_bounds__(128) verify_mu_kernel(uint64_t* __restrict__ mu, const uint8_t* __restrict__ tr,
+                                                        const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ offsets, uint32_t n) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint8_t* m = msgs + offsets[t];
+    const size_t mlen = (size_t)(offsets[t + 1] - offsets[t]);
+    uint64_t A[25];
+    shake256_absorb_lanes(A, 32 + mlen, [&](size_t idx) -> uint64_t {
+        if (idx < 4) return load_lane_bytes(tr, idx * 8, 32);
+        return load_lane_bytes(m, (idx - 4) * 8, mlen);
+    });
+#pragma unroll
+    for (int i = 0; i < 8; i++) mu[(size_t)t * 8 + i] = A[i];
+}
+
+// tr = SHAKE256(rho || t1_packed)[0:32]   (combined_top.v:980); single thread, once per key
+__global__ void tr_kernel(uint64_t* __restrict__ tr, const uint8_t* __restrict__ rho, const uint8_t* __restrict__ t1p, uint32_t t1_bytes) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint64_t A[25];
+    shake256_absorb_lanes(A, 32 + t1_bytes, [&](size_t idx) -> uint64_t {
+        if (idx < 4) return load_lane_bytes(rho, idx * 8, 32);
+        return load_lane_bytes(t1p, (idx - 4) * 8, t1_bytes);
+    });
+#pragma unroll
+    for (int i = 0; i < 4; i++) tr[i] = A[i];
+}
+
+// z unpack (decoder.v:89-143: gamma1 - x, 18/20 bits) into v[item][j][256] of an (L+1)-poly item
+// record, with the ||z||_inf < gamma1 - beta check; one thread per 8 coefficients
+template <int L, int GAMMA1_BITS, int BETA>
+__global__ void __launch_bounds__(256) unpack_z_kernel(int32_t* __restrict__ v, uint32_t* __restrict__ bad, const uint8_t* __restrict__ zp,
+                                                       size_t n_groups) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_groups) return;
+    constexpr int BITS = GAMMA1_BITS + 1;
+    constexpr int32_t G1 = 1 << GAMMA1_BITS;
+    const size_t item = t / (L * 32);
+    const uint32_t g = (uint32_t)(t % (L * 32));     // group inside the item's l polynomials
+    const uint8_t* src = zp + item * (size_t)(L * 32 * BITS) + (size_t)g * BITS;
+    uint64_t lo, mid;
+    uint32_t hi;
+    if constexpr (BITS == 18) {
+        const uint16_t* h = reinterpret_cast<const uint16_t*>(src);
+        lo = (uint64_t)h[0] | ((uint64_t)h[1] << 16) | ((uint64_t)h[2] << 32) | ((uint64_t)h[3] << 48);
+        mid = (uint64_t)h[4] | ((uint64_t)h[5] << 16) | ((uint64_t)h[6] << 32) | ((uint64_t)h[7] << 48);
+        hi = h[8];
+    } else {
+        const uint32_t* h = reinterpret_cast<const uint32_t*>(src);
+        lo = (uint64_t)h[0] | ((uint64_t)h[1] << 32);
+        mid = (uint64_t)h[2] | ((uint64_t)h[3] << 32);
+        hi = h[4];
+    }
+    int32_t o[8];
+    bool b = false;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const int pos = c * BITS;
+        uint64_t bits;
+        if (pos + BITS <= 64) bits = lo >> pos;
+        else if (pos < 64) bits = (lo >> pos) | (mid << (64 - pos));
+        else if (pos + BITS <= 128) bits = mid >> (pos - 64);
+        else if (pos < 128) bits = (mid >> (pos - 64)) | ((uint64_t)hi << (128 - pos));
+        else bits = hi >> (pos - 128);
+        o[c] = G1 - (int32_t)((uint32_t)bits & ((1u << BITS) - 1));
+        b |= (o[c] >= G1 - BETA) || (o[c] <= -(G1 - BETA));
+    }
+    int4* dst = reinterpret_cast<int4*>(v + item * (size_t)((L + 1) * N) + (size_t)g * 8);
+    dst[0] = make_int4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_int4(o[4], o[5], o[6], o[7]);
+    if (b) bad[item] = 1;
+}
+
+// per item: hint decode (omega position bytes + k running counts) with the standard well-formedness
+// checks -> 256-bit masks; c = SampleInBall(c~) written as the (L+1)-th polynomial of the item record
+template <int K, int L, int OMEGA, int TAU>
+__global__ void __launch_bounds__(128) verify_prep_kernel(int32_t* __restrict__ v, uint32_t* __restrict__ hmask, uint32_t* __restrict__ bad,
+                                                          const uint8_t* __restrict__ h, const uint64_t* __restrict__ ctilde, uint32_t n) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint8_t* hp = h + (size_t)t * (OMEGA + K);
+    uint32_t m[K * 8];
+#pragma unroll
+    for (int i = 0; i < K * 8; i++) m[i] = 0;
+    bool b = false;
+    int idx = 0;
+    for (int i = 0; i < K; i++) {
+        int end = hp[OMEGA + i];
+        if (end < idx || end > OMEGA) { b = true; break; }
+        for (int j = idx; j < end; j++) {
+            int pos = hp[j];
+            if (j > idx && pos <= hp[j - 1]) b = true;
+            m[i * 8 + (pos >> 5)] |= 1u << (pos & 31);
+        }
+        idx = end;
+    }
+    for (int j = idx; j < OMEGA && !b; j++)
+        if (hp[j]) b = true;
+    for (int i = 0; i < K * 8; i++) hmask[(size_t)t * (K * 8) + i] = m[i];
+    if (b) bad[t] = 1;
+    // SampleInBall
+    uint64_t A[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) A[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) A[i] = ctilde[(size_t)t * 4 + i];
+    A[4] = 0x1F;
+    A[16] = 0x80ULL << 56;
+    keccak_f1600(A);
+    uint64_t signs = A[0];
+    __align__(8) uint8_t buf[136];
+    __align__(4) int8_t c[N];
+#pragma unroll
+    for (int i = 0; i < 17; i++) reinterpret_cast<uint64_t*>(buf)[i] = A[i];
+    for (int i = 0; i < N; i++) c[i] = 0;
+    int pos = 8;
+    for (int i = N - TAU; i < N; i++) {
+        int bb;
+        do {
+            if (pos == 136) {
+                keccak_f1600(A);
+#pragma unroll
+                for (int q = 0; q < 17; q++) reinterpret_cast<uint64_t*>(buf)[q] = A[q];
+                pos = 0;
+            }
+            bb = buf[pos++];
+        } while (bb > i);
+        c[i] = c[bb];
+        c[bb] = (signs & 1) ? -1 : 1;
+        signs >>= 1;
+    }
+    int32_t* dst = v + (size_t)t * ((L + 1) * N) + L * N;
+    for (int i = 0; i < N; i++) dst[i] = c[i];
+}
+
+// w1' = UseHint(h, w') (usehint.v:134-155), packed; one thread per 16 coefficients
+template <int K, int32_t GAMMA2>
+__global__ void __launch_bounds__(256) usehint_pack_kernel(uint32_t* __restrict__ w1p, const int32_t* __restrict__ w,
+                                                           const uint32_t* __restrict__ hmask, size_t n_groups) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_groups) return;
+    const int4* src = reinterpret_cast<const int4*>(w) + t * 4;
+    // group t covers coefficients 16*(t%16) .. +15 of polynomial t/16; hint word (t%16)>>1, half (t&1)
+    const uint32_t hw = hmask[(t >> 4) * 8 + ((t & 15) >> 1)] >> ((t & 1) * 16);
+    constexpr int32_t M = (Q_I - 1) / (2 * GAMMA2);   // 44 or 16
+    int32_t hh[16];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        int4 x = src[q];
+        int32_t in[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            int32_t a1, a0;
+            decompose<GAMMA2>(in[e], a1, a0);
+            if ((hw >> (4 * q + e)) & 1u) a1 = a0 > 0 ? (a1 + 1 == M ? 0 : a1 + 1) : (a1 == 0 ? M - 1 : a1 - 1);
+            hh[4 * q + e] = a1;
+        }
+    }
+    if constexpr (GAMMA2 == (Q_I - 1) / 32) {
+        uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            o0 |= (uint32_t)hh[c] << (4 * c);
+            o1 |= (uint32_t)hh[8 + c] << (4 * c);
+        }
+        w1p[t * 2] = o0;
+        w1p[t * 2 + 1] = o1;
+    } else {
+        uint64_t lo = 0;
+#pragma unroll
+        for (int c = 0; c < 10; c++) lo |= (uint64_t)hh[c] << (6 * c);
+        lo |= (uint64_t)hh[10] << 60;
+        uint32_t hi = ((uint32_t)hh[10] >> 4) | ((uint32_t)hh[11] << 2) | ((uint32_t)hh[12] << 8) | ((uint32_t)hh[13] << 14) |
+                      ((uint32_t)hh[14] << 20) | ((uint32_t)hh[15] << 26);
+        w1p[t * 3] = (uint32_t)lo;
+        w1p[t * 3 + 1] = (uint32_t)(lo >> 32);
+        w1p[t * 3 + 2] = hi;
+    }
+}
+
+// c~' = SHAKE256(mu || w1'_packed)[0:32]; ok = (c~' == c~) && !bad; one thread per item
+template <int K, int W1_BYTES>
+__global__ void __launch_bounds__(128) verify_hash_kernel(uint8_t* __restrict__ ok, const uint64_t* __restrict__ mu,
+                                                          const uint64_t* __restrict__ w1p, const uint64_t* __restrict__ ctilde,
+                                                          const uint32_t* __restrict__ bad, uint32_t n) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    constexpr int W1_LANES = K * W1_BYTES / 8;
+    const uint64_t* m = mu + (size_t)t * 8;
+    const uint64_t* w = w1p + (size_t)t * W1_LANES;
+    uint64_t A[25];
+    shake256_absorb_lanes(A, 64 + K * W1_BYTES, [&](size_t idx) -> uint64_t { return idx < 8 ? m[idx] : w[idx - 8]; });
+    bool same = true;
+#pragma unroll
+    for (int i = 0; i < 4; i++) same &= (A[i] == ctilde[(size_t)t * 4 + i]);
+    ok[t] = (same && bad[t] == 0) ? 1 : 0;
+}
+
+// ---- launchers ----
+cudaError_t launch_verify_mu(uint64_t* mu, const uint8_t* tr, const uint8_t* msgs, const uint64_t* offsets, uint32_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    verify_mu_kernel<<<(n + 127) / 128, 128, 0, st>>>(mu, tr, msgs, offsets, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_tr(uint64_t* tr, const uint8_t* rho, const uint8_t* t1p, uint32_t t1_bytes, cudaStream_t st) {
+    tr_kernel<<<1, 32, 0, st>>>(tr, rho, t1p, t1_bytes);
+    return cudaGetLastError();
+}
+cudaError_t launch_unpack_z(int level, int32_t* v, uint32_t* bad, const uint8_t* zp, uint32_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const LevelParams P = level_params(level);
+    size_t n_groups = (size_t)n * P.l * 32;
+    unsigned grid = (unsigned)((n_groups + 255) / 256);
+    switch (level) {
+        case 2: unpack_z_kernel<4, 17, 78><<<grid, 256, 0, st>>>(v, bad, zp, n_groups); break;
+        case 3: unpack_z_kernel<5, 19, 196><<<grid, 256, 0, st>>>(v, bad, zp, n_groups); break;
+        case 5: unpack_z_kernel<7, 19, 120><<<grid, 256, 0, st>>>(v, bad, zp, n_groups); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_verify_prep(int level, int32_t* v, uint32_t* hmask, uint32_t* bad, const uint8_t* h, const uint64_t* ctilde,
+                               uint32_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    unsigned grid = (n + 127) / 128;
+    switch (level) {
+        case 2: verify_prep_kernel<4, 4, 80, 39><<<grid, 128, 0, st>>>(v, hmask, bad, h, ctilde, n); break;
+        case 3: verify_prep_kernel<6, 5, 55, 49><<<grid, 128, 0, st>>>(v, hmask, bad, h, ctilde, n); break;
+        case 5: verify_prep_kernel<8, 7, 75, 60><<<grid, 128, 0, st>>>(v, hmask, bad, h, ctilde, n); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_usehint_pack(int level, uint32_t* w1p, const int32_t* w, const uint32_t* hmask, uint32_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const LevelParams P = level_params(level);
+    size_t n_groups = (size_t)n * P.k * 16;
+    unsigned grid = (unsigned)((n_groups + 255) / 256);
+    switch (level) {
+        case 2: usehint_pack_kernel<4, (Q_I - 1) / 88><<<grid, 256, 0, st>>>(w1p, w, hmask, n_groups); break;
+        case 3: usehint_pack_kernel<6, (Q_I - 1) / 32><<<grid, 256, 0, st>>>(w1p, w, hmask, n_groups); break;
+        case 5: usehint_pack_kernel<8, (Q_I - 1) / 32><<<grid, 256, 0, st>>>(w1p, w, hmask, n_groups); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_verify_hash(int level, uint8_t* ok, const uint64_t* mu, const uint64_t* w1p, const uint64_t* ctilde,
+                               const uint32_t* bad, uint32_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    unsigned grid = (n + 127) / 128;
+    switch (level) {
+        case 2: verify_hash_kernel<4, 192><<<grid, 128, 0, st>>>(ok, mu, w1p, ctilde, bad, n); break;
+        case 3: verify_hash_kernel<6, 128><<<grid, 128, 0, st>>>(ok, mu, w1p, ctilde, bad, n); break;
+        case 5: verify_hash_kernel<8, 128><<<grid, 128, 0, st>>>(ok, mu, w1p, ctilde, bad, n); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace dil

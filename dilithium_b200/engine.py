@@ -293,3 +293,52 @@ class SignKey:
                                                  ctypes.c_void_p(d_h.data_ptr()), ctypes.c_void_p(d_c.data_ptr()),
                                                  ctypes.c_void_p(d_att.data_ptr()), self.engine._stream())
         self.engine._check(rc, "dil_sign_batch_dev")
+
+
+class VerifyKey:
+    """Expanded public key on the device (rho, t1 as in the KAT files / tb_verify_top.v:144-240)."""
+
+    def __init__(self, engine, level, rho, t1_packed):
+        self.engine, self.level = engine, int(level)
+        lib = engine._lib
+        zb, hb = ctypes.c_size_t(), ctypes.c_size_t()
+        engine._check(lib.dil_sign_sizes(self.level, ctypes.byref(zb), ctypes.byref(hb)), "dil_sign_sizes")
+        self.z_bytes, self.h_bytes = zb.value, hb.value
+        bufs = [np.ascontiguousarray(x, dtype=np.uint8) for x in (rho, t1_packed)]
+        h = ctypes.c_void_p()
+        engine._check(lib.dil_verify_key_create(engine._h, ctypes.byref(h), self.level, *[b.ctypes.data_as(ctypes.c_void_p) for b in bufs]),
+                      "dil_verify_key_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.engine, "_h", None):
+            self.engine._lib.dil_verify_key_destroy(self.engine._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def verify(self, msgs, z, h, ctilde):
+        """Host path: returns ok[n] (uint8, 1 = accept)."""
+        n = len(msgs)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(m) for m in msgs])
+        blob = np.frombuffer(b"".join(msgs), dtype=np.uint8).copy() if off[-1] else np.zeros(1, np.uint8)
+        z, h, c = (np.ascontiguousarray(x, dtype=np.uint8) for x in (z, h, ctilde))
+        assert z.size == n * self.z_bytes and h.size == n * self.h_bytes and c.size == n * 32
+        ok = np.zeros(n, dtype=np.uint8)
+        P = ctypes.c_void_p
+        rc = self.engine._lib.dil_verify_batch_host(self.engine._h, self._h, blob.ctypes.data_as(P), off.ctypes.data_as(P), n,
+                                                    z.ctypes.data_as(P), h.ctypes.data_as(P), c.ctypes.data_as(P), ok.ctypes.data_as(P))
+        self.engine._check(rc, "dil_verify_batch_host")
+        return ok
+
+    def verify_dev(self, d_msgs, d_offsets, n, d_z, d_h, d_c, d_ok):
+        rc = self.engine._lib.dil_verify_batch_dev(self.engine._h, self._h, ctypes.c_void_p(d_msgs.data_ptr()),
+                                                   ctypes.c_void_p(d_offsets.data_ptr()), n, ctypes.c_void_p(d_z.data_ptr()),
+                                                   ctypes.c_void_p(d_h.data_ptr()), ctypes.c_void_p(d_c.data_ptr()),
+                                                   ctypes.c_void_p(d_ok.data_ptr()), self.engine._stream())
+        self.engine._check(rc, "dil_verify_batch_dev")

@@ -142,6 +142,18 @@ uint32_t dil_sign_last_rounds(const dil_sign_key_t *k);   /* rejection rounds of
 int dil_sign_set_profile(dil_sign_key_t *k, int on);
 int dil_sign_get_profile(const dil_sign_key_t *k, double *ms, uint64_t *units);
 
+/* ---- batched verification (combined_top.v mode 1, FSM :1080-1534) ----
+ * I/O of rtl_tb/tb_verify_top.v:144-249: public key rho + t1 (10-bit packed), per signature c~, z, h and the
+ * message; result ok[i] = 1 (accept) / 0 (reject: hash mismatch, ||z|| >= gamma1 - beta or malformed hint).
+ * One public key per handle; A_hat and -NTT(t1*2^13) are expanded once, tr = SHAKE256(rho || t1) on device. */
+typedef struct dil_verify_key dil_verify_key_t;
+int dil_verify_key_create(dil_engine_t *e, dil_verify_key_t **out, int level, const uint8_t *rho, const uint8_t *t1_packed);
+int dil_verify_key_destroy(dil_engine_t *e, dil_verify_key_t *k);
+int dil_verify_batch_host(dil_engine_t *e, dil_verify_key_t *k, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                          const uint8_t *z, const uint8_t *h, const uint8_t *ctilde, uint8_t *ok);
+int dil_verify_batch_dev(dil_engine_t *e, dil_verify_key_t *k, const uint8_t *d_msgs, const uint64_t *d_offsets, size_t n,
+                         const uint8_t *d_z, const uint8_t *d_h, const uint8_t *d_ctilde, uint8_t *d_ok, void *stream);
+
 /* ---- north_star aliases (plain domain, identical to the above) ---- */
 int dil_invntt_tomont_dev(dil_engine_t *e, int32_t *dst, const int32_t *src, size_t n_polys, void *stream);
 int dil_poly_pointwise_dev(dil_engine_t *e, int32_t *c, const int32_t *a, const int32_t *b, size_t n_polys, void *stream);
