@@ -48,4 +48,11 @@ cudaError_t launch_usehint_pack(int level, uint32_t* w1p, const int32_t* w, cons
 cudaError_t launch_verify_hash(int level, uint8_t* ok, const uint64_t* mu, const uint64_t* w1p, const uint64_t* ctilde,
                                const uint32_t* bad, uint32_t n, cudaStream_t st);
 
+// ---- keygen pipeline ----
+cudaError_t launch_keygen_seed(uint8_t* rho, uint64_t* rhop, uint8_t* key, const uint8_t* xi, uint32_t n, cudaStream_t st);
+cudaError_t launch_eta_sample(int level, int32_t* s1, int32_t* s2, const uint64_t* rhop, uint32_t n, cudaStream_t st);
+cudaError_t launch_t_pack(uint8_t* t1p, uint8_t* t0p, const int32_t* t, const int32_t* s2, size_t n_polys, cudaStream_t st);
+cudaError_t launch_s_pack(int eta, uint8_t* sp, const int32_t* s, size_t n_polys, cudaStream_t st);
+cudaError_t launch_tr_batch(uint8_t* tr, const uint8_t* rho, const uint8_t* t1p, uint32_t t1_bytes, uint32_t n, cudaStream_t st);
+
 }  // namespace dil

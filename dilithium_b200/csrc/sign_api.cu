@@ -549,3 +549,60 @@ int dil_verify_batch_host(dil_engine_t* e, dil_verify_key_t* k, const uint8_t* m
 }
 
 }  // extern "C"
+
+// =======================================================================================
+// Batched key generation (combined_top.v mode 0; outputs as rtl_tb/tb_keygen_top.v:180-275)
+// =======================================================================================
+extern "C" int dil_keygen_batch_host(dil_engine_t* e, int level, const uint8_t* xi, size_t n, uint8_t* rho, uint8_t* key,
+                                     uint8_t* tr, uint8_t* s1p, uint8_t* s2p, uint8_t* t1p, uint8_t* t0p) {
+    if (!e) return DIL_ERR_ARG;
+    if (level != 2 && level != 3 && level != 5) return DIL_ERR_ARG;
+    if (n == 0) return DIL_OK;
+    if (!xi || !rho || !key || !tr || !s1p || !s2p || !t1p || !t0p || n > 0x00FFFFFFu) return DIL_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    const LevelParams P = dil::level_params(level);
+    cudaStream_t st = e->host_stream;
+    const size_t K = P.k, L = P.l, sb = P.s_bytes;
+    // one transient arena for the whole batch
+    struct Seg { size_t off, bytes; };
+    size_t total = 0;
+    auto seg = [&](size_t bytes) { Seg s{total, bytes}; total += (bytes + 255) & ~(size_t)255; return s; };
+    Seg S_xi = seg(n * 32), S_rho = seg(n * 32), S_key = seg(n * 32), S_tr = seg(n * 32), S_rhop = seg(n * 64);
+    Seg S_s1 = seg(n * L * 1024), S_s2 = seg(n * K * 1024), S_t = seg(n * K * 1024);
+    Seg S_s1p = seg(n * L * sb), S_s2p = seg(n * K * sb), S_t1p = seg(n * K * 320), S_t0p = seg(n * K * 416);
+    uint8_t* base = nullptr;
+    cudaError_t aerr = cudaMalloc(reinterpret_cast<void**>(&base), total);
+    if (aerr != cudaSuccess) {
+        e->last_error = std::string("keygen arena: ") + cudaGetErrorString(aerr);
+        return DIL_ERR_ALLOC;
+    }
+    auto P8 = [&](Seg s) { return base + s.off; };
+    auto P32 = [&](Seg s) { return reinterpret_cast<int32_t*>(base + s.off); };
+    int rc = DIL_OK;
+    cudaError_t err = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+    A(cudaMemcpyAsync(P8(S_xi), xi, n * 32, cudaMemcpyHostToDevice, st));
+    A(dil::launch_keygen_seed(P8(S_rho), reinterpret_cast<uint64_t*>(P8(S_rhop)), P8(S_key), P8(S_xi), (uint32_t)n, st));
+    A(dil::launch_eta_sample(level, P32(S_s1), P32(S_s2), reinterpret_cast<const uint64_t*>(P8(S_rhop)), (uint32_t)n, st));
+    // t = INTT(ExpandA(rho) * NTT(s1)): per-item rho, A generated on chip
+    A(dil::launch_matvec_expand(P32(S_t), P8(S_rho), P32(S_s1), P.k, P.l, n, DIL_RHO_PER_ITEM | DIL_NTT_INPUT | DIL_INTT_OUTPUT,
+                                e->sm_count, st));
+    A(dil::launch_t_pack(P8(S_t1p), P8(S_t0p), P32(S_t), P32(S_s2), n * K, st));
+    A(dil::launch_s_pack(P.eta, P8(S_s1p), P32(S_s1), n * L, st));
+    A(dil::launch_s_pack(P.eta, P8(S_s2p), P32(S_s2), n * K, st));
+    A(dil::launch_tr_batch(P8(S_tr), P8(S_rho), P8(S_t1p), (uint32_t)(K * 320), (uint32_t)n, st));
+    A(cudaMemcpyAsync(rho, P8(S_rho), n * 32, cudaMemcpyDeviceToHost, st));
+    A(cudaMemcpyAsync(key, P8(S_key), n * 32, cudaMemcpyDeviceToHost, st));
+    A(cudaMemcpyAsync(tr, P8(S_tr), n * 32, cudaMemcpyDeviceToHost, st));
+    A(cudaMemcpyAsync(s1p, P8(S_s1p), n * L * sb, cudaMemcpyDeviceToHost, st));
+    A(cudaMemcpyAsync(s2p, P8(S_s2p), n * K * sb, cudaMemcpyDeviceToHost, st));
+    A(cudaMemcpyAsync(t1p, P8(S_t1p), n * K * 320, cudaMemcpyDeviceToHost, st));
+    A(cudaMemcpyAsync(t0p, P8(S_t0p), n * K * 416, cudaMemcpyDeviceToHost, st));
+    A(cudaStreamSynchronize(st));
+    if (err != cudaSuccess) rc = fail(e, err, "dil_keygen_batch_host");
+    else e->launches += 7;
+    cudaFree(base);
+    return rc;
+}

@@ -836,3 +836,173 @@ cudaError_t launch_verify_hash(int level, uint8_t* ok, const uint64_t* mu, const
 }
 
 }  // namespace dil
+
+// =======================================================================================
+// Key generation (rtl_src/combined_top.v:754-1079; outputs in the order of
+// rtl_tb/tb_keygen_top.v:180-275: rho, K, s1, s2, t1, t0, tr)
+// =======================================================================================
+namespace dil {
+
+// (rho, rho', K) = SHAKE256(xi)[0:128]  (combined_top.v:776, :805-827); thread per item
+__global__ void __launch_bounds__(128) keygen_seed_kernel(uint8_t* __restrict__ rho, uint64_t* __restrict__ rhop, uint8_t* __restrict__ key,
+                                                          const uint8_t* __restrict__ xi, uint32_t n) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    uint64_t A[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) A[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) A[i] = load_lane_bytes(xi + (size_t)t * 32, i * 8, 32);
+    A[4] = 0x1F;
+    A[16] = 0x80ULL << 56;
+    keccak_f1600(A);
+    uint64_t* r = reinterpret_cast<uint64_t*>(rho) + (size_t)t * 4;
+    uint64_t* kk = reinterpret_cast<uint64_t*>(key) + (size_t)t * 4;
+#pragma unroll
+    for (int i = 0; i < 4; i++) r[i] = A[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) rhop[(size_t)t * 8 + i] = A[4 + i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) kk[i] = A[12 + i];
+}
+
+// s1_j = RejEta(SHAKE256(rho' || u16le(j))), s2_i uses nonce l+i (gen_s.v:115, sampler_s.v:117-135,
+// rejection_s.v:47-51,:85-138); thread per polynomial; writes centred int32 coefficients
+template <int K, int L, int ETA>
+__global__ void __launch_bounds__(128) eta_sample_kernel(int32_t* __restrict__ s1, int32_t* __restrict__ s2,
+                                                         const uint64_t* __restrict__ rhop, uint32_t n) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * (K + L)) return;
+    const uint32_t item = t / (K + L), p = t % (K + L);
+    int32_t* out = p < L ? s1 + ((size_t)item * L + p) * N : s2 + ((size_t)item * K + (p - L)) * N;
+    uint64_t A[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) A[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) A[i] = rhop[(size_t)item * 8 + i];
+    A[8] = (uint64_t)p | (0x1FULL << 16);
+    A[16] = 0x80ULL << 56;
+    int cnt = 0;
+    while (cnt < N) {
+        keccak_f1600(A);
+#pragma unroll
+        for (int ln = 0; ln < 17; ln++) {
+            uint64_t v = A[ln];
+#pragma unroll
+            for (int nib = 0; nib < 16; nib++) {
+                uint32_t x = (uint32_t)(v >> (4 * nib)) & 15u;
+                if (ETA == 2) {
+                    if (x < 15 && cnt < N) out[cnt++] = 2 - (int32_t)(x - (205 * x >> 10) * 5);
+                } else {
+                    if (x < 9 && cnt < N) out[cnt++] = 4 - (int32_t)x;
+                }
+            }
+        }
+    }
+}
+
+// t = t + s2 (canonical); Power2Round (uncenter_coeff.v:54-55); pack t1 (10 bit) and 2^12 - t0 (13 bit).
+// One thread per 8 coefficients -> 10 + 13 bytes.
+__global__ void __launch_bounds__(256) t_pack_kernel(uint8_t* __restrict__ t1p, uint8_t* __restrict__ t0p, const int32_t* __restrict__ t,
+                                                     const int32_t* __restrict__ s2, size_t n_groups) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const int4* a = reinterpret_cast<const int4*>(t) + g * 2;
+    const int4* b = reinterpret_cast<const int4*>(s2) + g * 2;
+    int4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+    int32_t tv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    int32_t sv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint64_t hi10 = 0, lo10 = 0;   // 80 bits of t1
+    uint64_t p0 = 0, p1 = 0;       // 104 bits of t0
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        uint32_t x = csub((uint32_t)tv[c] + canon_signed(sv[c]));
+        uint32_t r1 = (x + (1u << (D_BITS - 1)) - 1) >> D_BITS;
+        uint32_t r0 = (uint32_t)((1 << (D_BITS - 1)) - ((int32_t)x - (int32_t)(r1 << D_BITS)));   // 2^12 - t0, 13 bits
+        const int q1 = 10 * c, q0 = 13 * c;
+        if (q1 < 64) { lo10 |= (uint64_t)r1 << q1; if (q1 + 10 > 64) hi10 |= (uint64_t)r1 >> (64 - q1); } else hi10 |= (uint64_t)r1 << (q1 - 64);
+        if (q0 < 64) { p0 |= (uint64_t)r0 << q0; if (q0 + 13 > 64) p1 |= (uint64_t)r0 >> (64 - q0); } else p1 |= (uint64_t)r0 << (q0 - 64);
+    }
+    uint8_t* d1 = t1p + g * 10;
+    uint8_t* d0 = t0p + g * 13;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d1[i] = (uint8_t)(lo10 >> (8 * i));
+    d1[8] = (uint8_t)hi10; d1[9] = (uint8_t)(hi10 >> 8);
+#pragma unroll
+    for (int i = 0; i < 8; i++) d0[i] = (uint8_t)(p0 >> (8 * i));
+#pragma unroll
+    for (int i = 0; i < 5; i++) d0[8 + i] = (uint8_t)(p1 >> (8 * i));
+}
+
+// pack eta - s (3 or 4 bits); one thread per 8 coefficients -> 3 or 4 bytes
+template <int ETA>
+__global__ void __launch_bounds__(256) s_pack_kernel(uint8_t* __restrict__ sp, const int32_t* __restrict__ s, size_t n_groups) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const int4* a = reinterpret_cast<const int4*>(s) + g * 2;
+    int4 a0 = a[0], a1 = a[1];
+    int32_t v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    constexpr int W = ETA == 2 ? 3 : 4;
+    uint32_t o = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) o |= (uint32_t)(ETA - v[c]) << (W * c);
+    uint8_t* d = sp + g * W;
+#pragma unroll
+    for (int i = 0; i < W; i++) d[i] = (uint8_t)(o >> (8 * i));
+}
+
+// tr = SHAKE256(rho || t1_packed)[0:32] per item
+__global__ void __launch_bounds__(128) tr_batch_kernel(uint8_t* __restrict__ tr, const uint8_t* __restrict__ rho,
+                                                       const uint8_t* __restrict__ t1p, uint32_t t1_bytes, uint32_t n) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint8_t* r = rho + (size_t)t * 32;
+    const uint8_t* p = t1p + (size_t)t * t1_bytes;
+    uint64_t A[25];
+    shake256_absorb_lanes(A, 32 + t1_bytes, [&](size_t idx) -> uint64_t {
+        if (idx < 4) return load_lane_bytes(r, idx * 8, 32);
+        return load_lane_bytes(p, (idx - 4) * 8, t1_bytes);
+    });
+    uint64_t* o = reinterpret_cast<uint64_t*>(tr) + (size_t)t * 4;
+#pragma unroll
+    for (int i = 0; i < 4; i++) o[i] = A[i];
+}
+
+cudaError_t launch_keygen_seed(uint8_t* rho, uint64_t* rhop, uint8_t* key, const uint8_t* xi, uint32_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    keygen_seed_kernel<<<(n + 127) / 128, 128, 0, st>>>(rho, rhop, key, xi, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_eta_sample(int level, int32_t* s1, int32_t* s2, const uint64_t* rhop, uint32_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const LevelParams P = level_params(level);
+    unsigned grid = (n * (P.k + P.l) + 127) / 128;
+    switch (level) {
+        case 2: eta_sample_kernel<4, 4, 2><<<grid, 128, 0, st>>>(s1, s2, rhop, n); break;
+        case 3: eta_sample_kernel<6, 5, 4><<<grid, 128, 0, st>>>(s1, s2, rhop, n); break;
+        case 5: eta_sample_kernel<8, 7, 2><<<grid, 128, 0, st>>>(s1, s2, rhop, n); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_t_pack(uint8_t* t1p, uint8_t* t0p, const int32_t* t, const int32_t* s2, size_t n_polys, cudaStream_t st) {
+    if (n_polys == 0) return cudaSuccess;
+    size_t n_groups = n_polys * 32;
+    t_pack_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(t1p, t0p, t, s2, n_groups);
+    return cudaGetLastError();
+}
+cudaError_t launch_s_pack(int eta, uint8_t* sp, const int32_t* s, size_t n_polys, cudaStream_t st) {
+    if (n_polys == 0) return cudaSuccess;
+    size_t n_groups = n_polys * 32;
+    unsigned grid = (unsigned)((n_groups + 255) / 256);
+    if (eta == 2) s_pack_kernel<2><<<grid, 256, 0, st>>>(sp, s, n_groups);
+    else s_pack_kernel<4><<<grid, 256, 0, st>>>(sp, s, n_groups);
+    return cudaGetLastError();
+}
+cudaError_t launch_tr_batch(uint8_t* tr, const uint8_t* rho, const uint8_t* t1p, uint32_t t1_bytes, uint32_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    tr_batch_kernel<<<(n + 127) / 128, 128, 0, st>>>(tr, rho, t1p, t1_bytes, n);
+    return cudaGetLastError();
+}
+
+}  // namespace dil

@@ -224,6 +224,22 @@ class Engine:
         self._check(rc, "dil_signcore_host")
         return w
 
+    def keygen(self, level, seeds):
+        """Batched key generation from 32-byte seeds xi (host path).  Returns a dict of uint8 arrays with the
+        KAT field names: rho, k, tr, s1, s2, t1, t0 (bit-packed as the reference's KAT files)."""
+        seeds = self._np(seeds, np.uint8).reshape(-1, 32)
+        n = seeds.shape[0]
+        k, l = LEVEL_DIMS[level]
+        sb = 128 if level == 3 else 96
+        out = dict(rho=np.empty((n, 32), np.uint8), k=np.empty((n, 32), np.uint8), tr=np.empty((n, 32), np.uint8),
+                   s1=np.empty((n, l * sb), np.uint8), s2=np.empty((n, k * sb), np.uint8),
+                   t1=np.empty((n, k * 320), np.uint8), t0=np.empty((n, k * 416), np.uint8))
+        P = ctypes.c_void_p
+        rc = self._lib.dil_keygen_batch_host(self._h, int(level), seeds.ctypes.data_as(P), n,
+                                             *[out[f].ctypes.data_as(P) for f in ("rho", "k", "tr", "s1", "s2", "t1", "t0")])
+        self._check(rc, "dil_keygen_batch_host")
+        return out
+
 
 class SignKey:
     """Expanded signing key on the device (ExpandA + NTT of s1, s2, t0 done once; LOAD_RHO / NTT_S1 /

@@ -154,6 +154,12 @@ int dil_verify_batch_host(dil_engine_t *e, dil_verify_key_t *k, const uint8_t *m
 int dil_verify_batch_dev(dil_engine_t *e, dil_verify_key_t *k, const uint8_t *d_msgs, const uint64_t *d_offsets, size_t n,
                          const uint8_t *d_z, const uint8_t *d_h, const uint8_t *d_ctilde, uint8_t *d_ok, void *stream);
 
+/* ---- batched key generation (combined_top.v mode 0, FSM :754-1079; outputs as tb_keygen_top.v:180-275) ----
+ * xi: n x 32-byte seeds.  Outputs per key, bit-packed exactly as the KAT files: rho, K, tr (32 B each),
+ * s1 (l polys), s2 (k polys) as eta - s, t1 (10 bit), t0 as 2^12 - t0 (13 bit). */
+int dil_keygen_batch_host(dil_engine_t *e, int level, const uint8_t *xi, size_t n, uint8_t *rho, uint8_t *key, uint8_t *tr,
+                          uint8_t *s1_packed, uint8_t *s2_packed, uint8_t *t1_packed, uint8_t *t0_packed);
+
 /* ---- north_star aliases (plain domain, identical to the above) ---- */
 int dil_invntt_tomont_dev(dil_engine_t *e, int32_t *dst, const int32_t *src, size_t n_polys, void *stream);
 int dil_poly_pointwise_dev(dil_engine_t *e, int32_t *c, const int32_t *a, const int32_t *b, size_t n_polys, void *stream);
