@@ -78,7 +78,8 @@ int dil_engine_create(dil_engine_t** out, int device) {
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
     DeviceGuard g(device);
-    if (!g.ok || cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (!g.ok || cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete e;
         return DIL_ERR_CUDA;
     }
@@ -93,6 +94,7 @@ int dil_engine_destroy(dil_engine_t* e) {
         for (auto& p : e->staging)
             if (p) cudaFree(p);
         if (e->host_stream) cudaStreamDestroy(e->host_stream);
+        if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     }
     delete e;
     return DIL_OK;

@@ -15,6 +15,7 @@ struct dil_engine {
     void* staging[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t staging_bytes[4] = {0, 0, 0, 0};
     cudaStream_t host_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // D2H of finished chunks overlaps compute of the next chunk
     std::string last_error;
 };
 

@@ -36,6 +36,7 @@ cudaError_t launch_resolve(int level, uint8_t* zp, uint8_t* h_out, uint64_t* ct_
                            const uint64_t* ct_slot, const uint8_t* accepted, const uint32_t* active, uint32_t n_items,
                            uint32_t spec, cudaStream_t st);
 cudaError_t launch_iota(uint32_t* dst, uint32_t n, cudaStream_t st);
+cudaError_t launch_publish_count(uint32_t* host_dst_dev, const uint32_t* src, cudaStream_t st);
 // ---- verify pipeline ----
 cudaError_t launch_verify_core(int32_t* w, const int32_t* a_ext, const int32_t* v, int level, size_t batch, int sm_count,
                                cudaStream_t st);

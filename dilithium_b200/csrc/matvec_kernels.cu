@@ -51,13 +51,20 @@ __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const in
                                           const uint32_t* __restrict__ a_sm, uint32_t* __restrict__ scr, int lane) {
     uint32_t yh[L][8];  // NTT-domain inputs in layout C
     if constexpr (NTT_IN) {
-        FwdTw ftw;
-        load_fwd_tw(ftw, &TW_FWD, lane);
 #pragma unroll
         for (int j = 0; j < L; j++) {
             const int32_t* p = v_item + j * N + lane;
 #pragma unroll
             for (int r = 0; r < 8; r++) yh[j][r] = (uint32_t)p[32 * r];  // layout A: 128-B line per access
+        }
+        FwdTw ftw;
+        {   // 2 KiB table, L1 resident; reloaded per item (opaque pointer defeats hoisting) to keep registers low
+            const TwTable* tab = &TW_FWD;
+            asm volatile("" : "+l"(tab));
+            load_fwd_tw(ftw, tab, lane);
+        }
+#pragma unroll
+        for (int j = 0; j < L; j++) {
             ntt_fwd_warp(yh[j], scr, ftw, lane);
             __syncwarp();
         }
@@ -70,8 +77,6 @@ __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const in
             yh[j][4] = canon_signed(hi.x); yh[j][5] = canon_signed(hi.y); yh[j][6] = canon_signed(hi.z); yh[j][7] = canon_signed(hi.w);
         }
     }
-    InvTw itw;
-    if constexpr (INTT_OUT) load_inv_tw(itw, &TW_INV, lane);
 #pragma unroll 1
     for (int i = 0; i < K; i++) {
         uint64_t acc[8];
@@ -90,6 +95,12 @@ __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const in
 #pragma unroll
         for (int r = 0; r < 8; r++) x[r] = reduce49(acc[r]);
         if constexpr (INTT_OUT) {
+            InvTw itw;
+            {
+                const TwTable* tab = &TW_INV;
+                asm volatile("" : "+l"(tab));
+                load_inv_tw(itw, tab, lane);
+            }
             ntt_inv_warp(x, scr, itw, lane);
             __syncwarp();
             int32_t* o = w_item + i * N + lane;
@@ -104,8 +115,13 @@ __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const in
 }
 
 // ---- shared-A persistent kernel ----
+// register budget: 2 CTAs/SM (<= 128 registers) for every level's shape, 1 for the 8 x 8 verification core.
+// (3 CTAs/SM at 80 registers was measured 5-9 % slower for levels 2/3: the kernel is bound by the
+// integer-multiply pipe, not by latency.)
+constexpr int shared_min_ctas(int k, int l) { return k * l <= 56 ? 2 : 1; }
+
 template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT>
-__global__ void __launch_bounds__(WARPS * 32) matvec_shared_kernel(int32_t* __restrict__ w, const int32_t* __restrict__ a_hat,
+__global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L)) matvec_shared_kernel(int32_t* __restrict__ w, const int32_t* __restrict__ a_hat,
                                                                    const uint8_t* __restrict__ rho,
                                                                    const int32_t* __restrict__ v, uint32_t batch) {
     extern __shared__ __align__(16) uint32_t smem_u32v[];
@@ -166,7 +182,7 @@ static cudaError_t launch_shared_t(int32_t* w, const int32_t* a_hat, const uint8
         configured = true;
     }
     int ctas_per_sm = (int)((220 * 1024) / smem);
-    if (ctas_per_sm > 2) ctas_per_sm = 2;
+    if (ctas_per_sm > shared_min_ctas(K, L)) ctas_per_sm = shared_min_ctas(K, L);
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     size_t want = (batch + WARPS - 1) / WARPS;
     size_t cap = (size_t)sm_count * ctas_per_sm;

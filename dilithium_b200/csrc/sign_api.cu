@@ -35,6 +35,8 @@ struct dil_sign_key {
     uint8_t *h_slot = nullptr, *accepted = nullptr;
     uint64_t* ct_slot = nullptr;
     size_t slots = 0;            // slot capacity of y/w/c/w1p/h_slot/ct_slot/accepted
+    uint32_t* count_host = nullptr;      // mapped pinned word the device publishes the next round's size into
+    uint32_t* count_host_dev = nullptr;  // its device alias
     // host-variant staging
     uint8_t *msgs_d = nullptr, *zp_d = nullptr, *h_d = nullptr, *ct_d = nullptr;
     uint64_t* off_d = nullptr;
@@ -187,9 +189,13 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
                                k->y, k->h_slot, k->ct_slot, k->accepted, k->active[cur], n_active, (uint32_t)spec, st));
         PROF_END(6, n_active);
         launches += 6;
-        uint32_t next = 0;
-        CK(cudaMemcpyAsync(&next, k->count, 4, cudaMemcpyDeviceToHost, st));
+        if (!k->count_host) {
+            CK(cudaHostAlloc(reinterpret_cast<void**>(&k->count_host), 64, cudaHostAllocMapped));
+            CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&k->count_host_dev), k->count_host, 0));
+        }
+        CK(dil::launch_publish_count(k->count_host_dev, k->count, st));
         CK(cudaStreamSynchronize(st));
+        const uint32_t next = *reinterpret_cast<volatile uint32_t*>(k->count_host);
         if (prof)
             for (int cls = 1; cls <= 6; cls++) {
                 float ms = 0;
@@ -281,6 +287,7 @@ int dil_sign_key_destroy(dil_engine_t* e, dil_sign_key_t* k) {
         if (p) cudaFree(p);
     for (auto& ev : k->ev)
         if (ev) cudaEventDestroy(ev);
+    if (k->count_host) cudaFreeHost(k->count_host);
     (void)e;
     delete k;
     return DIL_OK;
@@ -347,12 +354,38 @@ int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs,
     }
     CK(cudaMemcpyAsync(k->msgs_d, msgs, offsets[n], cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(k->off_d, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    int rc = sign_rounds(e, k, k->msgs_d, k->off_d, n, k->zp_d, k->h_d, k->ct_d, k->att_d, st);
+    // Chunked so that the D2H of a finished chunk's signatures (2.4-4.6 KB each, ~47 ns per signature over
+    // PCIe) overlaps the signing of the next chunk.  Signing has a fixed per-batch latency (rejection
+    // tail), so chunks are unequal: 64 K-message chunks while a lot remains, then a 3:1 split so that only
+    // the small last chunk's transfer is exposed.
+    std::vector<size_t> chunks;
+    {
+        size_t rem = n;
+        while (rem > 98304) { chunks.push_back(65536); rem -= 65536; }
+        if (rem > 16384) { size_t a = (rem * 3 / 4 + 255) & ~(size_t)255; chunks.push_back(a); chunks.push_back(rem - a); }
+        else chunks.push_back(rem);
+    }
+    cudaStream_t cs = e->copy_stream;
+    cudaEvent_t done = nullptr;
+    CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    int rc = DIL_OK;
+    size_t lo = 0;
+    for (size_t ci = 0; ci < chunks.size() && rc == DIL_OK; lo += chunks[ci], ci++) {
+        const size_t m = chunks[ci];
+        rc = sign_rounds(e, k, k->msgs_d, k->off_d + lo, m, k->zp_d + lo * zb, k->h_d + lo * hb, k->ct_d + lo * 32, k->att_d + lo, st);
+        if (rc) break;
+        cudaError_t er = cudaEventRecord(done, st);
+        if (er == cudaSuccess) er = cudaStreamWaitEvent(cs, done, 0);
+        if (er == cudaSuccess) er = cudaMemcpyAsync(z + lo * zb, k->zp_d + lo * zb, m * zb, cudaMemcpyDeviceToHost, cs);
+        if (er == cudaSuccess) er = cudaMemcpyAsync(h + lo * hb, k->h_d + lo * hb, m * hb, cudaMemcpyDeviceToHost, cs);
+        if (er == cudaSuccess) er = cudaMemcpyAsync(ctilde + lo * 32, k->ct_d + lo * 32, m * 32, cudaMemcpyDeviceToHost, cs);
+        if (er == cudaSuccess && attempts) er = cudaMemcpyAsync(attempts + lo, k->att_d + lo, m * 4, cudaMemcpyDeviceToHost, cs);
+        if (er != cudaSuccess) rc = fail(e, er, "sign D2H");
+    }
+    cudaError_t er2 = cudaStreamSynchronize(cs);
+    cudaEventDestroy(done);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(z, k->zp_d, n * zb, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h, k->h_d, n * hb, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(ctilde, k->ct_d, n * 32, cudaMemcpyDeviceToHost, st));
-    if (attempts) CK(cudaMemcpyAsync(attempts, k->att_d, n * 4, cudaMemcpyDeviceToHost, st));
+    if (er2 != cudaSuccess) return fail(e, er2, "sign D2H sync");
     CK(cudaStreamSynchronize(st));
     return DIL_OK;
 }

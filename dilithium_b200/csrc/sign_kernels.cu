@@ -499,11 +499,12 @@ cudaError_t launch_pack_w1(int level, uint32_t* w1p, const int32_t* w, uint32_t 
 cudaError_t launch_challenge(int level, int8_t* c, uint64_t* ct_slot, const uint64_t* mu, const uint64_t* w1p,
                              const uint32_t* active, uint32_t n_slots, uint32_t spec, cudaStream_t st) {
     if (n_slots == 0) return cudaSuccess;
-    unsigned grid = (n_slots + 127) / 128;
+    // 64-thread CTAs: 1024 CTAs for a 65536-slot round spread evenly over 148 SMs
+    unsigned grid = (n_slots + 63) / 64;
     switch (level) {
-        case 2: challenge_kernel<4, 192, 39><<<grid, 128, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
-        case 3: challenge_kernel<6, 128, 49><<<grid, 128, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
-        case 5: challenge_kernel<8, 128, 60><<<grid, 128, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
+        case 2: challenge_kernel<4, 192, 39><<<grid, 64, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
+        case 3: challenge_kernel<6, 128, 49><<<grid, 64, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
+        case 5: challenge_kernel<8, 128, 60><<<grid, 64, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -559,6 +560,16 @@ namespace dil {
 __global__ void iota_kernel(uint32_t* dst, uint32_t n) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) dst[t] = t;
+}
+// publish the next round's item count into mapped pinned host memory: a posted PCIe write, so the
+// host never queues a D2H copy behind the bulk signature transfers of the previous chunk
+__global__ void publish_count_kernel(volatile uint32_t* host_dst, const uint32_t* src) {
+    *host_dst = *src;
+    __threadfence_system();
+}
+cudaError_t launch_publish_count(uint32_t* host_dst_dev, const uint32_t* src, cudaStream_t st) {
+    publish_count_kernel<<<1, 1, 0, st>>>(host_dst_dev, src);
+    return cudaGetLastError();
 }
 cudaError_t launch_iota(uint32_t* dst, uint32_t n, cudaStream_t st) {
     if (n == 0) return cudaSuccess;

@@ -1,0 +1,39 @@
+"""The C++ host driver (examples/kat_driver.cpp) replays the reference's keygen / sign / verify
+testbenches over the C ABI.  The KAT files are re-materialised in the reference's hex format
+from the committed fixtures (the GPU box has no /root/reference)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _write_kat_dir(tmp, level, n):
+    K = ol.kat(level)
+    for stem in ("rho", "k", "tr", "z", "s1", "s2", "t0", "t1", "zs", "h", "c"):
+        with open(os.path.join(tmp, f"{stem}_{level}.txt"), "w") as f:
+            for i in range(n):
+                f.write(K[stem][i].tobytes().hex().upper() + "\n")
+    with open(os.path.join(tmp, f"m_{level}.txt"), "w") as f:
+        for i in range(n):
+            f.write(K["msgs"][i].ljust(3300, b"\0").hex().upper() + "\n")   # zero padded like the reference's m_*.txt
+    with open(os.path.join(tmp, f"mlen_{level}.txt"), "w") as f:
+        for i in range(n):
+            f.write(f"{len(K['msgs'][i]):04X}\n")
+
+
+@pytest.mark.parametrize("level", [2, 3, 5])
+def test_cpp_driver_replays_testbenches(tmp_path, level):
+    exe = os.path.join(ROOT, "examples", "kat_driver")
+    if not os.path.exists(exe):
+        pytest.skip("examples/kat_driver not built")
+    n = 100 if level == 2 else 25
+    _write_kat_dir(str(tmp_path), level, n)
+    out = subprocess.run([exe, str(tmp_path), str(level), str(n)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "MISMATCH" not in out.stdout and out.stdout.count("completed") == 3, out.stdout
