@@ -14,6 +14,8 @@
 // HBM traffic per item is (l + k) KiB (+32 B of rho); A never touches HBM.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "dilithium_b200.h"
 #include "keccak.cuh"
 #include "kernels.h"
@@ -118,10 +120,10 @@ __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const in
 // register budget: 2 CTAs/SM (<= 128 registers) for every level's shape, 1 for the 8 x 8 verification core.
 // (3 CTAs/SM at 80 registers was measured 5-9 % slower for levels 2/3: the kernel is bound by the
 // integer-multiply pipe, not by latency.)
-constexpr int shared_min_ctas(int k, int l) { return k * l <= 56 ? 2 : 1; }
+constexpr int shared_min_ctas(int k, int l, int warps = 8) { return warps > 8 ? 1 : (k * l <= 56 ? 2 : 1); }
 
 template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT>
-__global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L)) matvec_shared_kernel(int32_t* __restrict__ w, const int32_t* __restrict__ a_hat,
+__global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L, WARPS)) matvec_shared_kernel(int32_t* __restrict__ w, const int32_t* __restrict__ a_hat,
                                                                    const uint8_t* __restrict__ rho,
                                                                    const int32_t* __restrict__ v, uint32_t batch) {
     extern __shared__ __align__(16) uint32_t smem_u32v[];
@@ -182,7 +184,7 @@ static cudaError_t launch_shared_t(int32_t* w, const int32_t* a_hat, const uint8
         configured = true;
     }
     int ctas_per_sm = (int)((220 * 1024) / smem);
-    if (ctas_per_sm > shared_min_ctas(K, L)) ctas_per_sm = shared_min_ctas(K, L);
+    if (ctas_per_sm > shared_min_ctas(K, L, WARPS)) ctas_per_sm = shared_min_ctas(K, L, WARPS);
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     size_t want = (batch + WARPS - 1) / WARPS;
     size_t cap = (size_t)sm_count * ctas_per_sm;
@@ -195,7 +197,13 @@ template <int K, int L, bool EXPAND>
 static cudaError_t launch_shared_flags(int32_t* w, const int32_t* a_hat, const uint8_t* rho, const int32_t* v, size_t batch,
                                        bool ntt_in, bool intt_out, int sm_count, cudaStream_t st) {
     constexpr int WARPS = 8;
-    if (ntt_in && intt_out) return launch_shared_t<K, L, WARPS, EXPAND, true, true>(w, a_hat, rho, v, batch, sm_count, st);
+    if (ntt_in && intt_out) {
+        // one 16-warp CTA per SM measured 3-5 % faster than two 8-warp CTAs (DIL_SC_WARPS=8 selects the latter)
+        static int big = -1;
+        if (big < 0) { const char* e = std::getenv("DIL_SC_WARPS"); big = (e && std::atoi(e) == 8) ? 0 : 1; }
+        if (big) return launch_shared_t<K, L, 16, EXPAND, true, true>(w, a_hat, rho, v, batch, sm_count, st);
+        return launch_shared_t<K, L, WARPS, EXPAND, true, true>(w, a_hat, rho, v, batch, sm_count, st);
+    }
     if (ntt_in) return launch_shared_t<K, L, WARPS, EXPAND, true, false>(w, a_hat, rho, v, batch, sm_count, st);
     if (intt_out) return launch_shared_t<K, L, WARPS, EXPAND, false, true>(w, a_hat, rho, v, batch, sm_count, st);
     return launch_shared_t<K, L, WARPS, EXPAND, false, false>(w, a_hat, rho, v, batch, sm_count, st);

@@ -12,6 +12,8 @@
 // 1 KiB in + 1 KiB out per polynomial, always as whole aligned 1 KiB bursts.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ntt_core.cuh"
 #include "tma.cuh"
@@ -107,26 +109,50 @@ ntt_tma_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ src, uint3
 }
 
 // ---- launch configuration ----
-constexpr int NTT_WARPS = 8;
-constexpr int NTT_STAGES = 3;
-constexpr int NTT_CTAS_PER_SM = 4;
-
-template <bool INVERSE>
-static cudaError_t launch_ntt(int32_t* dst, const int32_t* src, size_t n_polys, int sm_count, cudaStream_t st) {
-    if (n_polys == 0) return cudaSuccess;
-    using Smem = NttSmem<NTT_WARPS, NTT_STAGES>;
-    auto kern = ntt_tma_kernel<NTT_WARPS, NTT_STAGES, NTT_CTAS_PER_SM, INVERSE>;
+// Default: ONE 32-warp CTA per SM, 3 stages (32 resident polynomials per SM).  Measured at 2^18 polys
+// (fraction of the 6482.7 GB/s HBM peak, forward / inverse): 32w x 1 CTA 0.846 / 0.801, 16w x 2 0.816 / 0.781,
+// 8w x 4 0.785 / 0.757, 4w x 8 0.771 / 0.747; 4 stages change nothing, forcing <= 48 registers for 5-6 CTAs
+// of 8 warps loses 10-18 %.  DIL_NTT_CFG=<n> selects the alternative shapes (development knob).
+template <int WARPS, int STAGES, int CTAS, bool INVERSE>
+static cudaError_t launch_ntt_cfg(int32_t* dst, const int32_t* src, size_t n_polys, int sm_count, cudaStream_t st) {
+    using Smem = NttSmem<WARPS, STAGES>;
+    auto kern = ntt_tma_kernel<WARPS, STAGES, CTAS, INVERSE>;
     static bool configured = false;  // per-process; attribute is per-function and idempotent
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    size_t want = (n_polys + NTT_WARPS - 1) / NTT_WARPS;
-    size_t cap = (size_t)sm_count * NTT_CTAS_PER_SM;
+    size_t want = (n_polys + WARPS - 1) / WARPS;
+    size_t cap = (size_t)sm_count * CTAS;
     unsigned grid = (unsigned)(want < cap ? want : cap);
-    kern<<<grid, NTT_WARPS * 32, sizeof(Smem), st>>>(dst, src, (uint32_t)n_polys);
+    kern<<<grid, WARPS * 32, sizeof(Smem), st>>>(dst, src, (uint32_t)n_polys);
     return cudaGetLastError();
+}
+
+static int ntt_cfg() {
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char* e = std::getenv("DIL_NTT_CFG");
+        cfg = e ? std::atoi(e) : 0;
+    }
+    return cfg;
+}
+
+template <bool INVERSE>
+static cudaError_t launch_ntt(int32_t* dst, const int32_t* src, size_t n_polys, int sm_count, cudaStream_t st) {
+    if (n_polys == 0) return cudaSuccess;
+    switch (ntt_cfg()) {
+        case 1: return launch_ntt_cfg<32, 3, 1, INVERSE>(dst, src, n_polys, sm_count, st);
+        case 2: return launch_ntt_cfg<4, 3, 8, INVERSE>(dst, src, n_polys, sm_count, st);
+        case 3: return launch_ntt_cfg<8, 4, 4, INVERSE>(dst, src, n_polys, sm_count, st);
+        case 4: return launch_ntt_cfg<16, 4, 2, INVERSE>(dst, src, n_polys, sm_count, st);
+        case 5: return launch_ntt_cfg<16, 3, 2, INVERSE>(dst, src, n_polys, sm_count, st);
+        case 6: return launch_ntt_cfg<32, 4, 1, INVERSE>(dst, src, n_polys, sm_count, st);
+        case 7: return launch_ntt_cfg<16, 5, 2, INVERSE>(dst, src, n_polys, sm_count, st);
+        case 8: return launch_ntt_cfg<8, 3, 4, INVERSE>(dst, src, n_polys, sm_count, st);
+        default: return launch_ntt_cfg<32, 3, 1, INVERSE>(dst, src, n_polys, sm_count, st);
+    }
 }
 
 cudaError_t launch_ntt_fwd(int32_t* dst, const int32_t* src, size_t n, int sms, cudaStream_t st) {

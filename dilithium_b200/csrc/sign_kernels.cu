@@ -13,6 +13,8 @@
 // items are compacted into the next round's active list.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "dil_params.h"
 #include "keccak.cuh"
 #include "kernels.h"
@@ -263,8 +265,8 @@ __global__ void __launch_bounds__(128) challenge_kernel(int8_t* __restrict__ c_o
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ int32_t centre(uint32_t a) { return (int32_t)a - (int32_t)((a > (Q - 1) / 2) ? Q : 0); }
 
-template <int K, int L, int32_t GAMMA1, int32_t GAMMA2, int BETA, int OMEGA, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 3) sign_tail_kernel(
+template <int K, int L, int32_t GAMMA1, int32_t GAMMA2, int BETA, int OMEGA, int WARPS, int CTAS>
+__global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
     int32_t* __restrict__ y /* in: y, out: z (in place) */, uint8_t* __restrict__ h_slot, uint8_t* __restrict__ accepted,
     const int32_t* __restrict__ key_hat, const int32_t* __restrict__ w, const int8_t* __restrict__ c, uint32_t n_slots) {
     extern __shared__ __align__(16) uint32_t sm_words[];
@@ -510,12 +512,11 @@ cudaError_t launch_challenge(int level, int8_t* c, uint64_t* ct_slot, const uint
     return cudaGetLastError();
 }
 
-template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA>
-static cudaError_t launch_sign_tail_t(int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat, const int32_t* w,
+template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA, int WARPS, int CTAS>
+static cudaError_t launch_sign_tail_w(int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat, const int32_t* w,
                                       const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st) {
-    constexpr int WARPS = 8;
     constexpr size_t smem = (size_t)((L + 2 * K) * N + WARPS * SCRATCH_WORDS + WARPS * K * 8) * 4;
-    auto kern = sign_tail_kernel<K, L, G1, G2, BETA, OMEGA, WARPS>;
+    auto kern = sign_tail_kernel<K, L, G1, G2, BETA, OMEGA, WARPS, CTAS>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -523,9 +524,19 @@ static cudaError_t launch_sign_tail_t(int32_t* y, uint8_t* h_slot, uint8_t* acce
         configured = true;
     }
     unsigned want = (n_slots + WARPS - 1) / WARPS;
-    unsigned cap = (unsigned)sm_count * 3;
+    unsigned cap = (unsigned)sm_count * CTAS;
     kern<<<want < cap ? want : cap, WARPS * 32, smem, st>>>(y, h_slot, accepted, key_hat, w, c, n_slots);
     return cudaGetLastError();
+}
+
+template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA>
+static cudaError_t launch_sign_tail_t(int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat, const int32_t* w,
+                                      const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st) {
+    // one 24-warp CTA per SM is marginally faster than three 8-warp CTAs (DIL_TAIL_WARPS=8 selects the latter)
+    static int big = -1;
+    if (big < 0) { const char* e = std::getenv("DIL_TAIL_WARPS"); big = (e && std::atoi(e) == 8) ? 0 : 1; }
+    if (big) return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 24, 1>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st);
+    return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 8, 3>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st);
 }
 
 cudaError_t launch_sign_tail(int level, int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat,
