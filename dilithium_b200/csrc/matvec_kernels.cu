@@ -103,7 +103,7 @@ __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const in
                 asm volatile("" : "+l"(tab));
                 load_inv_tw(itw, tab, lane);
             }
-            ntt_inv_warp(x, scr, itw, lane);
+            ntt_inv_warp<true>(x, scr, itw, lane);   // a_sm carries the 256^-1 factor
             __syncwarp();
             int32_t* o = w_item + i * N + lane;
 #pragma unroll
@@ -130,17 +130,20 @@ __global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L, WARPS)) matv
     uint32_t* a_sm = smem_u32v;                               // K*L*A_STRIDE
     uint32_t* scr_all = smem_u32v + K * L * A_STRIDE;         // WARPS*SCRATCH_WORDS
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // When the output is inverse-transformed the matrix is stored pre-multiplied by 256^-1 (once per CTA),
+    // which removes the scaling multiplications from every inverse transform (ntt_inv_warp<true>).
+    auto scale = [](uint32_t v) -> uint32_t { return INTT_OUT ? mul_full(v, INV256) : v; };
     if constexpr (EXPAND) {
         for (int t = threadIdx.x; t < K * L; t += blockDim.x) {
             uint32_t* out = a_sm + t * A_STRIDE;
-            expand_a_poly(rho, t / L, t % L, [&](int idx, uint32_t val) { out[idx] = val; });
+            expand_a_poly(rho, t / L, t % L, [&](int idx, uint32_t val) { out[idx] = scale(val); });
         }
     } else {
         for (int t = threadIdx.x; t < K * L * (N / 4); t += blockDim.x) {
             int p = t >> 6, c = t & 63;
             int4 q = __ldg(reinterpret_cast<const int4*>(a_hat) + t);
             reinterpret_cast<uint4*>(a_sm + p * A_STRIDE)[c] =
-                make_uint4(canon_signed(q.x), canon_signed(q.y), canon_signed(q.z), canon_signed(q.w));
+                make_uint4(scale(canon_signed(q.x)), scale(canon_signed(q.y)), scale(canon_signed(q.z)), scale(canon_signed(q.w)));
         }
     }
     __syncthreads();
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(((K * L + 31) / 32) * 32) matvec_item_kernel(i
     const int t = threadIdx.x;
     if (t < K * L) {
         uint32_t* out = a_sm + t * A_STRIDE;
-        expand_a_poly(rho + item * 32, t / L, t % L, [&](int idx, uint32_t val) { out[idx] = val; });
+        expand_a_poly(rho + item * 32, t / L, t % L, [&](int idx, uint32_t val) { out[idx] = INTT_OUT ? mul_full(val, INV256) : val; });
     }
     __syncthreads();
     if (t < 32) item_core<K, L, NTT_IN, INTT_OUT>(w + item * K * N, v + item * L * N, a_sm, scr, t);

@@ -192,7 +192,11 @@ __device__ __forceinline__ void ntt_fwd_warp(uint32_t (&x)[8], uint32_t* __restr
 
 // Inverse NTT incl. 256^-1.  in: x in layout C, representatives in (-Q, Q) (bit-reversed order).
 //                            out: x in layout A, canonical [0, Q), natural order.
+// PRESCALED = true: the caller has already folded 256^-1 into the NTT-domain input (the fused kernels
+// scale their shared-memory matrix / key polynomials once per CTA), so the sum path of the last layer
+// needs only a canonicalisation instead of a Shoup multiplication (12 of ~180 multiply slots per transform).
 // The caller must __syncwarp() before the scratch is reused by another transform.
+template <bool PRESCALED = false>
 __device__ __forceinline__ void ntt_inv_warp(uint32_t (&x)[8], uint32_t* __restrict__ scr, const InvTw& tw, int lane) {
     // phase C: spans 1, 2
     gs_first(x[0], x[1], tw.s1[0]); gs_first(x[2], x[3], tw.s1[1]); gs_first(x[4], x[5], tw.s1[2]); gs_first(x[6], x[7], tw.s1[3]);
@@ -226,8 +230,13 @@ __device__ __forceinline__ void ntt_inv_warp(uint32_t (&x)[8], uint32_t* __restr
     for (int r = 0; r < 4; r++) {
         uint32_t d = x[r] + 256 * Q - x[r + 4];
         uint32_t s = x[r] + x[r + 4];
-        x[r] = csub(mul_shoup(s, ZLast::f, ZLast::fp));
-        x[r + 4] = csub(mul_shoup(d, ZLast::wf, ZLast::wfp));
+        if constexpr (PRESCALED) {
+            x[r] = canon_small(s);
+            x[r + 4] = csub(mul_shoup(d, ZI<1>::w, ZI<1>::wp));
+        } else {
+            x[r] = csub(mul_shoup(s, ZLast::f, ZLast::fp));
+            x[r + 4] = csub(mul_shoup(d, ZLast::wf, ZLast::wfp));
+        }
     }
 }
 

@@ -275,9 +275,12 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
     uint32_t* scr_all = sm_words + NKEY * N;           // WARPS * SCRATCH_WORDS
     uint32_t* hm_all = scr_all + WARPS * SCRATCH_WORDS;  // WARPS * K * 8 hint masks
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // key polynomials are kept pre-multiplied by 256^-1 so that every inverse transform below can skip
+    // its scaling multiplications (ntt_inv_warp<true>)
     for (int t = threadIdx.x; t < NKEY * (N / 4); t += blockDim.x) {
         int4 q = __ldg(reinterpret_cast<const int4*>(key_hat) + t);
-        reinterpret_cast<uint4*>(key_sm)[t] = make_uint4(canon_signed(q.x), canon_signed(q.y), canon_signed(q.z), canon_signed(q.w));
+        reinterpret_cast<uint4*>(key_sm)[t] = make_uint4(mul_full(canon_signed(q.x), INV256), mul_full(canon_signed(q.y), INV256),
+                                                         mul_full(canon_signed(q.z), INV256), mul_full(canon_signed(q.w), INV256));
     }
     __syncthreads();
     uint32_t* scr = scr_all + warp * SCRATCH_WORDS;
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
             uint4 lo = kp[0], hi = kp[32];
             x[0] = mul_full(ch[0], lo.x); x[1] = mul_full(ch[1], lo.y); x[2] = mul_full(ch[2], lo.z); x[3] = mul_full(ch[3], lo.w);
             x[4] = mul_full(ch[4], hi.x); x[5] = mul_full(ch[5], hi.y); x[6] = mul_full(ch[6], hi.z); x[7] = mul_full(ch[7], hi.w);
-            ntt_inv_warp(x, scr, itw, lane);
+            ntt_inv_warp<true>(x, scr, itw, lane);
             __syncwarp();
         };
         bool bad = false;
