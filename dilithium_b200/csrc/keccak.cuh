@@ -48,19 +48,18 @@ __device__ __forceinline__ void keccak_f1600(uint64_t (&A)[25]) {
     constexpr int RHO[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
 #pragma unroll 1
     for (int r = 0; r < 24; r++) {
-        uint64_t C[5], B[25];
+        uint64_t C[5], R1[5], B[25];
 #pragma unroll
         for (int x = 0; x < 5; x++) C[x] = A[x] ^ A[x + 5] ^ A[x + 10] ^ A[x + 15] ^ A[x + 20];
 #pragma unroll
-        for (int x = 0; x < 5; x++) {
-            uint64_t D = C[(x + 4) % 5] ^ rotl64(C[(x + 1) % 5], 1);
-#pragma unroll
-            for (int y = 0; y < 5; y++) A[x + 5 * y] ^= D;
-        }
+        for (int x = 0; x < 5; x++) R1[x] = rotl64(C[x], 1);
+        // theta folded into the rho/pi input: A ^ C[x-1] ^ rot(C[x+1],1) is one three-input LOP3 per half,
+        // so the five D words are never materialised (10 LOP3 fewer per round)
 #pragma unroll
         for (int x = 0; x < 5; x++)
 #pragma unroll
-            for (int y = 0; y < 5; y++) B[y + 5 * ((2 * x + 3 * y) % 5)] = rotl64(A[x + 5 * y], RHO[x + 5 * y]);
+            for (int y = 0; y < 5; y++)
+                B[y + 5 * ((2 * x + 3 * y) % 5)] = rotl64(A[x + 5 * y] ^ C[(x + 4) % 5] ^ R1[(x + 1) % 5], RHO[x + 5 * y]);
 #pragma unroll
         for (int y = 0; y < 5; y++)
 #pragma unroll

@@ -282,7 +282,11 @@ static cudaError_t launch_ntt(int32_t* dst, const int32_t* src, size_t n_polys, 
         case 9: return launch_ntt_pair<24, INVERSE>(dst, src, n_polys, sm_count, st);
         case 10: return launch_ntt_pair<16, INVERSE>(dst, src, n_polys, sm_count, st);
         case 11: return launch_ntt_pair<28, INVERSE>(dst, src, n_polys, sm_count, st);
-        default: return launch_ntt_cfg<32, 3, 1, INVERSE>(dst, src, n_polys, sm_count, st);
+        case 12: return launch_ntt_cfg<32, 3, 1, INVERSE>(dst, src, n_polys, sm_count, st);
+        default:
+            // forward: one polynomial per warp iteration; inverse: the pair variant measured 2 % faster
+            if (INVERSE) return launch_ntt_pair<24, INVERSE>(dst, src, n_polys, sm_count, st);
+            return launch_ntt_cfg<32, 3, 1, INVERSE>(dst, src, n_polys, sm_count, st);
     }
 }
 
