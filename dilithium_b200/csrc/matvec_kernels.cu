@@ -48,9 +48,14 @@ cudaError_t launch_expand_a(int32_t* a_hat, const uint8_t* rho, size_t n_rho, in
 
 // ---- per-item core, executed by one warp ----
 // v_item: l polys (global), w_item: k polys (global), a_sm: k*l polys in shared memory (stride A_STRIDE)
-template <int K, int L, bool NTT_IN, bool INTT_OUT>
+// EXTRA = true (verification with per-item public keys): v_item holds L+1 polynomials, and the last one is
+// multiplied by a per-item column extra_item[i] read from global memory (-NTT(t1_i * 2^13)) instead of a
+// shared-memory matrix column.
+template <int K, int LA, bool NTT_IN, bool INTT_OUT, bool EXTRA = false>
 __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const int32_t* __restrict__ v_item,
-                                          const uint32_t* __restrict__ a_sm, uint32_t* __restrict__ scr, int lane) {
+                                          const uint32_t* __restrict__ a_sm, uint32_t* __restrict__ scr, int lane,
+                                          const int32_t* __restrict__ extra_item = nullptr) {
+    constexpr int L = LA + (EXTRA ? 1 : 0);   // number of input polynomials
     uint32_t yh[L][8];  // NTT-domain inputs in layout C
     if constexpr (NTT_IN) {
 #pragma unroll
@@ -86,8 +91,18 @@ __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const in
         for (int r = 0; r < 8; r++) acc[r] = 0;
 #pragma unroll
         for (int j = 0; j < L; j++) {
-            const uint4* ap = reinterpret_cast<const uint4*>(a_sm + (i * L + j) * A_STRIDE) + lane;
-            uint4 lo = ap[0], hi = ap[32];
+            uint4 lo, hi;
+            if (EXTRA && j == LA) {
+                const int4* ep = reinterpret_cast<const int4*>(extra_item + i * N) + lane;
+                int4 elo = __ldg(ep), ehi = __ldg(ep + 32);
+                auto sc = [](int32_t x) -> uint32_t { return INTT_OUT ? mul_full(canon_signed(x), INV256) : canon_signed(x); };
+                lo = make_uint4(sc(elo.x), sc(elo.y), sc(elo.z), sc(elo.w));
+                hi = make_uint4(sc(ehi.x), sc(ehi.y), sc(ehi.z), sc(ehi.w));
+            } else {
+                const uint4* ap = reinterpret_cast<const uint4*>(a_sm + (i * LA + j) * A_STRIDE) + lane;
+                lo = ap[0];
+                hi = ap[32];
+            }
             acc[0] += (uint64_t)lo.x * yh[j][0]; acc[1] += (uint64_t)lo.y * yh[j][1];
             acc[2] += (uint64_t)lo.z * yh[j][2]; acc[3] += (uint64_t)lo.w * yh[j][3];
             acc[4] += (uint64_t)hi.x * yh[j][4]; acc[5] += (uint64_t)hi.y * yh[j][5];
@@ -152,22 +167,41 @@ __global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L, WARPS)) matv
         item_core<K, L, NTT_IN, INTT_OUT>(w + (size_t)item * K * N, v + (size_t)item * L * N, a_sm, scr, lane);
 }
 
-// ---- per-item-rho kernel: one CTA per item ----
-template <int K, int L, bool NTT_IN, bool INTT_OUT>
-__global__ void __launch_bounds__(((K * L + 31) / 32) * 32) matvec_item_kernel(int32_t* __restrict__ w,
-                                                                             const uint8_t* __restrict__ rho,
-                                                                             const int32_t* __restrict__ v) {
+// ---- per-item-rho kernel: G items per CTA ----
+// G*K*L threads expand the G matrices (one Keccak state per thread; G is chosen so that the Keccak
+// phase fills whole warps: level 2 has only 16 polynomials per item), then each warp of the CTA runs
+// the per-item core for its share of the G items.
+template <int K, int L>
+constexpr int item_group() { return K * L == 16 ? 4 : 1; }
+
+template <int K, int L, int G, bool NTT_IN, bool INTT_OUT, bool EXTRA = false>
+__global__ void __launch_bounds__(((G * K * L + 31) / 32) * 32) matvec_item_kernel(int32_t* __restrict__ w,
+                                                                                 const uint8_t* __restrict__ rho,
+                                                                                 const int32_t* __restrict__ v, uint32_t batch,
+                                                                                 const int32_t* __restrict__ extra = nullptr) {
     extern __shared__ __align__(16) uint32_t smem_u32v[];
-    uint32_t* a_sm = smem_u32v;
-    uint32_t* scr = smem_u32v + K * L * A_STRIDE;
-    const size_t item = blockIdx.x;
+    constexpr int NW = (G * K * L + 31) / 32;
+    uint32_t* a_sm = smem_u32v;                                   // G * K*L * A_STRIDE
+    uint32_t* scr_all = smem_u32v + G * K * L * A_STRIDE;         // NW * SCRATCH_WORDS
     const int t = threadIdx.x;
-    if (t < K * L) {
-        uint32_t* out = a_sm + t * A_STRIDE;
-        expand_a_poly(rho + item * 32, t / L, t % L, [&](int idx, uint32_t val) { out[idx] = INTT_OUT ? mul_full(val, INV256) : val; });
+    const size_t item0 = (size_t)blockIdx.x * G;
+    if (t < G * K * L) {
+        const int g = t / (K * L), ij = t % (K * L);
+        if (item0 + g < batch) {
+            uint32_t* out = a_sm + t * A_STRIDE;
+            expand_a_poly(rho + (item0 + g) * 32, ij / L, ij % L,
+                          [&](int idx, uint32_t val) { out[idx] = INTT_OUT ? mul_full(val, INV256) : val; });
+        }
     }
     __syncthreads();
-    if (t < 32) item_core<K, L, NTT_IN, INTT_OUT>(w + item * K * N, v + item * L * N, a_sm, scr, t);
+    const int warp = t >> 5, lane = t & 31;
+    for (int g = warp; g < G; g += NW) {
+        const size_t item = item0 + g;
+        if (item < batch)
+            item_core<K, L, NTT_IN, INTT_OUT, EXTRA>(w + item * K * N, v + item * (L + (EXTRA ? 1 : 0)) * N,
+                                                     a_sm + g * K * L * A_STRIDE, scr_all + warp * SCRATCH_WORDS, lane,
+                                                     EXTRA ? extra + item * K * N : nullptr);
+    }
 }
 
 template <int K, int L>
@@ -214,16 +248,18 @@ static cudaError_t launch_shared_flags(int32_t* w, const int32_t* a_hat, const u
 
 template <int K, int L, bool NTT_IN, bool INTT_OUT>
 static cudaError_t launch_item_t(int32_t* w, const uint8_t* rho, const int32_t* v, size_t batch, cudaStream_t st) {
-    auto kern = matvec_item_kernel<K, L, NTT_IN, INTT_OUT>;
-    constexpr size_t smem = (size_t)(K * L * A_STRIDE + SCRATCH_WORDS) * 4;
+    constexpr int G = item_group<K, L>();
+    constexpr int NW = (G * K * L + 31) / 32;
+    auto kern = matvec_item_kernel<K, L, G, NTT_IN, INTT_OUT>;
+    constexpr size_t smem = (size_t)(G * K * L * A_STRIDE + NW * SCRATCH_WORDS) * 4;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    constexpr int threads = ((K * L + 31) / 32) * 32;
-    kern<<<(unsigned)batch, threads, smem, st>>>(w, rho, v);
+    constexpr int threads = NW * 32;
+    kern<<<(unsigned)((batch + G - 1) / G), threads, smem, st>>>(w, rho, v, (uint32_t)batch, nullptr);
     return cudaGetLastError();
 }
 
@@ -261,6 +297,34 @@ cudaError_t launch_signcore(int32_t* w, const int32_t* a_hat, const int32_t* y, 
     return cudaErrorInvalidValue;
 }
 
+
+// verification core with per-item public keys: A from rho[item] on chip, extra column t1neg_hat[item] from HBM
+template <int K, int L>
+static cudaError_t launch_verify_item_t(int32_t* w, const uint8_t* rho, const int32_t* v, const int32_t* extra, size_t batch,
+                                        cudaStream_t st) {
+    constexpr int G = item_group<K, L>();
+    constexpr int NW = (G * K * L + 31) / 32;
+    auto kern = matvec_item_kernel<K, L, G, true, true, true>;
+    constexpr size_t smem = (size_t)(G * K * L * A_STRIDE + NW * SCRATCH_WORDS) * 4;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<(unsigned)((batch + G - 1) / G), NW * 32, smem, st>>>(w, rho, v, (uint32_t)batch, extra);
+    return cudaGetLastError();
+}
+cudaError_t launch_verify_core_item(int32_t* w, const uint8_t* rho, const int32_t* v, const int32_t* extra, int level,
+                                    size_t batch, cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    switch (level) {
+        case 2: return launch_verify_item_t<4, 4>(w, rho, v, extra, batch, st);
+        case 3: return launch_verify_item_t<6, 5>(w, rho, v, extra, batch, st);
+        case 5: return launch_verify_item_t<8, 7>(w, rho, v, extra, batch, st);
+    }
+    return cudaErrorInvalidValue;
+}
 
 // verification core: k x (l+1) matrix [A_hat | -t1_hat*2^13], inputs [z_0..z_{l-1}, c] in the time domain
 cudaError_t launch_verify_core(int32_t* w, const int32_t* a_ext, const int32_t* v, int level, size_t batch, int sm_count,

@@ -66,30 +66,49 @@ cudaError_t launch_elementwise(EwOp op, int32_t* c, const int32_t* a, const int3
 // 16..56 KiB and shared by the whole batch, so it lives in L1/L2), accumulates each output
 // row in 64-bit and reduces once per output coefficient.  HBM traffic is exactly
 // (l + k) KiB per item.
-template <int K, int L>
+template <int K, int L, int ITEMS>
 __global__ void __launch_bounds__(256) matvec_kernel(int4* __restrict__ w, const int4* __restrict__ a_hat,
-                                                     const int4* __restrict__ v, size_t n_slices) {
+                                                     const int4* __restrict__ v, size_t batch) {
+    // a thread owns one 4-coefficient column slice of ITEMS consecutive batch items, so every slice of A it
+    // pulls through L1 is used ITEMS times (A re-reads, not HBM, bound the level-3/5 shapes otherwise)
+    const size_t n_groups = (batch + ITEMS - 1) / ITEMS;
+    const size_t n_slices = n_groups * 64;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_slices; t += stride) {
-        size_t item = t >> 6;
-        unsigned col = (unsigned)(t & 63);
-        const int4* vi = v + item * (size_t)(L * 64) + col;
-        uint4 vr[L];
+        const size_t item0 = (t >> 6) * ITEMS;
+        const unsigned col = (unsigned)(t & 63);
+        uint4 vr[ITEMS][L];
 #pragma unroll
-        for (int j = 0; j < L; j++) vr[j] = canon4(vi[j * 64]);
-        int4* wi = w + item * (size_t)(K * 64) + col;
+        for (int q = 0; q < ITEMS; q++) {
+            const size_t item = item0 + q < batch ? item0 + q : batch - 1;   // tail: duplicate the last item
+            const int4* vi = v + item * (size_t)(L * 64) + col;
+#pragma unroll
+            for (int j = 0; j < L; j++) vr[q][j] = canon4(vi[j * 64]);
+        }
 #pragma unroll
         for (int i = 0; i < K; i++) {
-            uint64_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+            uint64_t acc[ITEMS][4];
+#pragma unroll
+            for (int q = 0; q < ITEMS; q++) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0;
 #pragma unroll
             for (int j = 0; j < L; j++) {
                 uint4 a = canon4(__ldg(a_hat + (i * L + j) * 64 + col));
-                acc0 += (uint64_t)a.x * vr[j].x;
-                acc1 += (uint64_t)a.y * vr[j].y;
-                acc2 += (uint64_t)a.z * vr[j].z;
-                acc3 += (uint64_t)a.w * vr[j].w;
+#pragma unroll
+                for (int q = 0; q < ITEMS; q++) {
+                    acc[q][0] += (uint64_t)a.x * vr[q][j].x;
+                    acc[q][1] += (uint64_t)a.y * vr[q][j].y;
+                    acc[q][2] += (uint64_t)a.z * vr[q][j].z;
+                    acc[q][3] += (uint64_t)a.w * vr[q][j].w;
+                }
             }
-            wi[i * 64] = make_int4((int)reduce49(acc0), (int)reduce49(acc1), (int)reduce49(acc2), (int)reduce49(acc3));
+#pragma unroll
+            for (int q = 0; q < ITEMS; q++) {
+                if (item0 + q < batch) {
+                    int4* wi = w + (item0 + q) * (size_t)(K * 64) + col;
+                    wi[i * 64] = make_int4((int)reduce49(acc[q][0]), (int)reduce49(acc[q][1]), (int)reduce49(acc[q][2]),
+                                           (int)reduce49(acc[q][3]));
+                }
+            }
         }
     }
 }
@@ -128,9 +147,9 @@ cudaError_t launch_matvec(int32_t* w, const int32_t* a_hat, const int32_t* v, in
     auto* W = reinterpret_cast<int4*>(w);
     auto* A = reinterpret_cast<const int4*>(a_hat);
     auto* V = reinterpret_cast<const int4*>(v);
-    if (k == 4 && l == 4) matvec_kernel<4, 4><<<grid, 256, 0, st>>>(W, A, V, n_slices);
-    else if (k == 6 && l == 5) matvec_kernel<6, 5><<<grid, 256, 0, st>>>(W, A, V, n_slices);
-    else if (k == 8 && l == 7) matvec_kernel<8, 7><<<grid, 256, 0, st>>>(W, A, V, n_slices);
+    if (k == 4 && l == 4) matvec_kernel<4, 4, 1><<<grid, 256, 0, st>>>(W, A, V, batch);
+    else if (k == 6 && l == 5) matvec_kernel<6, 5, 1><<<grid, 256, 0, st>>>(W, A, V, batch);   // 2 items/thread measured slower here
+    else if (k == 8 && l == 7) matvec_kernel<8, 7, 2><<<grid, 256, 0, st>>>(W, A, V, batch);
     else matvec_generic_kernel<<<grid, 256, 0, st>>>(W, A, V, k, l, n_slices);
     return cudaGetLastError();
 }

@@ -445,7 +445,7 @@ int verify_run(dil_engine* e, dil_verify_key* k, const uint8_t* d_msgs, const ui
     if (rc) return rc;
     const uint32_t nn = (uint32_t)n;
     CK(cudaMemsetAsync(k->bad, 0, n * 4, st));
-    CK(dil::launch_verify_mu(k->mu_d, k->seeds, d_msgs, d_off, nn, st));
+    CK(dil::launch_verify_mu(k->mu_d, k->seeds, d_msgs, d_off, nn, 0, st));
     CK(dil::launch_unpack_z(P.level, k->v, k->bad, d_z, nn, st));
     CK(dil::launch_verify_prep(P.level, k->v, k->hmask, k->bad, d_h, reinterpret_cast<const uint64_t*>(d_ct), nn, st));
     CK(dil::launch_verify_core(k->w, k->a_ext, k->v, P.level, n, e->sm_count, st));
@@ -636,6 +636,69 @@ extern "C" int dil_keygen_batch_host(dil_engine_t* e, int level, const uint8_t* 
     A(cudaStreamSynchronize(st));
     if (err != cudaSuccess) rc = fail(e, err, "dil_keygen_batch_host");
     else e->launches += 7;
+    cudaFree(base);
+    return rc;
+}
+
+// =======================================================================================
+// Verification with one public key PER signature (SURVEY.md §8d cfg4 "per-item rho"): A is expanded
+// on chip from rho[i] inside the fused kernel; t1[i] is unpacked, negated, scaled and NTT'd per item.
+// =======================================================================================
+extern "C" int dil_verify_multi_host(dil_engine_t* e, int level, const uint8_t* rho, const uint8_t* t1p, const uint8_t* msgs,
+                                     const uint64_t* offsets, size_t n, const uint8_t* z, const uint8_t* h,
+                                     const uint8_t* ctilde, uint8_t* ok) {
+    if (!e) return DIL_ERR_ARG;
+    if (level != 2 && level != 3 && level != 5) return DIL_ERR_ARG;
+    if (n == 0) return DIL_OK;
+    if (!rho || !t1p || !msgs || !offsets || !z || !h || !ctilde || !ok || n > 0x00FFFFFFu) return DIL_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    const LevelParams P = dil::level_params(level);
+    cudaStream_t st = e->host_stream;
+    const size_t K = P.k, L = P.l, zb = L * P.z_bytes, hb = (size_t)P.omega + P.k, t1b = K * 320;
+    const size_t mbytes = offsets[n] > 0 ? offsets[n] : 1;
+    struct Seg { size_t off; };
+    size_t total = 0;
+    auto seg = [&](size_t bytes) { Seg s{total}; total += (bytes + 255) & ~(size_t)255; return s; };
+    Seg S_rho = seg(n * 32), S_t1p = seg(n * t1b), S_msgs = seg(mbytes), S_off = seg((n + 1) * 8), S_z = seg(n * zb), S_h = seg(n * hb),
+        S_ct = seg(n * 32), S_ok = seg(n), S_tr = seg(n * 32), S_mu = seg(n * 64), S_bad = seg(n * 4), S_hm = seg(n * K * 32),
+        S_v = seg(n * (L + 1) * 1024), S_w = seg(n * K * 1024), S_t1n = seg(n * K * 1024), S_w1p = seg(n * K * P.w1_bytes);
+    uint8_t* base = nullptr;
+    cudaError_t aerr = cudaMalloc(reinterpret_cast<void**>(&base), total);
+    if (aerr != cudaSuccess) {
+        e->last_error = std::string("verify arena: ") + cudaGetErrorString(aerr);
+        return DIL_ERR_ALLOC;
+    }
+    auto P8 = [&](Seg s) { return base + s.off; };
+    auto P32 = [&](Seg s) { return reinterpret_cast<int32_t*>(base + s.off); };
+    auto PU32 = [&](Seg s) { return reinterpret_cast<uint32_t*>(base + s.off); };
+    auto PU64 = [&](Seg s) { return reinterpret_cast<uint64_t*>(base + s.off); };
+    cudaError_t err = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+    const uint32_t nn = (uint32_t)n;
+    A(cudaMemcpyAsync(P8(S_rho), rho, n * 32, cudaMemcpyHostToDevice, st));
+    A(cudaMemcpyAsync(P8(S_t1p), t1p, n * t1b, cudaMemcpyHostToDevice, st));
+    A(cudaMemcpyAsync(P8(S_msgs), msgs, offsets[n], cudaMemcpyHostToDevice, st));
+    A(cudaMemcpyAsync(P8(S_off), offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    A(cudaMemcpyAsync(P8(S_z), z, n * zb, cudaMemcpyHostToDevice, st));
+    A(cudaMemcpyAsync(P8(S_h), h, n * hb, cudaMemcpyHostToDevice, st));
+    A(cudaMemcpyAsync(P8(S_ct), ctilde, n * 32, cudaMemcpyHostToDevice, st));
+    A(cudaMemsetAsync(P8(S_bad), 0, n * 4, st));
+    A(dil::launch_tr_batch(P8(S_tr), P8(S_rho), P8(S_t1p), (uint32_t)t1b, nn, st));
+    A(dil::launch_verify_mu(PU64(S_mu), P8(S_tr), P8(S_msgs), PU64(S_off), nn, 32, st));
+    A(dil::launch_unpack_z(level, P32(S_v), PU32(S_bad), P8(S_z), nn, st));
+    A(dil::launch_verify_prep(level, P32(S_v), PU32(S_hm), PU32(S_bad), P8(S_h), PU64(S_ct), nn, st));
+    A(dil::launch_unpack_t1neg(P32(S_t1n), P8(S_t1p), n * K, st));
+    A(dil::launch_ntt_fwd(P32(S_t1n), P32(S_t1n), n * K, e->sm_count, st));
+    A(dil::launch_verify_core_item(P32(S_w), P8(S_rho), P32(S_v), P32(S_t1n), level, n, st));
+    A(dil::launch_usehint_pack(level, PU32(S_w1p), P32(S_w), PU32(S_hm), nn, st));
+    A(dil::launch_verify_hash(level, P8(S_ok), PU64(S_mu), PU64(S_w1p), PU64(S_ct), PU32(S_bad), nn, st));
+    A(cudaMemcpyAsync(ok, P8(S_ok), n, cudaMemcpyDeviceToHost, st));
+    A(cudaStreamSynchronize(st));
+    int rc = DIL_OK;
+    if (err != cudaSuccess) rc = fail(e, err, "dil_verify_multi_host");
+    else e->launches += 9;
     cudaFree(base);
     return rc;
 }

@@ -602,10 +602,12 @@ cudaError_t launch_iota(uint32_t* dst, uint32_t n, cudaStream_t st) {
 namespace dil {
 
 // mu = SHAKE256(tr || M); one thread per item
-__global__ void __launch_bounds__(128) verify_mu_kernel(uint64_t* __restrict__ mu, const uint8_t* __restrict__ tr,
-                                                        const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ offsets, uint32_t n) {
+__global__ void __launch_bounds__(128) verify_mu_kernel(uint64_t* __restrict__ mu, const uint8_t* __restrict__ tr_base,
+                                                        const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ offsets, uint32_t n,
+                                                        uint32_t tr_stride) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
+    const uint8_t* tr = tr_base + (size_t)t * tr_stride;   // stride 0: one key for the batch, 32: one key per item
     const uint8_t* m = msgs + offsets[t];
     const size_t mlen = (size_t)(offsets[t + 1] - offsets[t]);
     uint64_t A[25];
@@ -800,9 +802,41 @@ __global__ void __launch_bounds__(128) verify_hash_kernel(uint8_t* __restrict__ 
 }
 
 // ---- launchers ----
-cudaError_t launch_verify_mu(uint64_t* mu, const uint8_t* tr, const uint8_t* msgs, const uint64_t* offsets, uint32_t n, cudaStream_t st) {
+cudaError_t launch_verify_mu(uint64_t* mu, const uint8_t* tr, const uint8_t* msgs, const uint64_t* offsets, uint32_t n,
+                             uint32_t tr_stride, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    verify_mu_kernel<<<(n + 127) / 128, 128, 0, st>>>(mu, tr, msgs, offsets, n);
+    verify_mu_kernel<<<(n + 127) / 128, 128, 0, st>>>(mu, tr, msgs, offsets, n, tr_stride);
+    return cudaGetLastError();
+}
+
+// -t1 * 2^13 mod Q from the 10-bit packed t1 (decoder.v:96-100); one thread per 8 coefficients (10 bytes)
+__global__ void __launch_bounds__(256) unpack_t1neg_kernel(int32_t* __restrict__ out, const uint8_t* __restrict__ t1p, size_t n_groups) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const uint8_t* src = t1p + g * 10;
+    uint64_t lo = 0;
+    uint32_t hi;
+#pragma unroll
+    for (int i = 0; i < 8; i++) lo |= (uint64_t)src[i] << (8 * i);
+    hi = (uint32_t)src[8] | ((uint32_t)src[9] << 8);
+    int32_t o[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const int pos = 10 * c;
+        uint32_t v = pos + 10 <= 64 ? (uint32_t)(lo >> pos)
+                     : (pos < 64 ? (uint32_t)((lo >> pos) | ((uint64_t)hi << (64 - pos))) : (hi >> (pos - 64)));
+        v &= 1023u;
+        uint32_t m = (v << D_BITS) % Q;        // t1 * 2^13 < 2^23: at most one subtraction
+        o[c] = (int32_t)((Q - m) % Q);
+    }
+    int4* dst = reinterpret_cast<int4*>(out) + g * 2;
+    dst[0] = make_int4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_int4(o[4], o[5], o[6], o[7]);
+}
+cudaError_t launch_unpack_t1neg(int32_t* out, const uint8_t* t1p, size_t n_polys, cudaStream_t st) {
+    if (n_polys == 0) return cudaSuccess;
+    size_t n_groups = n_polys * 32;
+    unpack_t1neg_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(out, t1p, n_groups);
     return cudaGetLastError();
 }
 cudaError_t launch_tr(uint64_t* tr, const uint8_t* rho, const uint8_t* t1p, uint32_t t1_bytes, cudaStream_t st) {

@@ -224,6 +224,22 @@ class Engine:
         self._check(rc, "dil_signcore_host")
         return w
 
+    def verify_multi(self, level, rho, t1_packed, msgs, z, h, ctilde):
+        """Verify n signatures, each under its own public key (rho[i], t1[i]).  Returns ok[n] (1 = accept)."""
+        n = len(msgs)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(m) for m in msgs])
+        blob = np.frombuffer(b"".join(msgs), dtype=np.uint8).copy() if off[-1] else np.zeros(1, np.uint8)
+        arrs = [np.ascontiguousarray(x, dtype=np.uint8) for x in (rho, t1_packed)]
+        sig = [np.ascontiguousarray(x, dtype=np.uint8) for x in (z, h, ctilde)]
+        ok = np.zeros(n, dtype=np.uint8)
+        P = ctypes.c_void_p
+        rc = self._lib.dil_verify_multi_host(self._h, int(level), arrs[0].ctypes.data_as(P), arrs[1].ctypes.data_as(P),
+                                             blob.ctypes.data_as(P), off.ctypes.data_as(P), n, sig[0].ctypes.data_as(P),
+                                             sig[1].ctypes.data_as(P), sig[2].ctypes.data_as(P), ok.ctypes.data_as(P))
+        self._check(rc, "dil_verify_multi_host")
+        return ok
+
     def keygen(self, level, seeds):
         """Batched key generation from 32-byte seeds xi (host path).  Returns a dict of uint8 arrays with the
         KAT field names: rho, k, tr, s1, s2, t1, t0 (bit-packed as the reference's KAT files)."""

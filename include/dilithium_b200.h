@@ -154,6 +154,11 @@ int dil_verify_batch_host(dil_engine_t *e, dil_verify_key_t *k, const uint8_t *m
 int dil_verify_batch_dev(dil_engine_t *e, dil_verify_key_t *k, const uint8_t *d_msgs, const uint64_t *d_offsets, size_t n,
                          const uint8_t *d_z, const uint8_t *d_h, const uint8_t *d_ctilde, uint8_t *d_ok, void *stream);
 
+/* one public key PER signature (cfg4 "per-item rho"): rho n x 32 B, t1 n x k*320 B; A is expanded on chip per item */
+int dil_verify_multi_host(dil_engine_t *e, int level, const uint8_t *rho, const uint8_t *t1_packed, const uint8_t *msgs,
+                          const uint64_t *offsets, size_t n, const uint8_t *z, const uint8_t *h, const uint8_t *ctilde,
+                          uint8_t *ok);
+
 /* ---- batched key generation (combined_top.v mode 0, FSM :754-1079; outputs as tb_keygen_top.v:180-275) ----
  * xi: n x 32-byte seeds.  Outputs per key, bit-packed exactly as the KAT files: rho, K, tr (32 B each),
  * s1 (l polys), s2 (k polys) as eta - s, t1 (10 bit), t0 as 2^12 - t0 (13 bit). */

@@ -63,3 +63,20 @@ def test_sign_then_verify_on_device(eng):
     exp = torch.ones(n, dtype=torch.uint8, device="cuda")
     exp[::7] = 0
     assert torch.equal(ok, exp)
+
+
+@pytest.mark.parametrize("level", [2, 3, 5])
+def test_verify_multi_key_all_kats_in_one_batch(eng, oracle, level):
+    """cfg4 style: 100 signatures under 100 different public keys verified as ONE batch (per-item rho:
+    A expanded on chip per item), plus tampered copies that must be rejected."""
+    K = ol.kat(level)
+    msgs = list(K["msgs"])
+    ok = eng.verify_multi(level, K["rho"], K["t1"], msgs, K["zs"], K["h"], K["c"])
+    assert ok.tolist() == [1] * 100
+    z2 = K["zs"].copy()
+    z2[::3, 50] ^= 2
+    t1x = K["t1"].copy()
+    t1x[1::3, 7] ^= 1                      # wrong public key
+    ok = eng.verify_multi(level, K["rho"], t1x, msgs, z2, K["h"], K["c"])
+    exp = [0 if (i % 3 == 0 or i % 3 == 1) else 1 for i in range(100)]
+    assert ok.tolist() == exp
