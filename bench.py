@@ -373,7 +373,9 @@ def run_engine(args):
             "step_profile_note": f"device time per kernel class in one step (sum {prof_total:.3f} ms of {ms_step:.3f} ms wall); "
                                  "the rest is launch latency and one 4-byte D2H + stream sync per rejection round",
             "roofline": {"kernel": CLASS_KERNEL[dominant], "class": dominant, "bound": "hbm", "achieved": dom_achieved, "peak": peak,
-                         "unit": "GB/s", "frac": dom_achieved / peak, "traffic": ncu_traffic(dominant),
+                         "unit": "GB/s", "frac": dom_achieved / peak,
+                         "traffic": (ncu_traffic(dominant) / 65536.0 * dom_units / max(rounds, 1)) if ncu_traffic(dominant) else None,
+                         "traffic_note": "ncu dram bytes of a 65536-slot launch scaled to this step's average launch size",
                          "algorithmic_bytes_per_slot": cb[dominant], "slots_per_step": dom_units, "launches_per_step": rounds,
                          "avg_launch_ms": dom_ms / max(rounds, 1), "peak_source": peak_src,
                          "true_limiter": CLASS_BOUND_NOTE.get(dominant, "")},

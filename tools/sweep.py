@@ -85,10 +85,32 @@ def main():
             c = torch.empty((B, 32), dtype=torch.uint8, device="cuda"); att = torch.zeros(B, dtype=torch.int32, device="cuda")
             t = timeit(lambda: key.sign_dev(msgs, off, B, z, h, c, att), 3 if lg >= 16 else 10)
             rec.update(sign_msigs=B / t / 1e3, sign_ms=t, sign_rounds=key.last_rounds, mean_attempts=float(att.float().mean().item()))
+            # verification of the signatures just produced: one key for the batch, and one key per signature
+            vk = d.VerifyKey(eng, level, K["rho"][0], K["t1"][0])
+            ok = torch.zeros(B, dtype=torch.uint8, device="cuda")
+            t = timeit(lambda: vk.verify_dev(msgs, off, B, z, h, c, ok), 5 if lg >= 16 else 10)
+            rec.update(verify_msigs=B / t / 1e3, verify_ms=t, verify_all_ok=bool(int(ok.sum()) == B))
+            vk.close()
             emit(**rec)
-            del msgs, off, z, h, c, att
+            del msgs, off, z, h, c, att, ok
             torch.cuda.empty_cache()
         key.close()
+        # key generation and per-key verification (host-pointer paths: they include PCIe)
+        import time
+        for n in (4096, 65536):
+            seeds = np.random.default_rng(n).integers(0, 256, size=(n, 32)).astype(np.uint8)
+            eng.keygen(level, seeds[:256])
+            t0 = time.perf_counter(); keys = eng.keygen(level, seeds); dt = time.perf_counter() - t0
+            emit(level=level, keygen_batch=n, keygen_mkeys_e2e=n / dt / 1e6, keygen_ms=dt * 1e3)
+        n = 4096
+        sk = d.SignKey(eng, level, *[keys[f][0] for f in ("rho", "k", "tr", "s1", "s2", "t0")])
+        msgs_l = [bytes([i & 255]) * 32 for i in range(n)]
+        z, h, c, _ = sk.sign(msgs_l)
+        rho_n = np.repeat(keys["rho"][:1], n, axis=0); t1_n = np.repeat(keys["t1"][:1], n, axis=0)
+        eng.verify_multi(level, rho_n[:64], t1_n[:64], msgs_l[:64], z[:64], h[:64], c[:64])
+        t0 = time.perf_counter(); ok = eng.verify_multi(level, rho_n, t1_n, msgs_l, z, h, c); dt = time.perf_counter() - t0
+        emit(level=level, verify_multi_batch=n, verify_multi_msigs_e2e=n / dt / 1e6, verify_multi_ms=dt * 1e3, all_ok=bool(ok.sum() == n))
+        sk.close()
 
 
 if __name__ == "__main__":
