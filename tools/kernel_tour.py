@@ -1,0 +1,33 @@
+"""One launch of every hot-path kernel at bench-like sizes (driver for ncu captures / compute-sanitizer)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, torch
+import dilithium_b200 as d
+small = len(sys.argv) > 1 and sys.argv[1] == "small"
+eng = d.Engine(0); Q = d.Q
+B = 256 if small else 65536
+for level in ((2,) if small else (2, 5)):
+    k, l = d.LEVEL_DIMS[level]
+    Bl = B if level == 2 else B // 2
+    y = torch.randint(0, Q, (Bl, l, 256), dtype=torch.int32, device="cuda"); o = torch.empty_like(y)
+    a_hat = torch.randint(0, Q, (k * l, 256), dtype=torch.int32, device="cuda")
+    w = torch.empty((Bl, k, 256), dtype=torch.int32, device="cuda")
+    rho = torch.randint(0, 256, (Bl, 32), dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        eng.ntt(y, out=o); eng.invntt(y, out=o); eng.pointwise_barrett(y, o, o); eng.add(y, o, o)
+        eng.matvec(a_hat, y, k, l, w=w); eng.signcore(a_hat, y, k, l, w=w)
+        eng.matvec_expand(rho[0], y, k, l, False, True, True, w=w)
+        n = Bl // 8
+        eng.matvec_expand(rho[:n], y[:n], k, l, True, True, True, w=w[:n])
+        eng.expand_a(rho[:256], k, l)
+torch.cuda.synchronize()
+import oracle_lib as ol
+K = ol.kat(2)
+sk = d.SignKey(eng, 2, K["rho"][0], K["k"][0], K["tr"][0], K["s1"][0], K["s2"][0], K["t0"][0])
+vk = d.VerifyKey(eng, 2, K["rho"][0], K["t1"][0])
+msgs = [bytes([i & 255]) * 40 for i in range(64 if small else 4096)]
+z, h, c, att = sk.sign(msgs)
+assert vk.verify(msgs, z, h, c).all()
+keys = eng.keygen(2, np.arange(64 * 32, dtype=np.uint8).reshape(64, 32))
+print("tour ok", eng.launch_count)
