@@ -209,7 +209,7 @@ constexpr size_t shared_smem_bytes(int warps) {
     return (size_t)(K * L * A_STRIDE + warps * SCRATCH_WORDS) * 4;
 }
 
-template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT>
+template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT, int MAX_CTAS = 8>
 static cudaError_t launch_shared_t(int32_t* w, const int32_t* a_hat, const uint8_t* rho, const int32_t* v, size_t batch,
                                    int sm_count, cudaStream_t st) {
     auto kern = matvec_shared_kernel<K, L, WARPS, EXPAND, NTT_IN, INTT_OUT>;
@@ -222,6 +222,7 @@ static cudaError_t launch_shared_t(int32_t* w, const int32_t* a_hat, const uint8
     }
     int ctas_per_sm = (int)((220 * 1024) / smem);
     if (ctas_per_sm > shared_min_ctas(K, L, WARPS)) ctas_per_sm = shared_min_ctas(K, L, WARPS);
+    if (ctas_per_sm > MAX_CTAS) ctas_per_sm = MAX_CTAS;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     size_t want = (batch + WARPS - 1) / WARPS;
     size_t cap = (size_t)sm_count * ctas_per_sm;
@@ -238,6 +239,9 @@ static cudaError_t launch_shared_flags(int32_t* w, const int32_t* a_hat, const u
         // one 16-warp CTA per SM measured 3-5 % faster than two 8-warp CTAs (DIL_SC_WARPS=8 selects the latter)
         static int big = -1;
         if (big < 0) { const char* e = std::getenv("DIL_SC_WARPS"); big = (e && std::atoi(e) == 8) ? 0 : 1; }
+        static int half = -1;   // overlap experiment: one 8-warp CTA per SM (half an SM's registers)
+        if (half < 0) { const char* e = std::getenv("DIL_SC_HALF"); half = (e && std::atoi(e)) ? 1 : 0; }
+        if (half) return launch_shared_t<K, L, 8, EXPAND, true, true, 1>(w, a_hat, rho, v, batch, sm_count, st);
         if (big) return launch_shared_t<K, L, 16, EXPAND, true, true>(w, a_hat, rho, v, batch, sm_count, st);
         return launch_shared_t<K, L, WARPS, EXPAND, true, true>(w, a_hat, rho, v, batch, sm_count, st);
     }

@@ -22,6 +22,12 @@
 
 namespace dil {
 
+// development knobs for the pipe-overlap experiment: cap CTAs per SM of a kernel class
+static int overlap_knob(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
 // ---------------------------------------------------------------------------------------
 // S0: mu = SHAKE256(tr || M)[0:64], rho' = SHAKE256(K || mu)[0:64]; one thread per item
 // ---------------------------------------------------------------------------------------
@@ -79,9 +85,10 @@ __global__ void __launch_bounds__(128) expand_mask_kernel(int32_t* __restrict__ 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* stage = sm_raw + (size_t)warp * 32 * ROW;
     const uint32_t n_polys = n_slots * L;
-    const uint32_t wbase = (blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+    const uint32_t wstride = gridDim.x * (blockDim.x >> 5) * 32;
+    // grid-stride over 32-polynomial chunks so that the launch can be capped to a fixed number of CTAs per SM
+    for (uint32_t wbase = (blockIdx.x * (blockDim.x >> 5) + warp) * 32; wbase < n_polys; wbase += wstride) {
     const uint32_t gid = wbase + lane;
-    if (wbase >= n_polys) return;
     if (gid < n_polys) {
         const uint32_t a = gid / L, j = gid % L;
         const uint32_t item = active[a / spec];
@@ -137,6 +144,8 @@ __global__ void __launch_bounds__(128) expand_mask_kernel(int32_t* __restrict__ 
         int4* dst = reinterpret_cast<int4*>(y + (size_t)(wbase + p) * N) + 2 * lane;
         dst[0] = make_int4(v[0], v[1], v[2], v[3]);
         dst[1] = make_int4(v[4], v[5], v[6], v[7]);
+    }
+    __syncwarp();   // staging area is reused by the next chunk
     }
 }
 
@@ -207,8 +216,7 @@ template <int K, int W1_BYTES, int TAU>
 __global__ void __launch_bounds__(128) challenge_kernel(int8_t* __restrict__ c_out, uint64_t* __restrict__ ctilde,
                                                         const uint64_t* __restrict__ mu, const uint64_t* __restrict__ w1p,
                                                         const uint32_t* __restrict__ active, uint32_t n_slots, uint32_t spec) {
-    uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n_slots) return;
+    for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_slots; a += gridDim.x * blockDim.x) {
     const uint32_t item = active[a / spec];
     constexpr int W1_LANES = K * W1_BYTES / 8;
     const uint64_t* m = mu + (size_t)item * 8;
@@ -253,6 +261,7 @@ __global__ void __launch_bounds__(128) challenge_kernel(int8_t* __restrict__ c_o
     }
     uint32_t* dst = reinterpret_cast<uint32_t*>(c_out + (size_t)a * N);
     for (int i = 0; i < N / 4; i++) dst[i] = reinterpret_cast<const uint32_t*>(c)[i];
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -476,7 +485,10 @@ static cudaError_t launch_expand_mask_t(int32_t* y, const uint64_t* rhop, const 
         configured = true;
     }
     uint32_t n_polys = n_slots * L;
-    kern<<<(n_polys + 127) / 128, 128, smem, st>>>(y, rhop, kappa, active, n_slots, spec);
+    unsigned grid = (n_polys + 127) / 128;
+    const unsigned cap = (unsigned)overlap_knob("DIL_EM_CTAS", 0) * 148u;   // 0: uncapped (one chunk per warp)
+    if (cap && grid > cap) grid = cap;
+    kern<<<grid, 128, smem, st>>>(y, rhop, kappa, active, n_slots, spec);
     return cudaGetLastError();
 }
 
@@ -506,6 +518,8 @@ cudaError_t launch_challenge(int level, int8_t* c, uint64_t* ct_slot, const uint
     if (n_slots == 0) return cudaSuccess;
     // 64-thread CTAs: 1024 CTAs for a 65536-slot round spread evenly over 148 SMs
     unsigned grid = (n_slots + 63) / 64;
+    const unsigned ccap = (unsigned)overlap_knob("DIL_CH_CTAS", 0) * 148u;
+    if (ccap && grid > ccap) grid = ccap;
     switch (level) {
         case 2: challenge_kernel<4, 192, 39><<<grid, 64, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
         case 3: challenge_kernel<6, 128, 49><<<grid, 64, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
@@ -538,6 +552,7 @@ static cudaError_t launch_sign_tail_t(int32_t* y, uint8_t* h_slot, uint8_t* acce
     // one 24-warp CTA per SM is marginally faster than three 8-warp CTAs (DIL_TAIL_WARPS=8 selects the latter)
     static int big = -1;
     if (big < 0) { const char* e = std::getenv("DIL_TAIL_WARPS"); big = (e && std::atoi(e) == 8) ? 0 : 1; }
+    if (overlap_knob("DIL_TAIL_HALF", 0)) return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 12, 1>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st);
     if (big) return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 24, 1>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st);
     return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 8, 3>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st);
 }
