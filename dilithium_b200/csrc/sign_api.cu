@@ -6,6 +6,7 @@
 // ExpandMask -> fused sign core -> w1 pack -> challenge -> tail over the active items.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>

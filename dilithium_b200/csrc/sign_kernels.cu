@@ -423,7 +423,12 @@ __global__ void __launch_bounds__(256) resolve_kernel(uint8_t* __restrict__ zp, 
     constexpr int BITS = GAMMA1_BITS + 1;
     constexpr int32_t G1 = 1 << GAMMA1_BITS;
     const int4* src = reinterpret_cast<const int4*>(zslot + (size_t)a * L * N);
-    uint8_t* dstp = zp + (size_t)item * (L * 32 * BITS);
+    // the packed z is staged in shared memory and leaves as 16-byte vectors, 512 contiguous bytes per warp
+    // store: efficient for HBM and - when the caller's buffers are pinned host memory mapped into the
+    // device (dil_sign_batch_host zero-copy path) - for PCIe posted writes
+    constexpr int ZB = L * 32 * BITS;
+    __shared__ __align__(16) uint8_t zstage[8][ZB];
+    uint8_t* dstp = zstage[threadIdx.x >> 5];
     for (int g = lane; g < L * 32; g += 32) {
         int4 va = src[2 * g], vb = src[2 * g + 1];
         uint32_t v[8] = {(uint32_t)(G1 - va.x), (uint32_t)(G1 - va.y), (uint32_t)(G1 - va.z), (uint32_t)(G1 - va.w),
@@ -456,6 +461,12 @@ __global__ void __launch_bounds__(256) resolve_kernel(uint8_t* __restrict__ zp, 
             uint32_t* d = reinterpret_cast<uint32_t*>(dst);
             d[0] = (uint32_t)lo; d[1] = (uint32_t)(lo >> 32); d[2] = (uint32_t)mid; d[3] = (uint32_t)(mid >> 32); d[4] = hi;
         }
+    }
+    __syncwarp();
+    {
+        uint4* out = reinterpret_cast<uint4*>(zp + (size_t)item * ZB);
+        const uint4* st = reinterpret_cast<const uint4*>(dstp);
+        for (int t = lane; t < ZB / 16; t += 32) out[t] = st[t];
     }
     for (int t = lane; t < HB; t += 32) h_out[(size_t)item * HB + t] = h_slot[(size_t)a * HB + t];
     if (lane < 4) ct_out[(size_t)item * 4 + lane] = ct_slot[(size_t)a * 4 + lane];
