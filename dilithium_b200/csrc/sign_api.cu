@@ -311,8 +311,9 @@ int dil_sign_batch_dev(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* d_msgs
                        uint8_t* d_z, uint8_t* d_h, uint8_t* d_ctilde, uint32_t* d_attempts, void* stream) {
     if (!e || !k) return DIL_ERR_ARG;
     if (n == 0) return DIL_OK;
-    if (!d_msgs || !d_offsets || !d_z || !d_h || !d_ctilde || !d_attempts || n > 0x7FFFFFFFu) return DIL_ERR_ARG;
-    if ((reinterpret_cast<uintptr_t>(d_ctilde) & 7u) || (reinterpret_cast<uintptr_t>(d_z) & 3u)) return DIL_ERR_ARG;
+    if (!d_msgs || !d_offsets || !d_z || !d_h || !d_ctilde || !d_attempts || n > 0x07FFFFFFu) return DIL_ERR_ARG;
+    // z leaves the device as 16-byte vectors, c~ as 64-bit words
+    if ((reinterpret_cast<uintptr_t>(d_ctilde) & 7u) || (reinterpret_cast<uintptr_t>(d_z) & 15u)) return DIL_ERR_ARG;
     std::lock_guard<std::mutex> g(k->mu);
     DeviceGuard dg(e->device);
     if (!dg.ok) return DIL_ERR_CUDA;
@@ -323,7 +324,7 @@ int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs,
                         uint8_t* z, uint8_t* h, uint8_t* ctilde, uint32_t* attempts) {
     if (!e || !k) return DIL_ERR_ARG;
     if (n == 0) return DIL_OK;
-    if (!msgs || !offsets || !z || !h || !ctilde || n > 0x7FFFFFFFu) return DIL_ERR_ARG;
+    if (!msgs || !offsets || !z || !h || !ctilde || n > 0x07FFFFFFu) return DIL_ERR_ARG;
     std::lock_guard<std::mutex> g(k->mu);
     DeviceGuard dg(e->device);
     if (!dg.ok) return DIL_ERR_CUDA;

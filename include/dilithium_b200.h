@@ -132,7 +132,7 @@ int dil_sign_key_create(dil_engine_t *e, dil_sign_key_t **out, int level, const 
 int dil_sign_key_destroy(dil_engine_t *e, dil_sign_key_t *k);
 int dil_sign_batch_host(dil_engine_t *e, dil_sign_key_t *k, const uint8_t *msgs, const uint64_t *offsets, size_t n,
                         uint8_t *z, uint8_t *h, uint8_t *ctilde, uint32_t *attempts);
-/* device pointers (d_ctilde 8-byte aligned); synchronises the stream once per rejection round */
+/* device pointers (d_z 16-byte, d_ctilde 8-byte aligned); synchronises the stream once per rejection round */
 int dil_sign_batch_dev(dil_engine_t *e, dil_sign_key_t *k, const uint8_t *d_msgs, const uint64_t *d_offsets, size_t n,
                        uint8_t *d_z, uint8_t *d_h, uint8_t *d_ctilde, uint32_t *d_attempts, void *stream);
 uint32_t dil_sign_last_rounds(const dil_sign_key_t *k);   /* rejection rounds of the last batch */
