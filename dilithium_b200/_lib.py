@@ -60,6 +60,7 @@ SIGNATURES = {
     "dil_verify_batch_host": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void]),
     "dil_verify_batch_dev": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void, c_void]),
     "dil_verify_multi_host": (c_int, [c_void, c_int, c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void]),
+    "dil_verify_multi_dev": (c_int, [c_void, c_int, c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void, c_void]),
     "dil_keygen_batch_host": (c_int, [c_void, c_int, c_void, c_size] + [c_void] * 7),
     "dil_invntt_tomont_dev": (c_int, [c_void, c_void, c_void, c_size, c_void]),
     "dil_poly_pointwise_dev": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void]),

@@ -646,6 +646,85 @@ extern "C" int dil_keygen_batch_host(dil_engine_t* e, int level, const uint8_t* 
 // Verification with one public key PER signature (SURVEY.md §8d cfg4 "per-item rho"): A is expanded
 // on chip from rho[i] inside the fused kernel; t1[i] is unpacked, negated, scaled and NTT'd per item.
 // =======================================================================================
+namespace {
+struct Arena {   // carve 256-byte aligned segments out of one grow-only device allocation (engine staging slot 3)
+    size_t total = 0;
+    size_t seg(size_t bytes) { size_t o = total; total += (bytes + 255) & ~(size_t)255; return o; }
+};
+
+int arena_reserve(dil_engine* e, size_t bytes, uint8_t** base) {
+    if (bytes > e->staging_bytes[3]) {
+        if (e->staging[3]) cudaFree(e->staging[3]);
+        e->staging[3] = nullptr;
+        e->staging_bytes[3] = 0;
+        cudaError_t err = cudaMalloc(&e->staging[3], bytes);
+        if (err != cudaSuccess) {
+            e->last_error = std::string("verify arena: ") + cudaGetErrorString(err);
+            return DIL_ERR_ALLOC;
+        }
+        e->staging_bytes[3] = bytes;
+    }
+    *base = static_cast<uint8_t*>(e->staging[3]);
+    return DIL_OK;
+}
+
+// all pointers device; `work` holds the intermediates laid out by the caller with multi_work_bytes()
+struct MultiWork { size_t tr, mu, bad, hm, v, w, t1n, w1p, total; };
+MultiWork multi_work_layout(const LevelParams& P, size_t n) {
+    Arena ar;
+    MultiWork m{};
+    const size_t K = P.k, L = P.l;
+    m.tr = ar.seg(n * 32); m.mu = ar.seg(n * 64); m.bad = ar.seg(n * 4); m.hm = ar.seg(n * K * 32);
+    m.v = ar.seg(n * (L + 1) * 1024); m.w = ar.seg(n * K * 1024); m.t1n = ar.seg(n * K * 1024); m.w1p = ar.seg(n * K * P.w1_bytes);
+    m.total = ar.total;
+    return m;
+}
+cudaError_t verify_multi_run(dil_engine* e, const LevelParams& P, uint8_t* work, const MultiWork& m, const uint8_t* d_rho,
+                             const uint8_t* d_t1p, const uint8_t* d_msgs, const uint64_t* d_off, size_t n, const uint8_t* d_z,
+                             const uint8_t* d_h, const uint8_t* d_ct, uint8_t* d_ok, cudaStream_t st) {
+    const uint32_t nn = (uint32_t)n;
+    const size_t K = P.k;
+    auto P32 = [&](size_t o) { return reinterpret_cast<int32_t*>(work + o); };
+    auto PU32 = [&](size_t o) { return reinterpret_cast<uint32_t*>(work + o); };
+    auto PU64 = [&](size_t o) { return reinterpret_cast<uint64_t*>(work + o); };
+    cudaError_t err = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+    A(cudaMemsetAsync(work + m.bad, 0, n * 4, st));
+    A(dil::launch_tr_batch(work + m.tr, d_rho, d_t1p, (uint32_t)(K * 320), nn, st));
+    A(dil::launch_verify_mu(PU64(m.mu), work + m.tr, d_msgs, d_off, nn, 32, st));
+    A(dil::launch_unpack_z(P.level, P32(m.v), PU32(m.bad), d_z, nn, st));
+    A(dil::launch_verify_prep(P.level, P32(m.v), PU32(m.hm), PU32(m.bad), d_h, reinterpret_cast<const uint64_t*>(d_ct), nn, st));
+    A(dil::launch_unpack_t1neg(P32(m.t1n), d_t1p, n * K, st));
+    A(dil::launch_ntt_fwd(P32(m.t1n), P32(m.t1n), n * K, e->sm_count, st));
+    A(dil::launch_verify_core_item(P32(m.w), d_rho, P32(m.v), P32(m.t1n), P.level, n, st));
+    A(dil::launch_usehint_pack(P.level, PU32(m.w1p), P32(m.w), PU32(m.hm), nn, st));
+    A(dil::launch_verify_hash(P.level, d_ok, PU64(m.mu), PU64(m.w1p), reinterpret_cast<const uint64_t*>(d_ct), PU32(m.bad), nn, st));
+    return err;
+}
+}  // namespace
+
+extern "C" int dil_verify_multi_dev(dil_engine_t* e, int level, const uint8_t* d_rho, const uint8_t* d_t1p, const uint8_t* d_msgs,
+                                    const uint64_t* d_offsets, size_t n, const uint8_t* d_z, const uint8_t* d_h,
+                                    const uint8_t* d_ctilde, uint8_t* d_ok, void* stream) {
+    if (!e) return DIL_ERR_ARG;
+    if (level != 2 && level != 3 && level != 5) return DIL_ERR_ARG;
+    if (n == 0) return DIL_OK;
+    if (!d_rho || !d_t1p || !d_msgs || !d_offsets || !d_z || !d_h || !d_ctilde || !d_ok || n > 0x00FFFFFFu) return DIL_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_ctilde) & 7u) || (reinterpret_cast<uintptr_t>(d_z) & 3u)) return DIL_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    const LevelParams P = dil::level_params(level);
+    const MultiWork m = multi_work_layout(P, n);
+    uint8_t* work = nullptr;
+    int rc = arena_reserve(e, m.total, &work);
+    if (rc) return rc;
+    cudaError_t err = verify_multi_run(e, P, work, m, d_rho, d_t1p, d_msgs, d_offsets, n, d_z, d_h, d_ctilde, d_ok, (cudaStream_t)stream);
+    if (err != cudaSuccess) return fail(e, err, "dil_verify_multi_dev");
+    e->launches += 9;
+    return DIL_OK;
+}
+
 extern "C" int dil_verify_multi_host(dil_engine_t* e, int level, const uint8_t* rho, const uint8_t* t1p, const uint8_t* msgs,
                                      const uint64_t* offsets, size_t n, const uint8_t* z, const uint8_t* h,
                                      const uint8_t* ctilde, uint8_t* ok) {
@@ -660,47 +739,29 @@ extern "C" int dil_verify_multi_host(dil_engine_t* e, int level, const uint8_t* 
     cudaStream_t st = e->host_stream;
     const size_t K = P.k, L = P.l, zb = L * P.z_bytes, hb = (size_t)P.omega + P.k, t1b = K * 320;
     const size_t mbytes = offsets[n] > 0 ? offsets[n] : 1;
-    struct Seg { size_t off; };
-    size_t total = 0;
-    auto seg = [&](size_t bytes) { Seg s{total}; total += (bytes + 255) & ~(size_t)255; return s; };
-    Seg S_rho = seg(n * 32), S_t1p = seg(n * t1b), S_msgs = seg(mbytes), S_off = seg((n + 1) * 8), S_z = seg(n * zb), S_h = seg(n * hb),
-        S_ct = seg(n * 32), S_ok = seg(n), S_tr = seg(n * 32), S_mu = seg(n * 64), S_bad = seg(n * 4), S_hm = seg(n * K * 32),
-        S_v = seg(n * (L + 1) * 1024), S_w = seg(n * K * 1024), S_t1n = seg(n * K * 1024), S_w1p = seg(n * K * P.w1_bytes);
+    const MultiWork m = multi_work_layout(P, n);
+    Arena io;
+    io.total = m.total;
+    const size_t o_rho = io.seg(n * 32), o_t1p = io.seg(n * t1b), o_msgs = io.seg(mbytes), o_off = io.seg((n + 1) * 8), o_z = io.seg(n * zb),
+                 o_h = io.seg(n * hb), o_ct = io.seg(n * 32), o_ok = io.seg(n);
     uint8_t* base = nullptr;
-    cudaError_t aerr = cudaMalloc(reinterpret_cast<void**>(&base), total);
-    if (aerr != cudaSuccess) {
-        e->last_error = std::string("verify arena: ") + cudaGetErrorString(aerr);
-        return DIL_ERR_ALLOC;
-    }
-    auto P8 = [&](Seg s) { return base + s.off; };
-    auto P32 = [&](Seg s) { return reinterpret_cast<int32_t*>(base + s.off); };
-    auto PU32 = [&](Seg s) { return reinterpret_cast<uint32_t*>(base + s.off); };
-    auto PU64 = [&](Seg s) { return reinterpret_cast<uint64_t*>(base + s.off); };
+    int rc = arena_reserve(e, io.total, &base);
+    if (rc) return rc;
     cudaError_t err = cudaSuccess;
     auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
-    const uint32_t nn = (uint32_t)n;
-    A(cudaMemcpyAsync(P8(S_rho), rho, n * 32, cudaMemcpyHostToDevice, st));
-    A(cudaMemcpyAsync(P8(S_t1p), t1p, n * t1b, cudaMemcpyHostToDevice, st));
-    A(cudaMemcpyAsync(P8(S_msgs), msgs, offsets[n], cudaMemcpyHostToDevice, st));
-    A(cudaMemcpyAsync(P8(S_off), offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    A(cudaMemcpyAsync(P8(S_z), z, n * zb, cudaMemcpyHostToDevice, st));
-    A(cudaMemcpyAsync(P8(S_h), h, n * hb, cudaMemcpyHostToDevice, st));
-    A(cudaMemcpyAsync(P8(S_ct), ctilde, n * 32, cudaMemcpyHostToDevice, st));
-    A(cudaMemsetAsync(P8(S_bad), 0, n * 4, st));
-    A(dil::launch_tr_batch(P8(S_tr), P8(S_rho), P8(S_t1p), (uint32_t)t1b, nn, st));
-    A(dil::launch_verify_mu(PU64(S_mu), P8(S_tr), P8(S_msgs), PU64(S_off), nn, 32, st));
-    A(dil::launch_unpack_z(level, P32(S_v), PU32(S_bad), P8(S_z), nn, st));
-    A(dil::launch_verify_prep(level, P32(S_v), PU32(S_hm), PU32(S_bad), P8(S_h), PU64(S_ct), nn, st));
-    A(dil::launch_unpack_t1neg(P32(S_t1n), P8(S_t1p), n * K, st));
-    A(dil::launch_ntt_fwd(P32(S_t1n), P32(S_t1n), n * K, e->sm_count, st));
-    A(dil::launch_verify_core_item(P32(S_w), P8(S_rho), P32(S_v), P32(S_t1n), level, n, st));
-    A(dil::launch_usehint_pack(level, PU32(S_w1p), P32(S_w), PU32(S_hm), nn, st));
-    A(dil::launch_verify_hash(level, P8(S_ok), PU64(S_mu), PU64(S_w1p), PU64(S_ct), PU32(S_bad), nn, st));
-    A(cudaMemcpyAsync(ok, P8(S_ok), n, cudaMemcpyDeviceToHost, st));
+    A(cudaMemcpyAsync(base + o_rho, rho, n * 32, cudaMemcpyHostToDevice, st));
+    A(cudaMemcpyAsync(base + o_t1p, t1p, n * t1b, cudaMemcpyHostToDevice, st));
+    A(cudaMemcpyAsync(base + o_msgs, msgs, offsets[n], cudaMemcpyHostToDevice, st));
+    A(cudaMemcpyAsync(base + o_off, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    A(cudaMemcpyAsync(base + o_z, z, n * zb, cudaMemcpyHostToDevice, st));
+    A(cudaMemcpyAsync(base + o_h, h, n * hb, cudaMemcpyHostToDevice, st));
+    A(cudaMemcpyAsync(base + o_ct, ctilde, n * 32, cudaMemcpyHostToDevice, st));
+    if (err == cudaSuccess)
+        err = verify_multi_run(e, P, base, m, base + o_rho, base + o_t1p, base + o_msgs, reinterpret_cast<const uint64_t*>(base + o_off), n,
+                               base + o_z, base + o_h, base + o_ct, base + o_ok, st);
+    A(cudaMemcpyAsync(ok, base + o_ok, n, cudaMemcpyDeviceToHost, st));
     A(cudaStreamSynchronize(st));
-    int rc = DIL_OK;
-    if (err != cudaSuccess) rc = fail(e, err, "dil_verify_multi_host");
-    else e->launches += 9;
-    cudaFree(base);
-    return rc;
+    if (err != cudaSuccess) return fail(e, err, "dil_verify_multi_host");
+    e->launches += 9;
+    return DIL_OK;
 }

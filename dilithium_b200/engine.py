@@ -240,6 +240,14 @@ class Engine:
         self._check(rc, "dil_verify_multi_host")
         return ok
 
+    def verify_multi_dev(self, level, d_rho, d_t1, d_msgs, d_offsets, n, d_z, d_h, d_c, d_ok):
+        """Device-resident per-key verification (torch CUDA uint8 tensors) on torch's current stream."""
+        P = ctypes.c_void_p
+        rc = self._lib.dil_verify_multi_dev(self._h, int(level), P(d_rho.data_ptr()), P(d_t1.data_ptr()), P(d_msgs.data_ptr()),
+                                            P(d_offsets.data_ptr()), n, P(d_z.data_ptr()), P(d_h.data_ptr()), P(d_c.data_ptr()),
+                                            P(d_ok.data_ptr()), self._stream())
+        self._check(rc, "dil_verify_multi_dev")
+
     def keygen(self, level, seeds):
         """Batched key generation from 32-byte seeds xi (host path).  Returns a dict of uint8 arrays with the
         KAT field names: rho, k, tr, s1, s2, t1, t0 (bit-packed as the reference's KAT files)."""

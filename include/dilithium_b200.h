@@ -158,6 +158,9 @@ int dil_verify_batch_dev(dil_engine_t *e, dil_verify_key_t *k, const uint8_t *d_
 int dil_verify_multi_host(dil_engine_t *e, int level, const uint8_t *rho, const uint8_t *t1_packed, const uint8_t *msgs,
                           const uint64_t *offsets, size_t n, const uint8_t *z, const uint8_t *h, const uint8_t *ctilde,
                           uint8_t *ok);
+int dil_verify_multi_dev(dil_engine_t *e, int level, const uint8_t *d_rho, const uint8_t *d_t1_packed, const uint8_t *d_msgs,
+                         const uint64_t *d_offsets, size_t n, const uint8_t *d_z, const uint8_t *d_h, const uint8_t *d_ctilde,
+                         uint8_t *d_ok, void *stream);
 
 /* ---- batched key generation (combined_top.v mode 0, FSM :754-1079; outputs as tb_keygen_top.v:180-275) ----
  * xi: n x 32-byte seeds.  Outputs per key, bit-packed exactly as the KAT files: rho, K, tr (32 B each),
