@@ -82,8 +82,17 @@ cudaError_t dmalloc(T** p, size_t count) {
 // longer saturated by distinct items, so each remaining item tries up to SPEC_MAX consecutive kappa
 // values per round in parallel slots; the smallest accepted kappa wins, which is exactly the
 // sequential result of combined_top.v:2217-2228 (restart with the next kappa).
-constexpr size_t SPEC_SLOT_TARGET = 32768;
+constexpr size_t SPEC_SLOT_TARGET_DEFAULT = 32768;
 constexpr size_t SPEC_MAX = 16;
+static size_t spec_slot_target() {   // DIL_SPEC_TARGET overrides (tuning knob)
+    static size_t v = 0;
+    if (!v) {
+        const char* e = std::getenv("DIL_SPEC_TARGET");
+        v = e && std::atol(e) > 0 ? (size_t)std::atol(e) : SPEC_SLOT_TARGET_DEFAULT;
+    }
+    return v;
+}
+#define SPEC_SLOT_TARGET spec_slot_target()
 
 void free_ws(dil_sign_key* k) {
     void* ptrs[] = {k->mu_d, k->rhop, k->w1p, k->kappa, k->active[0], k->active[1], k->count, k->y, k->w, k->c,
