@@ -19,7 +19,7 @@ cudaError_t launch_expand_a(int32_t* a_hat, const uint8_t* rho, size_t n_rho, in
 cudaError_t launch_matvec_expand(int32_t* w, const uint8_t* rho, const int32_t* v, int k, int l, size_t batch,
                                  unsigned flags, int sm_count, cudaStream_t st);
 cudaError_t launch_signcore(int32_t* w, const int32_t* a_hat, const int32_t* y, int k, int l, size_t batch, int sm_count,
-                            cudaStream_t st);
+                            cudaStream_t st, uint32_t* work_ctr = nullptr);
 
 // ---- sign pipeline (sign_kernels.cu) ----
 cudaError_t launch_sign_init(uint64_t* mu, uint64_t* rhop, uint16_t* kappa, const uint8_t* tr, const uint8_t* key,
@@ -30,11 +30,14 @@ cudaError_t launch_pack_w1(int level, uint32_t* w1p, const int32_t* w, uint32_t 
 cudaError_t launch_challenge(int level, int8_t* c, uint64_t* ct_slot, const uint64_t* mu, const uint64_t* w1p,
                              const uint32_t* active, uint32_t n_slots, uint32_t spec, cudaStream_t st);
 cudaError_t launch_sign_tail(int level, int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat,
-                             const int32_t* w, const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st);
+                             const int32_t* w, const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st, uint32_t* work_ctr = nullptr);
 cudaError_t launch_resolve(int level, uint8_t* zp, uint8_t* h_out, uint64_t* ct_out, uint32_t* attempts, uint16_t* kappa,
                            uint32_t* next_active, uint32_t* next_count, const int32_t* zslot, const uint8_t* h_slot,
                            const uint64_t* ct_slot, const uint8_t* accepted, const uint32_t* active, uint32_t n_items,
-                           uint32_t spec, cudaStream_t st);
+                           uint32_t spec, uint32_t* done_list, cudaStream_t st);
+cudaError_t launch_drain(uint8_t* hz, uint8_t* hh, uint8_t* hct, uint32_t* hatt, const uint8_t* zp, const uint8_t* h,
+                         const uint8_t* ct, const uint32_t* att, const uint32_t* list, uint32_t n, uint32_t zb, uint32_t hb,
+                         cudaStream_t st);
 cudaError_t launch_iota(uint32_t* dst, uint32_t n, cudaStream_t st);
 cudaError_t launch_publish_count(uint32_t* host_dst_dev, const uint32_t* src, cudaStream_t st);
 // ---- verify pipeline ----

@@ -140,7 +140,8 @@ constexpr int shared_min_ctas(int k, int l, int warps = 8) { return warps > 8 ? 
 template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT>
 __global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L, WARPS)) matvec_shared_kernel(int32_t* __restrict__ w, const int32_t* __restrict__ a_hat,
                                                                    const uint8_t* __restrict__ rho,
-                                                                   const int32_t* __restrict__ v, uint32_t batch) {
+                                                                   const int32_t* __restrict__ v, uint32_t batch,
+                                                                   uint32_t* __restrict__ work_ctr) {
     extern __shared__ __align__(16) uint32_t smem_u32v[];
     uint32_t* a_sm = smem_u32v;                               // K*L*A_STRIDE
     uint32_t* scr_all = smem_u32v + K * L * A_STRIDE;         // WARPS*SCRATCH_WORDS
@@ -148,6 +149,12 @@ __global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L, WARPS)) matv
     // When the output is inverse-transformed the matrix is stored pre-multiplied by 256^-1 (once per CTA),
     // which removes the scaling multiplications from every inverse transform (ntt_inv_warp<true>).
     auto scale = [](uint32_t v) -> uint32_t { return INTT_OUT ? mul_full(v, INV256) : v; };
+    if (work_ctr != nullptr) {   // a CTA that starts when every item is already claimed leaves at once (uniform decision)
+        __shared__ uint32_t late;
+        if (threadIdx.x == 0) late = *reinterpret_cast<volatile uint32_t*>(work_ctr) >= batch;
+        __syncthreads();
+        if (late) return;
+    }
     if constexpr (EXPAND) {
         for (int t = threadIdx.x; t < K * L; t += blockDim.x) {
             uint32_t* out = a_sm + t * A_STRIDE;
@@ -163,8 +170,24 @@ __global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L, WARPS)) matv
     }
     __syncthreads();
     uint32_t* scr = scr_all + warp * SCRATCH_WORDS;
-    for (uint32_t item = blockIdx.x * WARPS + warp; item < batch; item += gridDim.x * WARPS)
-        item_core<K, L, NTT_IN, INTT_OUT>(w + (size_t)item * K * N, v + (size_t)item * L * N, a_sm, scr, lane);
+    // With a work counter (zeroed by the caller before the launch) items are claimed dynamically, one atomic
+    // per item, issued before the current item is processed so its latency is hidden.  Dynamic claiming keeps
+    // the kernel balanced when SMs run at different speeds or are partly taken by other streams' kernels (a
+    // CTA that starts late finds the counter exhausted and leaves).  Without a counter the distribution is
+    // the static warp-stride one.
+    if (work_ctr != nullptr) {
+        uint32_t claim = 0;
+        if (lane == 0) claim = atomicAdd(work_ctr, 1u);
+        uint32_t item = __shfl_sync(0xffffffffu, claim, 0);
+        while (item < batch) {
+            if (lane == 0) claim = atomicAdd(work_ctr, 1u);
+            item_core<K, L, NTT_IN, INTT_OUT>(w + (size_t)item * K * N, v + (size_t)item * L * N, a_sm, scr, lane);
+            item = __shfl_sync(0xffffffffu, claim, 0);
+        }
+    } else {
+        for (uint32_t item = blockIdx.x * WARPS + warp; item < batch; item += gridDim.x * WARPS)
+            item_core<K, L, NTT_IN, INTT_OUT>(w + (size_t)item * K * N, v + (size_t)item * L * N, a_sm, scr, lane);
+    }
 }
 
 // ---- per-item-rho kernel: G items per CTA ----
@@ -211,7 +234,7 @@ constexpr size_t shared_smem_bytes(int warps) {
 
 template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT, int MAX_CTAS = 8>
 static cudaError_t launch_shared_t(int32_t* w, const int32_t* a_hat, const uint8_t* rho, const int32_t* v, size_t batch,
-                                   int sm_count, cudaStream_t st) {
+                                   int sm_count, cudaStream_t st, uint32_t* work_ctr = nullptr) {
     auto kern = matvec_shared_kernel<K, L, WARPS, EXPAND, NTT_IN, INTT_OUT>;
     constexpr size_t smem = shared_smem_bytes<K, L>(WARPS);
     static bool configured = false;
@@ -227,13 +250,14 @@ static cudaError_t launch_shared_t(int32_t* w, const int32_t* a_hat, const uint8
     size_t want = (batch + WARPS - 1) / WARPS;
     size_t cap = (size_t)sm_count * ctas_per_sm;
     unsigned grid = (unsigned)(want < cap ? want : cap);
-    kern<<<grid, WARPS * 32, smem, st>>>(w, a_hat, rho, v, (uint32_t)batch);
+    kern<<<grid, WARPS * 32, smem, st>>>(w, a_hat, rho, v, (uint32_t)batch, work_ctr);
     return cudaGetLastError();
 }
 
 template <int K, int L, bool EXPAND>
 static cudaError_t launch_shared_flags(int32_t* w, const int32_t* a_hat, const uint8_t* rho, const int32_t* v, size_t batch,
-                                       bool ntt_in, bool intt_out, int sm_count, cudaStream_t st) {
+                                       bool ntt_in, bool intt_out, int sm_count, cudaStream_t st,
+                                       uint32_t* work_ctr = nullptr) {
     constexpr int WARPS = 8;
     if (ntt_in && intt_out) {
         // one 16-warp CTA per SM measured 3-5 % faster than two 8-warp CTAs (DIL_SC_WARPS=8 selects the latter)
@@ -241,9 +265,9 @@ static cudaError_t launch_shared_flags(int32_t* w, const int32_t* a_hat, const u
         if (big < 0) { const char* e = std::getenv("DIL_SC_WARPS"); big = (e && std::atoi(e) == 8) ? 0 : 1; }
         static int half = -1;   // overlap experiment: one 8-warp CTA per SM (half an SM's registers)
         if (half < 0) { const char* e = std::getenv("DIL_SC_HALF"); half = (e && std::atoi(e)) ? 1 : 0; }
-        if (half) return launch_shared_t<K, L, 8, EXPAND, true, true, 1>(w, a_hat, rho, v, batch, sm_count, st);
-        if (big) return launch_shared_t<K, L, 16, EXPAND, true, true>(w, a_hat, rho, v, batch, sm_count, st);
-        return launch_shared_t<K, L, WARPS, EXPAND, true, true>(w, a_hat, rho, v, batch, sm_count, st);
+        if (half) return launch_shared_t<K, L, 8, EXPAND, true, true, 1>(w, a_hat, rho, v, batch, sm_count, st, work_ctr);
+        if (big) return launch_shared_t<K, L, 16, EXPAND, true, true>(w, a_hat, rho, v, batch, sm_count, st, work_ctr);
+        return launch_shared_t<K, L, WARPS, EXPAND, true, true>(w, a_hat, rho, v, batch, sm_count, st, work_ctr);
     }
     if (ntt_in) return launch_shared_t<K, L, WARPS, EXPAND, true, false>(w, a_hat, rho, v, batch, sm_count, st);
     if (intt_out) return launch_shared_t<K, L, WARPS, EXPAND, false, true>(w, a_hat, rho, v, batch, sm_count, st);
@@ -293,11 +317,11 @@ cudaError_t launch_matvec_expand(int32_t* w, const uint8_t* rho, const int32_t* 
 }
 
 cudaError_t launch_signcore(int32_t* w, const int32_t* a_hat, const int32_t* y, int k, int l, size_t batch, int sm_count,
-                            cudaStream_t st) {
+                            cudaStream_t st, uint32_t* work_ctr) {
     if (batch == 0) return cudaSuccess;
-    if (k == 4 && l == 4) return launch_shared_flags<4, 4, false>(w, a_hat, nullptr, y, batch, true, true, sm_count, st);
-    if (k == 6 && l == 5) return launch_shared_flags<6, 5, false>(w, a_hat, nullptr, y, batch, true, true, sm_count, st);
-    if (k == 8 && l == 7) return launch_shared_flags<8, 7, false>(w, a_hat, nullptr, y, batch, true, true, sm_count, st);
+    if (k == 4 && l == 4) return launch_shared_flags<4, 4, false>(w, a_hat, nullptr, y, batch, true, true, sm_count, st, work_ctr);
+    if (k == 6 && l == 5) return launch_shared_flags<6, 5, false>(w, a_hat, nullptr, y, batch, true, true, sm_count, st, work_ctr);
+    if (k == 8 && l == 7) return launch_shared_flags<8, 7, false>(w, a_hat, nullptr, y, batch, true, true, sm_count, st, work_ctr);
     return cudaErrorInvalidValue;
 }
 

@@ -6,6 +6,8 @@
 // ExpandMask -> fused sign core -> w1 pack -> challenge -> tail over the active items.
 #include <cuda_runtime.h>
 
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -30,7 +32,8 @@ struct dil_sign_key {
     size_t cap = 0;
     uint64_t *mu_d = nullptr, *rhop = nullptr, *w1p = nullptr;
     uint16_t* kappa = nullptr;
-    uint32_t *active[2] = {nullptr, nullptr}, *count = nullptr;
+    uint32_t *active[2] = {nullptr, nullptr}, *count = nullptr;   // [0] next round's size, [1] sign-core work counter, [2] tail work counter, [3] finished items
+    uint32_t* done_list = nullptr;   // finished items in completion order (host path: per-round drain)
     int32_t *y = nullptr, *w = nullptr;
     int8_t* c = nullptr;
     uint8_t *h_slot = nullptr, *accepted = nullptr;
@@ -96,12 +99,12 @@ static size_t spec_slot_target() {   // DIL_SPEC_TARGET overrides (tuning knob)
 
 void free_ws(dil_sign_key* k) {
     void* ptrs[] = {k->mu_d, k->rhop, k->w1p, k->kappa, k->active[0], k->active[1], k->count, k->y, k->w, k->c,
-                    k->h_slot, k->accepted, k->ct_slot};
+                    k->h_slot, k->accepted, k->ct_slot, k->done_list};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     k->mu_d = k->rhop = k->w1p = k->ct_slot = nullptr;
     k->kappa = nullptr;
-    k->active[0] = k->active[1] = k->count = nullptr;
+    k->active[0] = k->active[1] = k->count = k->done_list = nullptr;
     k->y = k->w = nullptr;
     k->c = nullptr;
     k->h_slot = k->accepted = nullptr;
@@ -122,6 +125,7 @@ int ensure_ws(dil_engine* e, dil_sign_key* k, size_t n) {
     A(dmalloc(&k->active[0], n));
     A(dmalloc(&k->active[1], n));
     A(dmalloc(&k->count, 4));
+    A(dmalloc(&k->done_list, n));
     A(dmalloc(&k->w1p, slots * (size_t)(P.k * P.w1_bytes / 8)));
     A(dmalloc(&k->y, slots * (size_t)P.l * 256));
     A(dmalloc(&k->w, slots * (size_t)P.k * 256));
@@ -139,12 +143,28 @@ int ensure_ws(dil_engine* e, dil_sign_key* k, size_t n) {
     return DIL_OK;
 }
 
+// Host-path streaming: device aliases of the caller's pinned (mapped) output buffers for the batch being
+// signed.  After every rejection round the signatures that round finished are copied out by drain_kernel
+// on `stream`, concurrently with the following rounds, so that only the last round's few signatures are
+// still on the device when signing ends.
+struct DrainTarget {
+    uint8_t *z = nullptr, *h = nullptr, *ct = nullptr;
+    uint32_t* att = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t idle = nullptr;   // recorded on `stream` after the last drain of a batch
+};
+
 // the round loop; all pointers are device pointers
 int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uint64_t* d_off, size_t n, uint8_t* d_zp,
-                uint8_t* d_h, uint8_t* d_ct, uint32_t* d_att, cudaStream_t st) {
+                uint8_t* d_h, uint8_t* d_ct, uint32_t* d_att, cudaStream_t st, const DrainTarget* drain = nullptr) {
     const LevelParams& P = k->P;
     int rc = ensure_ws(e, k, n);
     if (rc) return rc;
+    if (drain) {
+        // the previous batch's last drains still read done_list: let them finish before it is rewritten
+        CK(cudaStreamWaitEvent(st, drain->idle, 0));
+        CK(cudaMemsetAsync(k->count + 3, 0, 4, st));
+    }
     uint64_t launches = 0;
     const bool prof = k->profile;
     if (prof) {
@@ -167,6 +187,9 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
     }
     uint32_t n_active = (uint32_t)n, rounds = 0;
     int cur = 0;
+    // DIL_SIGN_STATIC=1: static warp-stride distribution in the two persistent kernels (A/B measurements)
+    const char* dyn_env = std::getenv("DIL_SIGN_STATIC");
+    const bool dyn = !(dyn_env && std::atoi(dyn_env) != 0);
     while (n_active > 0) {
         if (++rounds > 4000) {
             e->last_error = "sign: rejection loop did not terminate";
@@ -178,12 +201,12 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
             spec = room < 1 ? 1 : (room > SPEC_MAX ? SPEC_MAX : room);
         }
         const uint32_t n_slots = (uint32_t)(n_active * spec);
-        CK(cudaMemsetAsync(k->count, 0, 4, st));
+        CK(cudaMemsetAsync(k->count, 0, 12, st));   // next round's size and the two work counters
         PROF_BEGIN(1);
         CK(dil::launch_expand_mask(P.level, k->y, k->rhop, k->kappa, k->active[cur], n_slots, (uint32_t)spec, st));
         PROF_END(1, n_slots);
         PROF_BEGIN(2);
-        CK(dil::launch_signcore(k->w, k->a_hat, k->y, P.k, P.l, n_slots, e->sm_count, st));
+        CK(dil::launch_signcore(k->w, k->a_hat, k->y, P.k, P.l, n_slots, e->sm_count, st, dyn ? k->count + 1 : nullptr));
         PROF_END(2, n_slots);
         PROF_BEGIN(3);
         CK(dil::launch_pack_w1(P.level, reinterpret_cast<uint32_t*>(k->w1p), k->w, n_slots, st));
@@ -192,11 +215,13 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
         CK(dil::launch_challenge(P.level, k->c, k->ct_slot, k->mu_d, k->w1p, k->active[cur], n_slots, (uint32_t)spec, st));
         PROF_END(4, n_slots);
         PROF_BEGIN(5);
-        CK(dil::launch_sign_tail(P.level, k->y, k->h_slot, k->accepted, k->key_hat, k->w, k->c, n_slots, e->sm_count, st));
+        CK(dil::launch_sign_tail(P.level, k->y, k->h_slot, k->accepted, k->key_hat, k->w, k->c, n_slots, e->sm_count, st,
+                                 dyn ? k->count + 2 : nullptr));
         PROF_END(5, n_slots);
         PROF_BEGIN(6);
         CK(dil::launch_resolve(P.level, d_zp, d_h, reinterpret_cast<uint64_t*>(d_ct), d_att, k->kappa, k->active[cur ^ 1], k->count,
-                               k->y, k->h_slot, k->ct_slot, k->accepted, k->active[cur], n_active, (uint32_t)spec, st));
+                               k->y, k->h_slot, k->ct_slot, k->accepted, k->active[cur], n_active, (uint32_t)spec,
+                               drain ? k->done_list : nullptr, st));
         PROF_END(6, n_active);
         launches += 6;
         if (!k->count_host) {
@@ -212,9 +237,16 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
                 CK(cudaEventElapsedTime(&ms, k->ev[2 * cls], k->ev[2 * cls + 1]));
                 k->prof_ms[cls] += ms;
             }
+        if (drain && next < n_active) {
+            // the stream was just synchronised, so this round's signatures are final in the staging arrays
+            CK(dil::launch_drain(drain->z, drain->h, drain->ct, drain->att, d_zp, d_h, d_ct, d_att, k->done_list + (n - n_active),
+                                 n_active - next, (uint32_t)(P.l * P.z_bytes), (uint32_t)(P.omega + P.k), drain->stream));
+            launches++;
+        }
         n_active = next;
         cur ^= 1;
     }
+    if (drain) CK(cudaEventRecord(drain->idle, drain->stream));
     e->launches += launches;
     k->last_rounds = rounds;
     return DIL_OK;
@@ -363,8 +395,63 @@ int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs,
         CK(dmalloc(&k->att_d, n));
         k->out_cap = n;
     }
+    const auto t_begin = std::chrono::steady_clock::now();
     CK(cudaMemcpyAsync(k->msgs_d, msgs, offsets[n], cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(k->off_d, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    cudaStream_t cs = e->copy_stream;
+    // Streaming path: when every output buffer is pinned host memory the device can address (cudaHostAlloc /
+    // cudaHostRegister; torch's pinned tensors are), finished signatures leave round by round (DrainTarget)
+    // and the transfer hides behind the remaining rounds.  Pageable buffers take the chunked copy path below.
+    {
+        // DIL_SIGN_DRAIN=0 forces the chunked copy path (A/B measurements); DIL_SIGN_CHUNK overrides the batch
+        // size of the streaming path (tests use it to cover the multi-batch case at small sizes)
+        const char* ev = std::getenv("DIL_SIGN_DRAIN");
+        const bool want = !(ev && std::atoi(ev) == 0);
+        ev = std::getenv("DIL_SIGN_CHUNK");
+        const size_t CHUNK = ev && std::atol(ev) > 0 ? (size_t)std::atol(ev) : 262144;
+        DrainTarget dt;
+        auto dev_alias = [&](const void* p, size_t align) -> void* {
+            cudaPointerAttributes a{};
+            if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+            if (reinterpret_cast<uintptr_t>(a.devicePointer) & (align - 1)) return nullptr;
+            return a.devicePointer;
+        };
+        dt.z = static_cast<uint8_t*>(dev_alias(z, 16));
+        dt.h = static_cast<uint8_t*>(dev_alias(h, 1));
+        dt.ct = static_cast<uint8_t*>(dev_alias(ctilde, 16));
+        dt.att = attempts ? static_cast<uint32_t*>(dev_alias(attempts, 4)) : nullptr;
+        if (want && dt.z && dt.h && dt.ct && (!attempts || dt.att)) {
+            dt.stream = cs;
+            CK(cudaEventCreateWithFlags(&dt.idle, cudaEventDisableTiming));
+            cudaError_t er = cudaEventRecord(dt.idle, cs);
+            int rc = er == cudaSuccess ? DIL_OK : fail(e, er, "sign drain event");
+            // large batches amortise the rejection tail better; 2^18 items keep the workspace at a few GiB
+            for (size_t lo = 0; lo < n && rc == DIL_OK;) {
+                const size_t m = n - lo <= CHUNK + CHUNK / 4 ? n - lo : CHUNK;
+                DrainTarget t = dt;
+                t.z += lo * zb; t.h += lo * hb; t.ct += lo * 32;
+                if (t.att) t.att += lo;
+                rc = sign_rounds(e, k, k->msgs_d, k->off_d + lo, m, k->zp_d + lo * zb, k->h_d + lo * hb, k->ct_d + lo * 32,
+                                 k->att_d + lo, st, &t);
+                lo += m;
+            }
+            cudaError_t e2 = cudaStreamSynchronize(st);
+            const auto t_compute = std::chrono::steady_clock::now();
+            cudaError_t e1 = cudaStreamSynchronize(cs);
+            if (std::getenv("DIL_SIGN_TRACE")) {
+                const auto t_end = std::chrono::steady_clock::now();
+                auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+                std::fprintf(stderr, "[dil] sign host path: signing done at %.3f ms, drain done at %.3f ms\n", ms(t_begin, t_compute),
+                             ms(t_begin, t_end));
+            }
+            cudaEventDestroy(dt.idle);
+            if (rc) return rc;
+            if (e1 != cudaSuccess) return fail(e, e1, "sign drain sync");
+            if (e2 != cudaSuccess) return fail(e, e2, "sign sync");
+            return DIL_OK;
+        }
+    }
     // Chunked so that the D2H of a finished chunk's signatures (2.4-4.6 KB each, ~47 ns per signature over
     // PCIe) overlaps the signing of the next chunk.  Signing has a fixed per-batch latency (rejection
     // tail), so chunks are unequal: 64 K-message chunks while a lot remains, then a 3:1 split so that only
@@ -376,7 +463,6 @@ int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs,
         if (rem > 16384) { size_t a = (rem * 3 / 4 + 255) & ~(size_t)255; chunks.push_back(a); chunks.push_back(rem - a); }
         else chunks.push_back(rem);
     }
-    cudaStream_t cs = e->copy_stream;
     cudaEvent_t done = nullptr;
     CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
     int rc = DIL_OK;

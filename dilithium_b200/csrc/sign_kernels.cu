@@ -277,13 +277,20 @@ __device__ __forceinline__ int32_t centre(uint32_t a) { return (int32_t)a - (int
 template <int K, int L, int32_t GAMMA1, int32_t GAMMA2, int BETA, int OMEGA, int WARPS, int CTAS>
 __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
     int32_t* __restrict__ y /* in: y, out: z (in place) */, uint8_t* __restrict__ h_slot, uint8_t* __restrict__ accepted,
-    const int32_t* __restrict__ key_hat, const int32_t* __restrict__ w, const int8_t* __restrict__ c, uint32_t n_slots) {
+    const int32_t* __restrict__ key_hat, const int32_t* __restrict__ w, const int8_t* __restrict__ c, uint32_t n_slots,
+    uint32_t* __restrict__ work_ctr) {
     extern __shared__ __align__(16) uint32_t sm_words[];
     constexpr int NKEY = L + 2 * K;
     uint32_t* key_sm = sm_words;                       // NKEY * 256
     uint32_t* scr_all = sm_words + NKEY * N;           // WARPS * SCRATCH_WORDS
     uint32_t* hm_all = scr_all + WARPS * SCRATCH_WORDS;  // WARPS * K * 8 hint masks
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (work_ctr != nullptr) {   // a CTA that starts when every slot is already claimed leaves at once (uniform decision)
+        __shared__ uint32_t late;
+        if (threadIdx.x == 0) late = *reinterpret_cast<volatile uint32_t*>(work_ctr) >= n_slots;
+        __syncthreads();
+        if (late) return;
+    }
     // key polynomials are kept pre-multiplied by 256^-1 so that every inverse transform below can skip
     // its scaling multiplications (ntt_inv_warp<true>)
     for (int t = threadIdx.x; t < NKEY * (N / 4); t += blockDim.x) {
@@ -298,7 +305,17 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
     InvTw itw;
     load_inv_tw(itw, &TW_INV, lane);
 
-    for (uint32_t a = blockIdx.x * WARPS + warp; a < n_slots; a += gridDim.x * WARPS) {
+    // Slots are claimed dynamically when the caller passes a (zeroed) work counter: the work per slot varies
+    // by an order of magnitude (early exits below), and SMs may run at different speeds or be partly taken by
+    // other streams' kernels; the claim for the next slot is issued before the current one is processed.
+    const uint32_t stride = gridDim.x * WARPS;
+    uint32_t claim = 0, a = blockIdx.x * WARPS + warp;
+    if (work_ctr != nullptr) {
+        if (lane == 0) claim = atomicAdd(work_ctr, 1u);
+        a = __shfl_sync(0xffffffffu, claim, 0);
+    }
+    for (; a < n_slots; a = work_ctr != nullptr ? __shfl_sync(0xffffffffu, claim, 0) : a + stride) {
+        if (work_ctr != nullptr && lane == 0) claim = atomicAdd(work_ctr, 1u);
         // c_hat in layout C
         uint32_t ch[8];
         {
@@ -403,7 +420,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(uint8_t* __restrict__ zp, 
                                                       uint32_t* __restrict__ next_count, const int32_t* __restrict__ zslot,
                                                       const uint8_t* __restrict__ h_slot, const uint64_t* __restrict__ ct_slot,
                                                       const uint8_t* __restrict__ accepted, const uint32_t* __restrict__ active,
-                                                      uint32_t n_items, uint32_t spec) {
+                                                      uint32_t n_items, uint32_t spec, uint32_t* __restrict__ done_list) {
     const int lane = threadIdx.x & 31;
     const uint32_t idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (idx >= n_items) return;
@@ -470,7 +487,39 @@ __global__ void __launch_bounds__(256) resolve_kernel(uint8_t* __restrict__ zp, 
     }
     for (int t = lane; t < HB; t += 32) h_out[(size_t)item * HB + t] = h_slot[(size_t)a * HB + t];
     if (lane < 4) ct_out[(size_t)item * 4 + lane] = ct_slot[(size_t)a * 4 + lane];
-    if (lane == 0) attempts[item] = (uint32_t)kappa[item] + s + 1;
+    if (lane == 0) {
+        attempts[item] = (uint32_t)kappa[item] + s + 1;
+        // completion-ordered list of finished items (next_count[3] counts them over the whole batch): the
+        // host path drains each round's finished signatures to host memory while later rounds still sign
+        if (done_list) done_list[atomicAdd(next_count + 3, 1u)] = item;
+    }
+}
+
+// Copies the finished signatures named by list[0..n) from the device staging arrays into the caller's
+// pinned host buffers (mapped into the device address space): posted PCIe writes, 512 contiguous bytes
+// per warp store.  Runs on the copy stream next to the following rejection rounds (launch_drain).
+__global__ void __launch_bounds__(512, 4) drain_kernel(uint8_t* __restrict__ hz, uint8_t* __restrict__ hh, uint8_t* __restrict__ hct,
+                                                        uint32_t* __restrict__ hatt, const uint8_t* __restrict__ zp,
+                                                        const uint8_t* __restrict__ h, const uint8_t* __restrict__ ct,
+                                                        const uint32_t* __restrict__ att, const uint32_t* __restrict__ list,
+                                                        uint32_t n, uint32_t zb, uint32_t hb) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t nv = zb >> 4;
+    for (uint32_t i = warp; i < n; i += nwarps) {
+        const uint32_t item = list[i];
+        const uint4* s = reinterpret_cast<const uint4*>(zp + (size_t)item * zb);
+        uint4* d = reinterpret_cast<uint4*>(hz + (size_t)item * zb);
+        uint32_t t = lane;
+        for (; t + 96 < nv; t += 128) {
+            uint4 a = __ldcs(s + t), b = __ldcs(s + t + 32), c = __ldcs(s + t + 64), e = __ldcs(s + t + 96);
+            d[t] = a; d[t + 32] = b; d[t + 64] = c; d[t + 96] = e;
+        }
+        for (; t < nv; t += 32) d[t] = __ldcs(s + t);
+        if (lane < 2) reinterpret_cast<uint4*>(hct + (size_t)item * 32)[lane] = reinterpret_cast<const uint4*>(ct + (size_t)item * 32)[lane];
+        for (uint32_t b = lane; b < hb; b += 32) hh[(size_t)item * hb + b] = h[(size_t)item * hb + b];
+        if (hatt && lane == 0) hatt[item] = att[item];
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -524,6 +573,29 @@ cudaError_t launch_pack_w1(int level, uint32_t* w1p, const int32_t* w, uint32_t 
     return cudaGetLastError();
 }
 
+cudaError_t launch_drain(uint8_t* hz, uint8_t* hh, uint8_t* hct, uint32_t* hatt, const uint8_t* zp, const uint8_t* h,
+                         const uint8_t* ct, const uint32_t* att, const uint32_t* list, uint32_t n, uint32_t zb, uint32_t hb,
+                         cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    // A handful of 16-warp CTAs, each asking for enough (unused) dynamic shared memory that the shared-memory
+    // using signing kernels cannot be co-resident: the drain owns its few SMs instead of slowing every SM's
+    // memory pipeline with PCIe-paced stores.  Launched right after a round's stream synchronisation, i.e.
+    // when the SMs are empty.  DIL_DRAIN_CTAS / DIL_DRAIN_SMEM_KB are tuning knobs.
+    static int ctas = -1, smem_kb = -1;
+    if (ctas < 0) {
+        const char* e = std::getenv("DIL_DRAIN_CTAS");
+        ctas = (e && std::atoi(e) > 0) ? std::atoi(e) : 4;
+        e = std::getenv("DIL_DRAIN_SMEM_KB");
+        smem_kb = (e && std::atoi(e) >= 0) ? std::atoi(e) : 200;
+        if (smem_kb > 226) smem_kb = 226;
+        cudaError_t er = cudaFuncSetAttribute(drain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kb * 1024);
+        if (er != cudaSuccess) { ctas = -1; return er; }
+    }
+    unsigned grid = (n + 15) / 16 < (unsigned)ctas ? (n + 15) / 16 : (unsigned)ctas;
+    drain_kernel<<<grid, 512, (size_t)smem_kb * 1024, st>>>(hz, hh, hct, hatt, zp, h, ct, att, list, n, zb, hb);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_challenge(int level, int8_t* c, uint64_t* ct_slot, const uint64_t* mu, const uint64_t* w1p,
                              const uint32_t* active, uint32_t n_slots, uint32_t spec, cudaStream_t st) {
     if (n_slots == 0) return cudaSuccess;
@@ -542,7 +614,7 @@ cudaError_t launch_challenge(int level, int8_t* c, uint64_t* ct_slot, const uint
 
 template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA, int WARPS, int CTAS>
 static cudaError_t launch_sign_tail_w(int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat, const int32_t* w,
-                                      const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st) {
+                                      const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st, uint32_t* work_ctr) {
     constexpr size_t smem = (size_t)((L + 2 * K) * N + WARPS * SCRATCH_WORDS + WARPS * K * 8) * 4;
     auto kern = sign_tail_kernel<K, L, G1, G2, BETA, OMEGA, WARPS, CTAS>;
     static bool configured = false;
@@ -553,28 +625,29 @@ static cudaError_t launch_sign_tail_w(int32_t* y, uint8_t* h_slot, uint8_t* acce
     }
     unsigned want = (n_slots + WARPS - 1) / WARPS;
     unsigned cap = (unsigned)sm_count * CTAS;
-    kern<<<want < cap ? want : cap, WARPS * 32, smem, st>>>(y, h_slot, accepted, key_hat, w, c, n_slots);
+    kern<<<want < cap ? want : cap, WARPS * 32, smem, st>>>(y, h_slot, accepted, key_hat, w, c, n_slots, work_ctr);
     return cudaGetLastError();
 }
 
 template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA>
 static cudaError_t launch_sign_tail_t(int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat, const int32_t* w,
-                                      const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st) {
+                                      const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st, uint32_t* work_ctr) {
     // one 24-warp CTA per SM is marginally faster than three 8-warp CTAs (DIL_TAIL_WARPS=8 selects the latter)
     static int big = -1;
     if (big < 0) { const char* e = std::getenv("DIL_TAIL_WARPS"); big = (e && std::atoi(e) == 8) ? 0 : 1; }
-    if (overlap_knob("DIL_TAIL_HALF", 0)) return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 12, 1>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st);
-    if (big) return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 24, 1>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st);
-    return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 8, 3>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st);
+    if (overlap_knob("DIL_TAIL_HALF", 0)) return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 12, 1>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr);
+    if (big) return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 24, 1>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr);
+    return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 8, 3>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr);
 }
 
 cudaError_t launch_sign_tail(int level, int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat,
-                             const int32_t* w, const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st) {
+                             const int32_t* w, const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st,
+                             uint32_t* work_ctr) {
     if (n_slots == 0) return cudaSuccess;
     switch (level) {
-        case 2: return launch_sign_tail_t<4, 4, 1 << 17, (Q_I - 1) / 88, 78, 80>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st);
-        case 3: return launch_sign_tail_t<6, 5, 1 << 19, (Q_I - 1) / 32, 196, 55>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st);
-        case 5: return launch_sign_tail_t<8, 7, 1 << 19, (Q_I - 1) / 32, 120, 75>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st);
+        case 2: return launch_sign_tail_t<4, 4, 1 << 17, (Q_I - 1) / 88, 78, 80>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr);
+        case 3: return launch_sign_tail_t<6, 5, 1 << 19, (Q_I - 1) / 32, 196, 55>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr);
+        case 5: return launch_sign_tail_t<8, 7, 1 << 19, (Q_I - 1) / 32, 120, 75>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr);
     }
     return cudaErrorInvalidValue;
 }
@@ -582,13 +655,13 @@ cudaError_t launch_sign_tail(int level, int32_t* y, uint8_t* h_slot, uint8_t* ac
 cudaError_t launch_resolve(int level, uint8_t* zp, uint8_t* h_out, uint64_t* ct_out, uint32_t* attempts, uint16_t* kappa,
                            uint32_t* next_active, uint32_t* next_count, const int32_t* zslot, const uint8_t* h_slot,
                            const uint64_t* ct_slot, const uint8_t* accepted, const uint32_t* active, uint32_t n_items,
-                           uint32_t spec, cudaStream_t st) {
+                           uint32_t spec, uint32_t* done_list, cudaStream_t st) {
     if (n_items == 0) return cudaSuccess;
     unsigned grid = (n_items + 7) / 8;
     switch (level) {
-        case 2: resolve_kernel<4, 17, 84><<<grid, 256, 0, st>>>(zp, h_out, ct_out, attempts, kappa, next_active, next_count, zslot, h_slot, ct_slot, accepted, active, n_items, spec); break;
-        case 3: resolve_kernel<5, 19, 61><<<grid, 256, 0, st>>>(zp, h_out, ct_out, attempts, kappa, next_active, next_count, zslot, h_slot, ct_slot, accepted, active, n_items, spec); break;
-        case 5: resolve_kernel<7, 19, 83><<<grid, 256, 0, st>>>(zp, h_out, ct_out, attempts, kappa, next_active, next_count, zslot, h_slot, ct_slot, accepted, active, n_items, spec); break;
+        case 2: resolve_kernel<4, 17, 84><<<grid, 256, 0, st>>>(zp, h_out, ct_out, attempts, kappa, next_active, next_count, zslot, h_slot, ct_slot, accepted, active, n_items, spec, done_list); break;
+        case 3: resolve_kernel<5, 19, 61><<<grid, 256, 0, st>>>(zp, h_out, ct_out, attempts, kappa, next_active, next_count, zslot, h_slot, ct_slot, accepted, active, n_items, spec, done_list); break;
+        case 5: resolve_kernel<7, 19, 83><<<grid, 256, 0, st>>>(zp, h_out, ct_out, attempts, kappa, next_active, next_count, zslot, h_slot, ct_slot, accepted, active, n_items, spec, done_list); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

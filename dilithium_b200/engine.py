@@ -309,17 +309,28 @@ class SignKey:
         self.engine._check(self.engine._lib.dil_sign_get_profile(self._h, ms, units), "dil_sign_get_profile")
         return {name: (ms[i], int(units[i])) for i, name in enumerate(self.PROFILE_CLASSES)}
 
-    def sign(self, msgs):
+    def sign(self, msgs, pinned=False):
         """Sign a list of byte strings (host path, dil_sign_batch_host).
-        Returns (z[n, z_bytes], h[n, h_bytes], ctilde[n, 32], attempts[n])."""
+        Returns (z[n, z_bytes], h[n, h_bytes], ctilde[n, 32], attempts[n]).
+        pinned=True returns the outputs in pinned host memory, which lets the library stream finished
+        signatures out round by round instead of copying whole chunks afterwards."""
         n = len(msgs)
         off = np.zeros(n + 1, dtype=np.uint64)
         off[1:] = np.cumsum([len(m) for m in msgs])
         blob = np.frombuffer(b"".join(msgs), dtype=np.uint8).copy() if off[-1] else np.zeros(1, np.uint8)
-        z = np.empty((n, self.z_bytes), dtype=np.uint8)
-        h = np.empty((n, self.h_bytes), dtype=np.uint8)
-        c = np.empty((n, 32), dtype=np.uint8)
-        att = np.zeros(n, dtype=np.uint32)
+        if pinned:
+            import torch
+            self._pinned = [torch.empty(shape, dtype=dt).pin_memory() for shape, dt in
+                            (((max(n, 1), self.z_bytes), torch.uint8), ((max(n, 1), self.h_bytes), torch.uint8),
+                             ((max(n, 1), 32), torch.uint8), ((max(n, 1),), torch.int32))]
+            z, h, c = (t.numpy()[:n] for t in self._pinned[:3])
+            att = self._pinned[3].numpy()[:n].view(np.uint32)
+            att[:] = 0
+        else:
+            z = np.empty((n, self.z_bytes), dtype=np.uint8)
+            h = np.empty((n, self.h_bytes), dtype=np.uint8)
+            c = np.empty((n, 32), dtype=np.uint8)
+            att = np.zeros(n, dtype=np.uint32)
         P = ctypes.c_void_p
         rc = self.engine._lib.dil_sign_batch_host(self.engine._h, self._h, blob.ctypes.data_as(P), off.ctypes.data_as(P), n,
                                                   z.ctypes.data_as(P), h.ctypes.data_as(P), c.ctypes.data_as(P), att.ctypes.data_as(P))

@@ -64,3 +64,27 @@ def test_sign_large_batch_properties(eng, oracle):
         assert oracle.verify(level, K["rho"][0], K["t1"][0], msgs[m], z[m], h[m], c[m]) == 0, m
     z2, h2, c2, att2 = key.sign(msgs)
     assert np.array_equal(z, z2) and np.array_equal(h, h2) and np.array_equal(c, c2) and np.array_equal(att, att2)
+
+
+def test_sign_streaming_host_path(eng, monkeypatch):
+    """dil_sign_batch_host with pinned output buffers streams finished signatures out round by round
+    (drain_kernel into mapped host memory); results must equal the pageable-buffer path (chunked
+    copy-engine transfers) bit for bit, also when the batch is split (DIL_SIGN_CHUNK) and for ragged sizes."""
+    import dilithium_b200 as d
+    for level, n in ((2, 20000), (3, 3001), (5, 1025), (2, 1), (2, 0)):
+        K = ol.kat(level)
+        key = d.SignKey(eng, level, K["rho"][1], K["k"][1], K["tr"][1], K["s1"][1], K["s2"][1], K["t0"][1])
+        msgs = [int(i).to_bytes(4, "little") * (1 + i % 9) for i in range(n)]
+        ref = key.sign(msgs)
+        monkeypatch.delenv("DIL_SIGN_CHUNK", raising=False)
+        got = [np.array(a) for a in key.sign(msgs, pinned=True)]
+        monkeypatch.setenv("DIL_SIGN_CHUNK", "4096")
+        got2 = [np.array(a) for a in key.sign(msgs, pinned=True)]
+        monkeypatch.setenv("DIL_SIGN_DRAIN", "0")
+        got3 = [np.array(a) for a in key.sign(msgs, pinned=True)]
+        monkeypatch.delenv("DIL_SIGN_DRAIN")
+        for name, r, a, b, c in zip(("z", "h", "c", "att"), ref, got, got2, got3):
+            assert np.array_equal(r, a), (level, n, name, "streaming")
+            assert np.array_equal(r, b), (level, n, name, "streaming, split batch")
+            assert np.array_equal(r, c), (level, n, name, "pinned buffers, copy path")
+        key.close()
