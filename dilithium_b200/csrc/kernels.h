@@ -19,7 +19,7 @@ cudaError_t launch_expand_a(int32_t* a_hat, const uint8_t* rho, size_t n_rho, in
 cudaError_t launch_matvec_expand(int32_t* w, const uint8_t* rho, const int32_t* v, int k, int l, size_t batch,
                                  unsigned flags, int sm_count, cudaStream_t st);
 cudaError_t launch_signcore(int32_t* w, const int32_t* a_hat, const int32_t* y, int k, int l, size_t batch, int sm_count,
-                            cudaStream_t st, uint32_t* work_ctr = nullptr);
+                            cudaStream_t st, uint32_t* work_ctr = nullptr, uint8_t* w1p = nullptr);
 
 // ---- sign pipeline (sign_kernels.cu) ----
 cudaError_t launch_sign_init(uint64_t* mu, uint64_t* rhop, uint16_t* kappa, const uint8_t* tr, const uint8_t* key,

@@ -20,6 +20,7 @@
 #include "keccak.cuh"
 #include "kernels.h"
 #include "ntt_core.cuh"
+#include "rounding.cuh"
 
 namespace dil {
 
@@ -51,10 +52,14 @@ cudaError_t launch_expand_a(int32_t* a_hat, const uint8_t* rho, size_t n_rho, in
 // EXTRA = true (verification with per-item public keys): v_item holds L+1 polynomials, and the last one is
 // multiplied by a per-item column extra_item[i] read from global memory (-NTT(t1_i * 2^13)) instead of a
 // shared-memory matrix column.
-template <int K, int LA, bool NTT_IN, bool INTT_OUT, bool EXTRA = false>
+// W1 = true (signing): besides w the core also emits w1 = HighBits(w), bit-packed as encoder.v:96-133 (6 bits for
+// gamma2 = (Q-1)/88, i.e. K = 4, else 4 bits), into w1_item - the input of the challenge hash - so that no
+// separate pass has to read w again.
+template <int K, int LA, bool NTT_IN, bool INTT_OUT, bool EXTRA = false, bool W1 = false>
 __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const int32_t* __restrict__ v_item,
                                           const uint32_t* __restrict__ a_sm, uint32_t* __restrict__ scr, int lane,
-                                          const int32_t* __restrict__ extra_item = nullptr) {
+                                          const int32_t* __restrict__ extra_item = nullptr,
+                                          uint8_t* __restrict__ w1_item = nullptr) {
     constexpr int L = LA + (EXTRA ? 1 : 0);   // number of input polynomials
     uint32_t yh[L][8];  // NTT-domain inputs in layout C
     if constexpr (NTT_IN) {
@@ -123,6 +128,28 @@ __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const in
             int32_t* o = w_item + i * N + lane;
 #pragma unroll
             for (int r = 0; r < 8; r++) o[32 * r] = (int32_t)x[r];
+            if constexpr (W1) {
+                static_assert(INTT_OUT, "w1 is defined on the time-domain w");
+                constexpr int32_t G2 = K == 4 ? (Q_I - 1) / 88 : (Q_I - 1) / 32;
+                // this lane holds coefficients lane + 32 r: stage HighBits as bytes, re-read 8 consecutive ones
+                uint8_t* sb = reinterpret_cast<uint8_t*>(scr);
+#pragma unroll
+                for (int r = 0; r < 8; r++) sb[32 * r + lane] = (uint8_t)highbits<G2>(x[r]);
+                __syncwarp();
+                const uint2 q = reinterpret_cast<const uint2*>(sb)[lane];
+                if constexpr (G2 == (Q_I - 1) / 32) {
+                    auto p4 = [](uint32_t v) { return (v & 0xFu) | ((v >> 4) & 0xF0u) | ((v >> 8) & 0xF00u) | ((v >> 12) & 0xF000u); };
+                    reinterpret_cast<uint32_t*>(w1_item + i * 128)[lane] = p4(q.x) | (p4(q.y) << 16);
+                } else {
+                    auto p6 = [](uint32_t v) { return (v & 0x3Fu) | ((v >> 2) & 0xFC0u) | ((v >> 4) & 0x3F000u) | ((v >> 6) & 0xFC0000u); };
+                    const uint32_t a = p6(q.x), b = p6(q.y);   // 24 bits each
+                    uint16_t* d = reinterpret_cast<uint16_t*>(w1_item + i * 192 + 6 * lane);
+                    d[0] = (uint16_t)a;
+                    d[1] = (uint16_t)((a >> 16) | (b << 8));
+                    d[2] = (uint16_t)(b >> 8);
+                }
+                __syncwarp();   // the scratch is reused by the next transform
+            }
         } else {
             int4* o = reinterpret_cast<int4*>(w_item + i * N) + lane;
             o[0] = make_int4((int)x[0], (int)x[1], (int)x[2], (int)x[3]);
@@ -137,11 +164,13 @@ __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const in
 // integer-multiply pipe, not by latency.)
 constexpr int shared_min_ctas(int k, int l, int warps = 8) { return warps > 8 ? 1 : (k * l <= 56 ? 2 : 1); }
 
-template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT>
+template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT, bool W1 = false>
 __global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L, WARPS)) matvec_shared_kernel(int32_t* __restrict__ w, const int32_t* __restrict__ a_hat,
                                                                    const uint8_t* __restrict__ rho,
                                                                    const int32_t* __restrict__ v, uint32_t batch,
-                                                                   uint32_t* __restrict__ work_ctr) {
+                                                                   uint32_t* __restrict__ work_ctr,
+                                                                   uint8_t* __restrict__ w1p = nullptr) {
+    constexpr int W1_ROW = K * (K == 4 ? 192 : 128);   // packed w1 bytes per item
     extern __shared__ __align__(16) uint32_t smem_u32v[];
     uint32_t* a_sm = smem_u32v;                               // K*L*A_STRIDE
     uint32_t* scr_all = smem_u32v + K * L * A_STRIDE;         // WARPS*SCRATCH_WORDS
@@ -181,12 +210,14 @@ __global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L, WARPS)) matv
         uint32_t item = __shfl_sync(0xffffffffu, claim, 0);
         while (item < batch) {
             if (lane == 0) claim = atomicAdd(work_ctr, 1u);
-            item_core<K, L, NTT_IN, INTT_OUT>(w + (size_t)item * K * N, v + (size_t)item * L * N, a_sm, scr, lane);
+            item_core<K, L, NTT_IN, INTT_OUT, false, W1>(w + (size_t)item * K * N, v + (size_t)item * L * N, a_sm, scr, lane, nullptr,
+                                                         W1 ? w1p + (size_t)item * W1_ROW : nullptr);
             item = __shfl_sync(0xffffffffu, claim, 0);
         }
     } else {
         for (uint32_t item = blockIdx.x * WARPS + warp; item < batch; item += gridDim.x * WARPS)
-            item_core<K, L, NTT_IN, INTT_OUT>(w + (size_t)item * K * N, v + (size_t)item * L * N, a_sm, scr, lane);
+            item_core<K, L, NTT_IN, INTT_OUT, false, W1>(w + (size_t)item * K * N, v + (size_t)item * L * N, a_sm, scr, lane, nullptr,
+                                                         W1 ? w1p + (size_t)item * W1_ROW : nullptr);
     }
 }
 
@@ -232,10 +263,10 @@ constexpr size_t shared_smem_bytes(int warps) {
     return (size_t)(K * L * A_STRIDE + warps * SCRATCH_WORDS) * 4;
 }
 
-template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT, int MAX_CTAS = 8>
+template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT, int MAX_CTAS = 8, bool W1 = false>
 static cudaError_t launch_shared_t(int32_t* w, const int32_t* a_hat, const uint8_t* rho, const int32_t* v, size_t batch,
-                                   int sm_count, cudaStream_t st, uint32_t* work_ctr = nullptr) {
-    auto kern = matvec_shared_kernel<K, L, WARPS, EXPAND, NTT_IN, INTT_OUT>;
+                                   int sm_count, cudaStream_t st, uint32_t* work_ctr = nullptr, uint8_t* w1p = nullptr) {
+    auto kern = matvec_shared_kernel<K, L, WARPS, EXPAND, NTT_IN, INTT_OUT, W1>;
     constexpr size_t smem = shared_smem_bytes<K, L>(WARPS);
     static bool configured = false;
     if (!configured) {
@@ -250,7 +281,7 @@ static cudaError_t launch_shared_t(int32_t* w, const int32_t* a_hat, const uint8
     size_t want = (batch + WARPS - 1) / WARPS;
     size_t cap = (size_t)sm_count * ctas_per_sm;
     unsigned grid = (unsigned)(want < cap ? want : cap);
-    kern<<<grid, WARPS * 32, smem, st>>>(w, a_hat, rho, v, (uint32_t)batch, work_ctr);
+    kern<<<grid, WARPS * 32, smem, st>>>(w, a_hat, rho, v, (uint32_t)batch, work_ctr, w1p);
     return cudaGetLastError();
 }
 
@@ -316,12 +347,31 @@ cudaError_t launch_matvec_expand(int32_t* w, const uint8_t* rho, const int32_t* 
     return cudaErrorInvalidValue;
 }
 
+// w1p != nullptr: also emit the packed w1 = HighBits(w) per item (signing); done inside the core by the default
+// 16-warp kernel, by a separate pack_w1 pass for the experiment shapes selected with DIL_SC_WARPS / DIL_SC_HALF / DIL_W1_FUSED=0
+template <int K, int L>
+static cudaError_t launch_signcore_t(int32_t* w, const int32_t* a_hat, const int32_t* y, size_t batch, int sm_count, cudaStream_t st,
+                                     uint32_t* work_ctr, uint8_t* w1p, int level) {
+    static int fused = -1;
+    if (fused < 0) {
+        const char* e = std::getenv("DIL_W1_FUSED");
+        const char* a = std::getenv("DIL_SC_WARPS");
+        const char* b = std::getenv("DIL_SC_HALF");
+        fused = !(e && std::atoi(e) == 0) && !(a && std::atoi(a) == 8) && !(b && std::atoi(b));
+    }
+    if (w1p != nullptr && fused)
+        return launch_shared_t<K, L, 16, false, true, true, 8, true>(w, a_hat, nullptr, y, batch, sm_count, st, work_ctr, w1p);
+    cudaError_t e = launch_shared_flags<K, L, false>(w, a_hat, nullptr, y, batch, true, true, sm_count, st, work_ctr);
+    if (e != cudaSuccess || w1p == nullptr) return e;
+    return launch_pack_w1(level, reinterpret_cast<uint32_t*>(w1p), w, (uint32_t)batch, st);
+}
+
 cudaError_t launch_signcore(int32_t* w, const int32_t* a_hat, const int32_t* y, int k, int l, size_t batch, int sm_count,
-                            cudaStream_t st, uint32_t* work_ctr) {
+                            cudaStream_t st, uint32_t* work_ctr, uint8_t* w1p) {
     if (batch == 0) return cudaSuccess;
-    if (k == 4 && l == 4) return launch_shared_flags<4, 4, false>(w, a_hat, nullptr, y, batch, true, true, sm_count, st, work_ctr);
-    if (k == 6 && l == 5) return launch_shared_flags<6, 5, false>(w, a_hat, nullptr, y, batch, true, true, sm_count, st, work_ctr);
-    if (k == 8 && l == 7) return launch_shared_flags<8, 7, false>(w, a_hat, nullptr, y, batch, true, true, sm_count, st, work_ctr);
+    if (k == 4 && l == 4) return launch_signcore_t<4, 4>(w, a_hat, y, batch, sm_count, st, work_ctr, w1p, 2);
+    if (k == 6 && l == 5) return launch_signcore_t<6, 5>(w, a_hat, y, batch, sm_count, st, work_ctr, w1p, 3);
+    if (k == 8 && l == 7) return launch_signcore_t<8, 7>(w, a_hat, y, batch, sm_count, st, work_ctr, w1p, 5);
     return cudaErrorInvalidValue;
 }
 

@@ -19,6 +19,7 @@
 #include "keccak.cuh"
 #include "kernels.h"
 #include "ntt_core.cuh"
+#include "rounding.cuh"
 
 namespace dil {
 
@@ -147,25 +148,6 @@ __global__ void __launch_bounds__(128) expand_mask_kernel(int32_t* __restrict__ 
     }
     __syncwarp();   // staging area is reused by the next chunk
     }
-}
-
-// ---------------------------------------------------------------------------------------
-// Decompose (decomp_map1.v / coeff_decomposer.v:80-88): a = a1*2*gamma2 + a0,
-// -gamma2 < a0 <= gamma2, with the wrap-around row mapped to a1 = 0.
-// ---------------------------------------------------------------------------------------
-template <int32_t GAMMA2>
-__device__ __forceinline__ void decompose(int32_t a, int32_t& a1, int32_t& a0) {
-    int32_t t = (a + 127) >> 7;
-    if constexpr (GAMMA2 == (Q_I - 1) / 32) {
-        t = (t * 1025 + (1 << 21)) >> 22;
-        t &= 15;
-    } else {
-        t = (t * 11275 + (1 << 23)) >> 24;
-        t ^= ((43 - t) >> 31) & t;
-    }
-    a1 = t;
-    a0 = a - t * 2 * GAMMA2;
-    a0 -= (((Q_I - 1) / 2 - a0) >> 31) & Q_I;
 }
 
 // S3: w1 = HighBits(w), bit-packed (encoder.v:96-133: 6 bits for gamma2=(Q-1)/88, else 4).
