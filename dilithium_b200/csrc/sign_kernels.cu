@@ -194,55 +194,74 @@ __global__ void __launch_bounds__(256) pack_w1_kernel(uint32_t* __restrict__ w1p
 // S4: c~ = SHAKE256(mu || w1_packed)[0:32]; c = SampleInBall(c~) (gen_c.v:163-222, :317-343).
 // One thread per active item; c is written as 256 int8 in {-1,0,1}.
 // ---------------------------------------------------------------------------------------
+// SampleInBall walks the squeezed bytes and the challenge polynomial with data-dependent indices; both live in
+// shared memory (a private row per thread) - as per-thread local arrays they cost an L1/L2 round trip per
+// access and dominated the kernel.  The finished polynomials leave as coalesced 16-byte vectors.
+constexpr int CH_THREADS = 64;
+constexpr int CH_C_STRIDE = 272;     // 256 coefficient bytes + 16: rows stay 16-byte aligned, banks are skewed
+constexpr int CH_BUF_STRIDE = 144;   // 136 squeezed bytes + 8
 template <int K, int W1_BYTES, int TAU>
-__global__ void __launch_bounds__(128) challenge_kernel(int8_t* __restrict__ c_out, uint64_t* __restrict__ ctilde,
-                                                        const uint64_t* __restrict__ mu, const uint64_t* __restrict__ w1p,
-                                                        const uint32_t* __restrict__ active, uint32_t n_slots, uint32_t spec) {
-    for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_slots; a += gridDim.x * blockDim.x) {
-    const uint32_t item = active[a / spec];
-    constexpr int W1_LANES = K * W1_BYTES / 8;
-    const uint64_t* m = mu + (size_t)item * 8;
-    const uint64_t* w = w1p + (size_t)a * W1_LANES;
-    uint64_t A[25];
-    shake256_absorb_lanes(A, 64 + K * W1_BYTES, [&](size_t idx) -> uint64_t { return idx < 8 ? m[idx] : w[idx - 8]; });
-    uint64_t ct[4];
+__global__ void __launch_bounds__(CH_THREADS) challenge_kernel(int8_t* __restrict__ c_out, uint64_t* __restrict__ ctilde,
+                                                               const uint64_t* __restrict__ mu, const uint64_t* __restrict__ w1p,
+                                                               const uint32_t* __restrict__ active, uint32_t n_slots, uint32_t spec) {
+    __shared__ __align__(16) uint8_t c_sm[CH_THREADS * CH_C_STRIDE];
+    __shared__ __align__(16) uint8_t buf_sm[CH_THREADS * CH_BUF_STRIDE];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* c = c_sm + threadIdx.x * CH_C_STRIDE;
+    uint8_t* buf = buf_sm + threadIdx.x * CH_BUF_STRIDE;
+    for (uint32_t base = blockIdx.x * blockDim.x + warp * 32; base < n_slots; base += gridDim.x * blockDim.x) {
+        const uint32_t a = base + lane;
+        if (a < n_slots) {
+            const uint32_t item = active[a / spec];
+            constexpr int W1_LANES = K * W1_BYTES / 8;
+            const uint64_t* m = mu + (size_t)item * 8;
+            const uint64_t* w = w1p + (size_t)a * W1_LANES;
+            uint64_t A[25];
+            shake256_absorb_lanes(A, 64 + K * W1_BYTES, [&](size_t idx) -> uint64_t { return idx < 8 ? m[idx] : w[idx - 8]; });
+            uint64_t ct[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        ct[i] = A[i];
-        ctilde[(size_t)a * 4 + i] = A[i];
-    }
-    // SampleInBall: SHAKE256(c~): first 8 bytes = sign bits, then rejection bytes
-#pragma unroll
-    for (int i = 0; i < 25; i++) A[i] = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) A[i] = ct[i];
-    A[4] = 0x1F;
-    A[16] = 0x80ULL << 56;
-    keccak_f1600(A);
-    uint64_t signs = A[0];
-    __align__(8) uint8_t buf[136];
-    __align__(4) int8_t c[N];
-#pragma unroll
-    for (int i = 0; i < 17; i++) reinterpret_cast<uint64_t*>(buf)[i] = A[i];
-    for (int i = 0; i < N; i++) c[i] = 0;
-    int pos = 8;
-    for (int i = N - TAU; i < N; i++) {
-        int b;
-        do {
-            if (pos == 136) {
-                keccak_f1600(A);
-#pragma unroll
-                for (int q = 0; q < 17; q++) reinterpret_cast<uint64_t*>(buf)[q] = A[q];
-                pos = 0;
+            for (int i = 0; i < 4; i++) {
+                ct[i] = A[i];
+                ctilde[(size_t)a * 4 + i] = A[i];
             }
-            b = buf[pos++];
-        } while (b > i);
-        c[i] = c[b];
-        c[b] = (signs & 1) ? -1 : 1;
-        signs >>= 1;
-    }
-    uint32_t* dst = reinterpret_cast<uint32_t*>(c_out + (size_t)a * N);
-    for (int i = 0; i < N / 4; i++) dst[i] = reinterpret_cast<const uint32_t*>(c)[i];
+            // SampleInBall: SHAKE256(c~): first 8 bytes = sign bits, then rejection bytes
+#pragma unroll
+            for (int i = 0; i < 25; i++) A[i] = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) A[i] = ct[i];
+            A[4] = 0x1F;
+            A[16] = 0x80ULL << 56;
+            keccak_f1600(A);
+            uint64_t signs = A[0];
+#pragma unroll
+            for (int i = 0; i < 17; i++) reinterpret_cast<uint64_t*>(buf)[i] = A[i];
+#pragma unroll
+            for (int i = 0; i < N / 16; i++) reinterpret_cast<uint4*>(c)[i] = make_uint4(0, 0, 0, 0);
+            int pos = 8;
+            for (int i = N - TAU; i < N; i++) {
+                int b;
+                do {
+                    if (pos == 136) {
+                        keccak_f1600(A);
+#pragma unroll
+                        for (int q = 0; q < 17; q++) reinterpret_cast<uint64_t*>(buf)[q] = A[q];
+                        pos = 0;
+                    }
+                    b = buf[pos++];
+                } while (b > i);
+                c[i] = c[b];
+                c[b] = (signs & 1) ? (uint8_t)0xFF : (uint8_t)1;
+                signs >>= 1;
+            }
+        }
+        __syncwarp();
+        // the warp's 32 polynomials (256 bytes each, consecutive slots) leave as 16-byte vectors
+        const uint32_t rows = n_slots - base < 32 ? n_slots - base : 32;
+        uint4* dst = reinterpret_cast<uint4*>(c_out + (size_t)base * N);
+        const uint8_t* src = c_sm + (size_t)warp * 32 * CH_C_STRIDE;
+        for (uint32_t t = lane; t < rows * (N / 16); t += 32)
+            dst[t] = *reinterpret_cast<const uint4*>(src + (t >> 4) * CH_C_STRIDE + (t & 15) * 16);
+        __syncwarp();
     }
 }
 
@@ -259,8 +278,8 @@ __device__ __forceinline__ int32_t centre(uint32_t a) { return (int32_t)a - (int
 template <int K, int L, int32_t GAMMA1, int32_t GAMMA2, int BETA, int OMEGA, int WARPS, int CTAS>
 __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
     int32_t* __restrict__ y /* in: y, out: z (in place) */, uint8_t* __restrict__ h_slot, uint8_t* __restrict__ accepted,
-    const int32_t* __restrict__ key_hat, const int32_t* __restrict__ w, const int8_t* __restrict__ c, uint32_t n_slots,
-    uint32_t* __restrict__ work_ctr) {
+    const int32_t* __restrict__ key_hat, int32_t* __restrict__ w /* in: w; scratch afterwards */, const int8_t* __restrict__ c,
+    uint32_t n_slots, uint32_t* __restrict__ work_ctr) {
     extern __shared__ __align__(16) uint32_t sm_words[];
     constexpr int NKEY = L + 2 * K;
     uint32_t* key_sm = sm_words;                       // NKEY * 256
@@ -316,14 +335,40 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
             ntt_inv_warp<true>(x, scr, itw, lane);
             __syncwarp();
         };
+        // The three norm checks are independent tests of equal cost per polynomial, so they run most-selective
+        // first (the accept/reject outcome does not depend on the order, combined_top.v:2098-2228 / SURVEY A.3):
+        // r0 = LowBits(w) - c*s2 rejects ~19 % per polynomial at level 2, z ~14 %, c*t0 < 1 %.  r0 and the
+        // "HighBits(w) != 0" flag needed by MakeHint are parked over w (dead after this kernel) for the survivors.
         bool bad = false;
+        int32_t* wi = w + (size_t)a * K * N + lane;
+#pragma unroll 1
+        for (int i = 0; i < K && !bad; i++) {
+            int32_t wv[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) wv[r] = wi[i * N + 32 * r];   // issued before the transform: latency hidden
+            uint32_t x[8];
+            mul_inv(x, L + i);                      // c*s2_i
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                int32_t a0, w1;
+                decompose<GAMMA2>(wv[r], w1, a0);
+                const int32_t r0 = a0 - centre(x[r]);
+                bad |= (r0 >= GAMMA2 - BETA) || (r0 <= -(GAMMA2 - BETA));
+                wv[r] = r0 * 2 + (w1 != 0 ? 1 : 0);
+            }
+            bad = __any_sync(0xffffffffu, bad);
+            if (!bad) {
+#pragma unroll
+                for (int r = 0; r < 8; r++) wi[i * N + 32 * r] = wv[r];
+            }
+        }
         // z = y + c*s1, written over y; stop at the first polynomial that violates the bound
         int32_t* yi = y + (size_t)a * L * N + lane;
 #pragma unroll 1
         for (int j = 0; j < L && !bad; j++) {
             int32_t yv[8];
 #pragma unroll
-            for (int r = 0; r < 8; r++) yv[r] = yi[j * N + 32 * r];   // issued before the transform: latency hidden
+            for (int r = 0; r < 8; r++) yv[r] = yi[j * N + 32 * r];
             uint32_t x[8];
             mul_inv(x, j);
 #pragma unroll
@@ -335,40 +380,26 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
             bad = __any_sync(0xffffffffu, bad);
         }
         uint32_t nh = 0;
-        if (!bad) {
-            const int32_t* wi = w + (size_t)a * K * N + lane;
 #pragma unroll 1
-            for (int i = 0; i < K && !bad; i++) {
-                int32_t wv[8];
+        for (int i = 0; i < K && !bad; i++) {
+            int32_t rv[8];
 #pragma unroll
-                for (int r = 0; r < 8; r++) wv[r] = wi[i * N + 32 * r];
-                uint32_t x[8];
-                int32_t r0[8], w1[8];
-                mul_inv(x, L + i);                      // c*s2_i
+            for (int r = 0; r < 8; r++) rv[r] = wi[i * N + 32 * r];   // r0 * 2 + (w1 != 0), parked above by this lane
+            uint32_t x[8];
+            mul_inv(x, L + K + i);                  // c*t0_i
 #pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    int32_t a0;
-                    decompose<GAMMA2>(wv[r], w1[r], a0);
-                    r0[r] = a0 - centre(x[r]);
-                    bad |= (r0[r] >= GAMMA2 - BETA) || (r0[r] <= -(GAMMA2 - BETA));
-                }
-                bad = __any_sync(0xffffffffu, bad);
-                if (bad) break;
-                mul_inv(x, L + K + i);                  // c*t0_i
-#pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    int32_t ct0 = centre(x[r]);
-                    bad |= (ct0 >= GAMMA2) || (ct0 <= -GAMMA2);
-                    int32_t v = r0[r] + ct0;
-                    bool hint = (v > GAMMA2) || (v < -GAMMA2) || (v == -GAMMA2 && w1[r] != 0);
-                    uint32_t mask = __ballot_sync(0xffffffffu, hint);
-                    nh += __popc(mask);
-                    if (lane == 0) hm[i * 8 + r] = mask;
-                }
-                bad = __any_sync(0xffffffffu, bad);
+            for (int r = 0; r < 8; r++) {
+                const int32_t ct0 = centre(x[r]);
+                bad |= (ct0 >= GAMMA2) || (ct0 <= -GAMMA2);
+                const int32_t v = (rv[r] >> 1) + ct0;
+                const bool hint = (v > GAMMA2) || (v < -GAMMA2) || (v == -GAMMA2 && (rv[r] & 1));
+                const uint32_t mask = __ballot_sync(0xffffffffu, hint);
+                nh += __popc(mask);
+                if (lane == 0) hm[i * 8 + r] = mask;
             }
-            bad = bad || nh > OMEGA;
+            bad = __any_sync(0xffffffffu, bad);
         }
+        bad = bad || nh > OMEGA;
         __syncwarp();
         if (!bad) {
             // hint encoding: omega position bytes (ascending inside each polynomial), then k running counts
@@ -582,20 +613,20 @@ cudaError_t launch_challenge(int level, int8_t* c, uint64_t* ct_slot, const uint
                              const uint32_t* active, uint32_t n_slots, uint32_t spec, cudaStream_t st) {
     if (n_slots == 0) return cudaSuccess;
     // 64-thread CTAs: 1024 CTAs for a 65536-slot round spread evenly over 148 SMs
-    unsigned grid = (n_slots + 63) / 64;
+    unsigned grid = (n_slots + CH_THREADS - 1) / CH_THREADS;
     const unsigned ccap = (unsigned)overlap_knob("DIL_CH_CTAS", 0) * 148u;
     if (ccap && grid > ccap) grid = ccap;
     switch (level) {
-        case 2: challenge_kernel<4, 192, 39><<<grid, 64, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
-        case 3: challenge_kernel<6, 128, 49><<<grid, 64, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
-        case 5: challenge_kernel<8, 128, 60><<<grid, 64, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
+        case 2: challenge_kernel<4, 192, 39><<<grid, CH_THREADS, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
+        case 3: challenge_kernel<6, 128, 49><<<grid, CH_THREADS, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
+        case 5: challenge_kernel<8, 128, 60><<<grid, CH_THREADS, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
 template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA, int WARPS, int CTAS>
-static cudaError_t launch_sign_tail_w(int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat, const int32_t* w,
+static cudaError_t launch_sign_tail_w(int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat, int32_t* w,
                                       const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st, uint32_t* work_ctr) {
     constexpr size_t smem = (size_t)((L + 2 * K) * N + WARPS * SCRATCH_WORDS + WARPS * K * 8) * 4;
     auto kern = sign_tail_kernel<K, L, G1, G2, BETA, OMEGA, WARPS, CTAS>;
@@ -612,7 +643,7 @@ static cudaError_t launch_sign_tail_w(int32_t* y, uint8_t* h_slot, uint8_t* acce
 }
 
 template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA>
-static cudaError_t launch_sign_tail_t(int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat, const int32_t* w,
+static cudaError_t launch_sign_tail_t(int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat, int32_t* w,
                                       const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st, uint32_t* work_ctr) {
     // one 24-warp CTA per SM is marginally faster than three 8-warp CTAs (DIL_TAIL_WARPS=8 selects the latter)
     static int big = -1;
@@ -623,7 +654,7 @@ static cudaError_t launch_sign_tail_t(int32_t* y, uint8_t* h_slot, uint8_t* acce
 }
 
 cudaError_t launch_sign_tail(int level, int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat,
-                             const int32_t* w, const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st,
+                             int32_t* w, const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st,
                              uint32_t* work_ctr) {
     if (n_slots == 0) return cudaSuccess;
     switch (level) {
