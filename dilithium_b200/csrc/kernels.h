@@ -29,8 +29,23 @@ cudaError_t launch_expand_mask(int level, int32_t* y, const uint64_t* rhop, cons
 cudaError_t launch_pack_w1(int level, uint32_t* w1p, const int32_t* w, uint32_t n_slots, cudaStream_t st);
 cudaError_t launch_challenge(int level, int8_t* c, uint64_t* ct_slot, const uint64_t* mu, const uint64_t* w1p,
                              const uint32_t* active, uint32_t n_slots, uint32_t spec, cudaStream_t st);
+// Outputs and queues of the resolve step, handed to the tail kernel in rounds with one slot per item: the tail
+// then finishes (packs the signature) or re-queues its item itself and launch_resolve is skipped.
+struct TailResolve {
+    uint8_t* zp;
+    uint8_t* h_out;
+    uint64_t* ct_out;
+    uint32_t* attempts;
+    uint16_t* kappa;
+    uint32_t* next_active;
+    uint32_t* next_count;
+    const uint64_t* ct_slot;
+    const uint32_t* active;
+    uint32_t* done_list;
+};
 cudaError_t launch_sign_tail(int level, int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat,
-                             int32_t* w, const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st, uint32_t* work_ctr = nullptr);
+                             int32_t* w, const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st,
+                             uint32_t* work_ctr = nullptr, const TailResolve* fused = nullptr);
 cudaError_t launch_resolve(int level, uint8_t* zp, uint8_t* h_out, uint64_t* ct_out, uint32_t* attempts, uint16_t* kappa,
                            uint32_t* next_active, uint32_t* next_count, const int32_t* zslot, const uint8_t* h_slot,
                            const uint64_t* ct_slot, const uint8_t* accepted, const uint32_t* active, uint32_t n_items,

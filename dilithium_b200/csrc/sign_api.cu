@@ -86,7 +86,16 @@ cudaError_t dmalloc(T** p, size_t count) {
 // values per round in parallel slots; the smallest accepted kappa wins, which is exactly the
 // sequential result of combined_top.v:2217-2228 (restart with the next kappa).
 constexpr size_t SPEC_SLOT_TARGET_DEFAULT = 32768;
-constexpr size_t SPEC_MAX = 16;
+// at most one warp lane per speculative slot in resolve_kernel; DIL_SPEC_MAX overrides (tuning knob)
+static size_t spec_max() {
+    static size_t v = 0;
+    if (!v) {
+        const char* e = std::getenv("DIL_SPEC_MAX");
+        v = e && std::atol(e) > 0 && std::atol(e) <= 32 ? (size_t)std::atol(e) : 32;
+    }
+    return v;
+}
+#define SPEC_MAX spec_max()
 static size_t spec_slot_target() {   // DIL_SPEC_TARGET overrides (tuning knob)
     static size_t v = 0;
     if (!v) {
@@ -190,6 +199,9 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
     // DIL_SIGN_STATIC=1: static warp-stride distribution in the two persistent kernels (A/B measurements)
     const char* dyn_env = std::getenv("DIL_SIGN_STATIC");
     const bool dyn = !(dyn_env && std::atoi(dyn_env) != 0);
+    // DIL_RESOLVE_FUSED=0: always run the separate resolve pass (A/B measurements)
+    const char* fuse_env = std::getenv("DIL_RESOLVE_FUSED");
+    const bool fuse_ok = !(fuse_env && std::atoi(fuse_env) == 0);
     while (n_active > 0) {
         if (++rounds > 4000) {
             e->last_error = "sign: rejection loop did not terminate";
@@ -214,16 +226,23 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
         PROF_BEGIN(4);
         CK(dil::launch_challenge(P.level, k->c, k->ct_slot, k->mu_d, k->w1p, k->active[cur], n_slots, (uint32_t)spec, st));
         PROF_END(4, n_slots);
+        // without speculation (one slot per item) the tail finishes or re-queues its item itself: no resolve pass
+        const bool fuse_resolve = spec == 1 && fuse_ok;
+        dil::TailResolve tr{d_zp, d_h, reinterpret_cast<uint64_t*>(d_ct), d_att, k->kappa, k->active[cur ^ 1], k->count, k->ct_slot,
+                            k->active[cur], drain ? k->done_list : nullptr};
         PROF_BEGIN(5);
         CK(dil::launch_sign_tail(P.level, k->y, k->h_slot, k->accepted, k->key_hat, k->w, k->c, n_slots, e->sm_count, st,
-                                 dyn ? k->count + 2 : nullptr));
+                                 dyn ? k->count + 2 : nullptr, fuse_resolve ? &tr : nullptr));
         PROF_END(5, n_slots);
-        PROF_BEGIN(6);
-        CK(dil::launch_resolve(P.level, d_zp, d_h, reinterpret_cast<uint64_t*>(d_ct), d_att, k->kappa, k->active[cur ^ 1], k->count,
-                               k->y, k->h_slot, k->ct_slot, k->accepted, k->active[cur], n_active, (uint32_t)spec,
-                               drain ? k->done_list : nullptr, st));
-        PROF_END(6, n_active);
-        launches += 5;
+        if (!fuse_resolve) {
+            PROF_BEGIN(6);
+            CK(dil::launch_resolve(P.level, d_zp, d_h, reinterpret_cast<uint64_t*>(d_ct), d_att, k->kappa, k->active[cur ^ 1], k->count,
+                                   k->y, k->h_slot, k->ct_slot, k->accepted, k->active[cur], n_active, (uint32_t)spec,
+                                   drain ? k->done_list : nullptr, st));
+            PROF_END(6, n_active);
+            launches++;
+        }
+        launches += 4;
         if (!k->count_host) {
             CK(cudaHostAlloc(reinterpret_cast<void**>(&k->count_host), 64, cudaHostAllocMapped));
             CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&k->count_host_dev), k->count_host, 0));
@@ -234,6 +253,7 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
         if (prof)
             for (int cls = 1; cls <= 6; cls++) {
                 if (cls == 3) continue;   // w1 packing is part of the sign core (class 2)
+                if (cls == 6 && fuse_resolve) continue;   // resolve ran inside the tail (class 5)
                 float ms = 0;
                 CK(cudaEventElapsedTime(&ms, k->ev[2 * cls], k->ev[2 * cls + 1]));
                 k->prof_ms[cls] += ms;

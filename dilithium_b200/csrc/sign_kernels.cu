@@ -266,6 +266,87 @@ __global__ void __launch_bounds__(CH_THREADS) challenge_kernel(int8_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------
+// Accepted slot `a` of `item` (its s-th speculative attempt) becomes the signature: z is packed
+// (encoder.v:96-133: gamma1 - z, 18 or 20 bits) through a per-warp shared staging row and leaves as
+// 16-byte vectors, h and c~ are copied, the attempt count is recorded and the item joins the
+// completion-ordered done list (next_count[3] counts finished items over the whole batch; the host path
+// drains each round's finished signatures while later rounds still sign).  Executed by one warp.
+// ---------------------------------------------------------------------------------------
+template <int L, int GAMMA1_BITS, int HB>
+__device__ __forceinline__ void resolve_finish(uint8_t* __restrict__ zp, uint8_t* __restrict__ h_out, uint64_t* __restrict__ ct_out,
+                                               uint32_t* __restrict__ attempts, const uint16_t* __restrict__ kappa,
+                                               uint32_t* __restrict__ next_count, const int32_t* zslot,
+                                               const uint8_t* h_slot, const uint64_t* __restrict__ ct_slot,
+                                               uint32_t* __restrict__ done_list, uint32_t item, uint32_t a, uint32_t s,
+                                               uint8_t* dstp, int lane) {
+    constexpr int BITS = GAMMA1_BITS + 1;
+    constexpr int32_t G1 = 1 << GAMMA1_BITS;
+    constexpr int ZB = L * 32 * BITS;
+    const int4* src = reinterpret_cast<const int4*>(zslot + (size_t)a * L * N);
+    for (int g = lane; g < L * 32; g += 32) {
+        int4 va = src[2 * g], vb = src[2 * g + 1];
+        uint32_t v[8] = {(uint32_t)(G1 - va.x), (uint32_t)(G1 - va.y), (uint32_t)(G1 - va.z), (uint32_t)(G1 - va.w),
+                         (uint32_t)(G1 - vb.x), (uint32_t)(G1 - vb.y), (uint32_t)(G1 - vb.z), (uint32_t)(G1 - vb.w)};
+        uint64_t lo = 0, mid = 0;
+        uint32_t hi = 0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int pos = c * BITS;
+            uint64_t x = v[c] & ((1u << BITS) - 1);
+            if (pos < 64) {
+                lo |= x << pos;
+                if (pos + BITS > 64) mid |= x >> (64 - pos);
+            } else if (pos < 128) {
+                mid |= x << (pos - 64);
+                if (pos + BITS > 128) hi |= (uint32_t)(x >> (128 - pos));
+            } else {
+                hi |= (uint32_t)x << (pos - 128);
+            }
+        }
+        uint8_t* dst = dstp + (size_t)g * BITS;
+        if constexpr (BITS == 18) {
+            uint16_t* d = reinterpret_cast<uint16_t*>(dst);
+#pragma unroll
+            for (int q = 0; q < 4; q++) d[q] = (uint16_t)(lo >> (16 * q));
+#pragma unroll
+            for (int q = 0; q < 4; q++) d[4 + q] = (uint16_t)(mid >> (16 * q));
+            d[8] = (uint16_t)hi;
+        } else {
+            uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+            d[0] = (uint32_t)lo; d[1] = (uint32_t)(lo >> 32); d[2] = (uint32_t)mid; d[3] = (uint32_t)(mid >> 32); d[4] = hi;
+        }
+    }
+    __syncwarp();
+    {
+        uint4* out = reinterpret_cast<uint4*>(zp + (size_t)item * ZB);
+        const uint4* st = reinterpret_cast<const uint4*>(dstp);
+        for (int t = lane; t < ZB / 16; t += 32) out[t] = st[t];
+    }
+    for (int t = lane; t < HB; t += 32) h_out[(size_t)item * HB + t] = h_slot[(size_t)a * HB + t];
+    if (lane < 4) ct_out[(size_t)item * 4 + lane] = ct_slot[(size_t)a * 4 + lane];
+    if (lane == 0) {
+        attempts[item] = (uint32_t)kappa[item] + s + 1;
+        if (done_list) done_list[atomicAdd(next_count + 3, 1u)] = item;
+    }
+    __syncwarp();
+}
+
+// Resolve arguments for the rounds without speculation (one slot per item), where the tail kernel
+// finishes or re-queues its item itself and no separate resolve pass runs (zp == nullptr: not fused).
+struct ResolveArgs {
+    uint8_t* zp = nullptr;
+    uint8_t* h_out = nullptr;
+    uint64_t* ct_out = nullptr;
+    uint32_t* attempts = nullptr;
+    uint16_t* kappa = nullptr;
+    uint32_t* next_active = nullptr;
+    uint32_t* next_count = nullptr;
+    const uint64_t* ct_slot = nullptr;
+    const uint32_t* active = nullptr;
+    uint32_t* done_list = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------
 // S5: signature tail, one warp per active item.
 //   c_hat = NTT(c); z = y + INTT(c_hat o s1_hat); ||z|| < gamma1 - beta
 //   r0 = LowBits(w) - INTT(c_hat o s2_hat); ||r0|| < gamma2 - beta
@@ -279,12 +360,15 @@ template <int K, int L, int32_t GAMMA1, int32_t GAMMA2, int BETA, int OMEGA, int
 __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
     int32_t* __restrict__ y /* in: y, out: z (in place) */, uint8_t* __restrict__ h_slot, uint8_t* __restrict__ accepted,
     const int32_t* __restrict__ key_hat, int32_t* __restrict__ w /* in: w; scratch afterwards */, const int8_t* __restrict__ c,
-    uint32_t n_slots, uint32_t* __restrict__ work_ctr) {
+    uint32_t n_slots, uint32_t* __restrict__ work_ctr, const ResolveArgs ra) {
     extern __shared__ __align__(16) uint32_t sm_words[];
     constexpr int NKEY = L + 2 * K;
+    constexpr int G1BITS = GAMMA1 == (1 << 17) ? 17 : 19;
+    constexpr int ZB = L * 32 * (G1BITS + 1);          // packed z bytes per signature
     uint32_t* key_sm = sm_words;                       // NKEY * 256
     uint32_t* scr_all = sm_words + NKEY * N;           // WARPS * SCRATCH_WORDS
     uint32_t* hm_all = scr_all + WARPS * SCRATCH_WORDS;  // WARPS * K * 8 hint masks
+    uint8_t* zstage_all = reinterpret_cast<uint8_t*>(hm_all + WARPS * K * 8);   // WARPS * ZB (fused resolve)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (work_ctr != nullptr) {   // a CTA that starts when every slot is already claimed leaves at once (uniform decision)
         __shared__ uint32_t late;
@@ -418,6 +502,18 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
         }
         if (lane == 0) accepted[a] = bad ? 0 : 1;
         __syncwarp();
+        if (ra.zp != nullptr) {   // one slot per item: finish or re-queue the item here (no resolve pass)
+            const uint32_t item = ra.active[a];
+            if (bad) {
+                if (lane == 0) {
+                    ra.kappa[item] += 1;
+                    ra.next_active[atomicAdd(ra.next_count, 1u)] = item;
+                }
+            } else {
+                resolve_finish<L, G1BITS, OMEGA + K>(ra.zp, ra.h_out, ra.ct_out, ra.attempts, ra.kappa, ra.next_count, y, h_slot, ra.ct_slot,
+                                                     ra.done_list, item, a, 0u, zstage_all + (size_t)warp * ZB, lane);
+            }
+        }
     }
 }
 
@@ -449,63 +545,10 @@ __global__ void __launch_bounds__(256) resolve_kernel(uint8_t* __restrict__ zp, 
         return;
     }
     const uint32_t s = __ffs(mask) - 1;
-    const uint32_t a = a0 + s;
-    constexpr int BITS = GAMMA1_BITS + 1;
-    constexpr int32_t G1 = 1 << GAMMA1_BITS;
-    const int4* src = reinterpret_cast<const int4*>(zslot + (size_t)a * L * N);
-    // the packed z is staged in shared memory and leaves as 16-byte vectors, 512 contiguous bytes per warp
-    // store: efficient for HBM and - when the caller's buffers are pinned host memory mapped into the
-    // device (dil_sign_batch_host zero-copy path) - for PCIe posted writes
-    constexpr int ZB = L * 32 * BITS;
+    constexpr int ZB = L * 32 * (GAMMA1_BITS + 1);
     __shared__ __align__(16) uint8_t zstage[8][ZB];
-    uint8_t* dstp = zstage[threadIdx.x >> 5];
-    for (int g = lane; g < L * 32; g += 32) {
-        int4 va = src[2 * g], vb = src[2 * g + 1];
-        uint32_t v[8] = {(uint32_t)(G1 - va.x), (uint32_t)(G1 - va.y), (uint32_t)(G1 - va.z), (uint32_t)(G1 - va.w),
-                         (uint32_t)(G1 - vb.x), (uint32_t)(G1 - vb.y), (uint32_t)(G1 - vb.z), (uint32_t)(G1 - vb.w)};
-        uint64_t lo = 0, mid = 0;
-        uint32_t hi = 0;
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            const int pos = c * BITS;
-            uint64_t x = v[c] & ((1u << BITS) - 1);
-            if (pos < 64) {
-                lo |= x << pos;
-                if (pos + BITS > 64) mid |= x >> (64 - pos);
-            } else if (pos < 128) {
-                mid |= x << (pos - 64);
-                if (pos + BITS > 128) hi |= (uint32_t)(x >> (128 - pos));
-            } else {
-                hi |= (uint32_t)x << (pos - 128);
-            }
-        }
-        uint8_t* dst = dstp + (size_t)g * BITS;
-        if constexpr (BITS == 18) {
-            uint16_t* d = reinterpret_cast<uint16_t*>(dst);
-#pragma unroll
-            for (int q = 0; q < 4; q++) d[q] = (uint16_t)(lo >> (16 * q));
-#pragma unroll
-            for (int q = 0; q < 4; q++) d[4 + q] = (uint16_t)(mid >> (16 * q));
-            d[8] = (uint16_t)hi;
-        } else {
-            uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-            d[0] = (uint32_t)lo; d[1] = (uint32_t)(lo >> 32); d[2] = (uint32_t)mid; d[3] = (uint32_t)(mid >> 32); d[4] = hi;
-        }
-    }
-    __syncwarp();
-    {
-        uint4* out = reinterpret_cast<uint4*>(zp + (size_t)item * ZB);
-        const uint4* st = reinterpret_cast<const uint4*>(dstp);
-        for (int t = lane; t < ZB / 16; t += 32) out[t] = st[t];
-    }
-    for (int t = lane; t < HB; t += 32) h_out[(size_t)item * HB + t] = h_slot[(size_t)a * HB + t];
-    if (lane < 4) ct_out[(size_t)item * 4 + lane] = ct_slot[(size_t)a * 4 + lane];
-    if (lane == 0) {
-        attempts[item] = (uint32_t)kappa[item] + s + 1;
-        // completion-ordered list of finished items (next_count[3] counts them over the whole batch): the
-        // host path drains each round's finished signatures to host memory while later rounds still sign
-        if (done_list) done_list[atomicAdd(next_count + 3, 1u)] = item;
-    }
+    resolve_finish<L, GAMMA1_BITS, HB>(zp, h_out, ct_out, attempts, kappa, next_count, zslot, h_slot, ct_slot, done_list, item, a0 + s, s,
+                                       zstage[threadIdx.x >> 5], lane);
 }
 
 // Copies the finished signatures named by list[0..n) from the device staging arrays into the caller's
@@ -627,8 +670,10 @@ cudaError_t launch_challenge(int level, int8_t* c, uint64_t* ct_slot, const uint
 
 template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA, int WARPS, int CTAS>
 static cudaError_t launch_sign_tail_w(int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat, int32_t* w,
-                                      const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st, uint32_t* work_ctr) {
-    constexpr size_t smem = (size_t)((L + 2 * K) * N + WARPS * SCRATCH_WORDS + WARPS * K * 8) * 4;
+                                      const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st, uint32_t* work_ctr,
+                                      const ResolveArgs& ra) {
+    constexpr int ZB = L * 32 * ((G1 == (1 << 17) ? 17 : 19) + 1);
+    constexpr size_t smem = (size_t)((L + 2 * K) * N + WARPS * SCRATCH_WORDS + WARPS * K * 8) * 4 + (size_t)WARPS * ZB;
     auto kern = sign_tail_kernel<K, L, G1, G2, BETA, OMEGA, WARPS, CTAS>;
     static bool configured = false;
     if (!configured) {
@@ -638,29 +683,36 @@ static cudaError_t launch_sign_tail_w(int32_t* y, uint8_t* h_slot, uint8_t* acce
     }
     unsigned want = (n_slots + WARPS - 1) / WARPS;
     unsigned cap = (unsigned)sm_count * CTAS;
-    kern<<<want < cap ? want : cap, WARPS * 32, smem, st>>>(y, h_slot, accepted, key_hat, w, c, n_slots, work_ctr);
+    kern<<<want < cap ? want : cap, WARPS * 32, smem, st>>>(y, h_slot, accepted, key_hat, w, c, n_slots, work_ctr, ra);
     return cudaGetLastError();
 }
 
 template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA>
 static cudaError_t launch_sign_tail_t(int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat, int32_t* w,
-                                      const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st, uint32_t* work_ctr) {
+                                      const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st, uint32_t* work_ctr,
+                                      const ResolveArgs& ra) {
     // one 24-warp CTA per SM is marginally faster than three 8-warp CTAs (DIL_TAIL_WARPS=8 selects the latter)
     static int big = -1;
     if (big < 0) { const char* e = std::getenv("DIL_TAIL_WARPS"); big = (e && std::atoi(e) == 8) ? 0 : 1; }
-    if (overlap_knob("DIL_TAIL_HALF", 0)) return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 12, 1>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr);
-    if (big) return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 24, 1>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr);
-    return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 8, 3>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr);
+    if (overlap_knob("DIL_TAIL_HALF", 0)) return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 12, 1>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr, ra);
+    if (big) return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 24, 1>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr, ra);
+    return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 8, 3>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr, ra);
 }
 
 cudaError_t launch_sign_tail(int level, int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat,
                              int32_t* w, const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st,
-                             uint32_t* work_ctr) {
+                             uint32_t* work_ctr, const TailResolve* fused) {
     if (n_slots == 0) return cudaSuccess;
+    ResolveArgs ra;
+    if (fused != nullptr) {
+        ra.zp = fused->zp; ra.h_out = fused->h_out; ra.ct_out = fused->ct_out; ra.attempts = fused->attempts; ra.kappa = fused->kappa;
+        ra.next_active = fused->next_active; ra.next_count = fused->next_count; ra.ct_slot = fused->ct_slot; ra.active = fused->active;
+        ra.done_list = fused->done_list;
+    }
     switch (level) {
-        case 2: return launch_sign_tail_t<4, 4, 1 << 17, (Q_I - 1) / 88, 78, 80>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr);
-        case 3: return launch_sign_tail_t<6, 5, 1 << 19, (Q_I - 1) / 32, 196, 55>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr);
-        case 5: return launch_sign_tail_t<8, 7, 1 << 19, (Q_I - 1) / 32, 120, 75>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr);
+        case 2: return launch_sign_tail_t<4, 4, 1 << 17, (Q_I - 1) / 88, 78, 80>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr, ra);
+        case 3: return launch_sign_tail_t<6, 5, 1 << 19, (Q_I - 1) / 32, 196, 55>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr, ra);
+        case 5: return launch_sign_tail_t<8, 7, 1 << 19, (Q_I - 1) / 32, 120, 75>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr, ra);
     }
     return cudaErrorInvalidValue;
 }
