@@ -18,9 +18,12 @@ Multi-GPU: one process per GPU (torchrun), every rank signs its own 65 536-messa
 scaling); the only collective is ONE NCCL broadcast of the key material from rank 0.
 
 `value`   signs/s over all GPUs, messages already resident in HBM, CUDA-event timed, max over ranks.
-`e2e`     the same through dil_sign_batch_host: pinned host messages in, signatures back on the host.
+`e2e`     the same through dil_sign_batch_host: pinned host messages in, signatures back on the host
+          (finished signatures are drained to the host round by round while later rounds still sign).
 `roofline` the kernel class with the largest share of the step's device time (measured with CUDA
-          events around every launch in a separate profiled step).
+          events around every launch in a separate profiled step): HBM fraction from algorithmic bytes as
+          the contract asks, plus `compute_roofline` (Keccak-f/s against the measured pure-Keccak peak)
+          because that class is bound by the integer ALU pipe, not by HBM.
 """
 import argparse
 import ctypes
@@ -71,6 +74,24 @@ def measured_peak():
         return float(p["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
     except Exception:
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+KECCAK_PEAK_GPS = 4.27   # G Keccak-f[1600]/s: pure-permutation micro-benchmark on one B200 (tools/keccak_pipe_bench.cu,
+                         # profiles/r1b_keccak_pipe_bench.txt): the ALU-pipe speed of light for the hash kernels
+
+
+def keccak_roofline(kernel_class, level, slots, ms):
+    """For the Keccak-bound classes: achieved permutations/s against the measured pure-Keccak peak."""
+    k, l = LEVEL_DIMS[level]
+    w1 = LEVEL_EXTRA[level]["w1"]
+    per_slot = {"expand_mask": l * 5,                                   # 576/640 squeezed bytes per polynomial = 5 blocks
+                "challenge": (64 + k * w1) // 136 + 1 + 1}.get(kernel_class)   # absorb mu||w1 + pad, then SampleInBall
+    if per_slot is None or ms <= 0:
+        return None
+    gps = per_slot * slots / (ms * 1e-3) / 1e9
+    return {"bound": "integer ALU (Keccak-f[1600])", "unit": "G Keccak-f/s", "achieved": gps, "peak": KECCAK_PEAK_GPS,
+            "frac": gps / KECCAK_PEAK_GPS, "permutations_per_slot": per_slot,
+            "peak_source": "tools/keccak_pipe_bench.cu on B200 (profiles/r1b_keccak_pipe_bench.txt)"}
 
 
 def ncu_traffic(kernel_class):
@@ -365,7 +386,9 @@ def run_engine(args):
                        "sharding": ("independent messages, one contiguous shard per rank; one NCCL broadcast of the key material"
                                     if world > 1 else "single GPU"),
                        "l2": "no flush: every round streams > 1 GiB of per-attempt state (y, w, c), far above the 126 MB L2",
-                       "timing": "CUDA events on torch's current stream (the stream every kernel is launched on), max over ranks"},
+                       "timing": "CUDA events on torch's current stream (the stream every kernel is launched on), max over ranks",
+                       "kernels_per_round": "ExpandMask, sign core (+ packed HighBits), challenge, tail (+ resolve when one slot per item), "
+                                            "resolve only in speculative rounds"},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "step_profile_ms": {n: round(ms, 4) for n, (ms, _) in prof.items()},
@@ -377,8 +400,9 @@ def run_engine(args):
                          "traffic_note": "ncu dram bytes of a 65536-slot launch scaled to this step's average launch size",
                          "algorithmic_bytes_per_slot": cb[dominant], "slots_per_step": dom_units, "launches_per_step": rounds,
                          "avg_launch_ms": dom_ms / max(rounds, 1), "peak_source": peak_src,
-                         "true_limiter": CLASS_BOUND_NOTE.get(dominant, "")},
-            "roofline_ntt": {"kernel": "ntt_tma_kernel<8,3,4,false> (stand-alone forward NTT, the north_star's named kernel)",
+                         "true_limiter": CLASS_BOUND_NOTE.get(dominant, ""),
+                         "compute_roofline": keccak_roofline(dominant, level, dom_units, dom_ms)},
+            "roofline_ntt": {"kernel": "ntt_tma_kernel<32,3,1,false> (stand-alone forward NTT, the north_star's named kernel)",
                              "bound": "hbm", "polys_per_s": npoly / (ntt_ms * 1e-3), "achieved": npoly * 2048 / (ntt_ms * 1e-3) / 1e9,
                              "peak": peak, "unit": "GB/s", "frac": npoly * 2048 / (ntt_ms * 1e-3) / 1e9 / peak, "polys_per_launch": npoly,
                              "invntt_polys_per_s": npoly / (intt_ms * 1e-3), "invntt_frac": npoly * 2048 / (intt_ms * 1e-3) / 1e9 / peak},

@@ -29,5 +29,8 @@ vk = d.VerifyKey(eng, 2, K["rho"][0], K["t1"][0])
 msgs = [bytes([i & 255]) * 40 for i in range(64 if small else 4096)]
 z, h, c, att = sk.sign(msgs)
 assert vk.verify(msgs, z, h, c).all()
+# host path with pinned outputs: finished signatures are drained round by round (drain_kernel)
+zp, hp, cp, ap = sk.sign(msgs, pinned=True)
+assert np.array_equal(z, zp) and np.array_equal(h, hp) and np.array_equal(c, cp) and np.array_equal(att, ap)
 keys = eng.keygen(2, np.arange(64 * 32, dtype=np.uint8).reshape(64, 32))
 print("tour ok", eng.launch_count)
