@@ -126,10 +126,10 @@ def class_bytes(level):
 CLASS_KERNEL = {"expand_mask": "expand_mask_kernel<L,GAMMA1_BITS> (SHAKE-256 ExpandMask, one Keccak state per thread)",
                 "signcore": "matvec_shared_kernel<K,L,16,0,1,1,1> (fused NTT -> A*y -> INTT -> w, packed HighBits(w))",
                 "challenge": "challenge_kernel (SHAKE-256 + SampleInBall)",
-                "tail": "sign_tail_kernel (NTT(c), c*s1/c*s2/c*t0, INTTs, norm checks, MakeHint)", "resolve": "resolve_kernel",
+                "tail": "sign_tail_sparse_kernel (sparse c*s2 / c*s1 products + norm checks; NTT(c), c*t0, MakeHint and resolve for survivors)", "resolve": "resolve_kernel",
                 "init": "sign_init_kernel"}
 CLASS_BOUND_NOTE = {"expand_mask": "integer ALU (Keccak): ncu alu pipe 95% busy; HBM fraction is not the limiter",
-                    "challenge": "integer ALU (Keccak)", "tail": "integer multiply pipe (fmaheavy) + load latency",
+                    "challenge": "integer ALU (Keccak)", "tail": "issue slots / ALU pipe 60 % + global-load latency (sparse products); fmaheavy 39 % (survivors' c*t0 transforms)",
                     "signcore": "integer multiply pipe (fmaheavy): ncu 73% busy", "resolve": "HBM/latency"}
 
 

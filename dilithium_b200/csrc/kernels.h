@@ -45,7 +45,7 @@ struct TailResolve {
 };
 cudaError_t launch_sign_tail(int level, int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat,
                              int32_t* w, const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st,
-                             uint32_t* work_ctr = nullptr, const TailResolve* fused = nullptr);
+                             uint32_t* work_ctr = nullptr, const TailResolve* fused = nullptr, const int8_t* key_small = nullptr);
 cudaError_t launch_resolve(int level, uint8_t* zp, uint8_t* h_out, uint64_t* ct_out, uint32_t* attempts, uint16_t* kappa,
                            uint32_t* next_active, uint32_t* next_count, const int32_t* zslot, const uint8_t* h_slot,
                            const uint64_t* ct_slot, const uint8_t* accepted, const uint32_t* active, uint32_t n_items,

@@ -26,6 +26,7 @@ struct dil_sign_key {
     int device = -1;
     int32_t* a_hat = nullptr;    // k*l polys
     int32_t* key_hat = nullptr;  // s1_hat (l) | s2_hat (k) | t0_hat (k)
+    int8_t* key_small = nullptr; // s1 (l) | s2 (k) in the time domain, coefficients in [-eta, eta] (sparse c*s products)
     uint8_t* seeds = nullptr;    // tr[32] | K[32]
     // workspace (grow-only, sized for `cap` items)
     std::mutex mu;
@@ -232,7 +233,7 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
                             k->active[cur], drain ? k->done_list : nullptr};
         PROF_BEGIN(5);
         CK(dil::launch_sign_tail(P.level, k->y, k->h_slot, k->accepted, k->key_hat, k->w, k->c, n_slots, e->sm_count, st,
-                                 dyn ? k->count + 2 : nullptr, fuse_resolve ? &tr : nullptr));
+                                 dyn ? k->count + 2 : nullptr, fuse_resolve ? &tr : nullptr, k->key_small));
         PROF_END(5, n_slots);
         if (!fuse_resolve) {
             PROF_BEGIN(6);
@@ -321,10 +322,14 @@ int dil_sign_key_create(dil_engine_t* e, dil_sign_key_t** out, int level, const 
     std::memcpy(seeds + 64, rho, 32);
     A(dmalloc(&k->a_hat, (size_t)P.k * P.l * 256));
     A(dmalloc(&k->key_hat, (size_t)nkey * 256));
+    A(dmalloc(&k->key_small, (size_t)(P.l + P.k) * 256));
     A(dmalloc(&k->seeds, 96));
+    std::vector<int8_t> small((size_t)(P.l + P.k) * 256);
+    for (size_t i = 0; i < small.size(); i++) small[i] = (int8_t)polys[i];
     if (err == cudaSuccess) {
         A(cudaMemcpyAsync(k->seeds, seeds, 96, cudaMemcpyHostToDevice, st));
         A(cudaMemcpyAsync(k->key_hat, polys.data(), polys.size() * 4, cudaMemcpyHostToDevice, st));
+        A(cudaMemcpyAsync(k->key_small, small.data(), small.size(), cudaMemcpyHostToDevice, st));
         A(dil::launch_expand_a(k->a_hat, k->seeds + 64, 1, P.k, P.l, e->sm_count, st));
         A(dil::launch_ntt_fwd(k->key_hat, k->key_hat, nkey, e->sm_count, st));
         A(cudaStreamSynchronize(st));
@@ -332,6 +337,7 @@ int dil_sign_key_create(dil_engine_t* e, dil_sign_key_t** out, int level, const 
     if (err != cudaSuccess) {
         if (k->a_hat) cudaFree(k->a_hat);
         if (k->key_hat) cudaFree(k->key_hat);
+        if (k->key_small) cudaFree(k->key_small);
         if (k->seeds) cudaFree(k->seeds);
         delete k;
         return fail(e, err, "dil_sign_key_create");
@@ -345,7 +351,7 @@ int dil_sign_key_destroy(dil_engine_t* e, dil_sign_key_t* k) {
     if (!k) return DIL_OK;
     DeviceGuard dg(k->device);
     free_ws(k);
-    void* ptrs[] = {k->a_hat, k->key_hat, k->seeds, k->msgs_d, k->zp_d, k->h_d, k->ct_d, k->off_d, k->att_d};
+    void* ptrs[] = {k->a_hat, k->key_hat, k->key_small, k->seeds, k->msgs_d, k->zp_d, k->h_d, k->ct_d, k->off_d, k->att_d};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& ev : k->ev)

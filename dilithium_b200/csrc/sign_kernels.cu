@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(CH_THREADS) challenge_kernel(int8_t* __restric
 // completion-ordered done list (next_count[3] counts finished items over the whole batch; the host path
 // drains each round's finished signatures while later rounds still sign).  Executed by one warp.
 // ---------------------------------------------------------------------------------------
-template <int L, int GAMMA1_BITS, int HB>
+template <int L, int GAMMA1_BITS, int HB, bool DIRECT = false>
 __device__ __forceinline__ void resolve_finish(uint8_t* __restrict__ zp, uint8_t* __restrict__ h_out, uint64_t* __restrict__ ct_out,
                                                uint32_t* __restrict__ attempts, const uint16_t* __restrict__ kappa,
                                                uint32_t* __restrict__ next_count, const int32_t* zslot,
@@ -303,7 +303,8 @@ __device__ __forceinline__ void resolve_finish(uint8_t* __restrict__ zp, uint8_t
                 hi |= (uint32_t)x << (pos - 128);
             }
         }
-        uint8_t* dst = dstp + (size_t)g * BITS;
+        // DIRECT: no staging row, the 18/20-byte pieces go straight to the signature (2-/4-byte stores)
+        uint8_t* dst = (DIRECT ? zp + (size_t)item * ZB : dstp) + (size_t)g * BITS;
         if constexpr (BITS == 18) {
             uint16_t* d = reinterpret_cast<uint16_t*>(dst);
 #pragma unroll
@@ -317,7 +318,7 @@ __device__ __forceinline__ void resolve_finish(uint8_t* __restrict__ zp, uint8_t
         }
     }
     __syncwarp();
-    {
+    if constexpr (!DIRECT) {
         uint4* out = reinterpret_cast<uint4*>(zp + (size_t)item * ZB);
         const uint4* st = reinterpret_cast<const uint4*>(dstp);
         for (int t = lane; t < ZB / 16; t += 32) out[t] = st[t];
@@ -518,6 +519,236 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
 }
 
 // ---------------------------------------------------------------------------------------
+// S5 (default): signature tail with SPARSE challenge products.  c has only TAU coefficients +-1 and s1, s2
+// have coefficients in [-eta, eta], so c*s1 and c*s2 are TAU signed negacyclic shifts of a small polynomial:
+//     (c*s)[n] = sum_t sign_t * e[256 + n - pos_t],   e[256 + i] = s[i], e[i] = -s[i]   (0 <= i < 256)
+// Per key polynomial the CTA keeps e in shared memory as biased NIBBLES (eta + e in 0..2*eta), once per sign and
+// once per alignment (pos_t mod 8), so a lane adds 8 consecutive coefficients of one term with ONE aligned
+// 4-byte shared load and one packed integer add; every GROUP terms (as many as fit in a nibble) the nibble
+// sums are spread into byte sums.  No NTT(c), no inverse transform and no multiplier work for the two
+// selective checks (r0, then z); shared-memory bandwidth (128 B/clk per SM) is the limit instead, which is why
+// the elements are nibbles and not bytes.  Only survivors (~24 %) pay NTT(c) and the c*t0 products through
+// the transform path.  Results are the same integers the transform path produces (|c*s| <= TAU*eta << Q/2),
+// so signatures stay bit-exact.  Used for eta = 2 (levels 2 and 5); level 3 (eta = 4) keeps the transform tail.
+// ---------------------------------------------------------------------------------------
+template <int K, int L, int32_t GAMMA1, int32_t GAMMA2, int BETA, int OMEGA, int TAU, int ETA, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) sign_tail_sparse_kernel(
+    int32_t* __restrict__ y /* in: y, out: z (in place) */, uint8_t* __restrict__ h_slot, uint8_t* __restrict__ accepted,
+    const int32_t* __restrict__ key_hat, const int8_t* __restrict__ key_small, int32_t* __restrict__ w /* in: w; scratch afterwards */,
+    const int8_t* __restrict__ c, uint32_t n_slots, uint32_t* __restrict__ work_ctr, const ResolveArgs ra) {
+    extern __shared__ __align__(16) uint32_t sm_words[];
+    constexpr int NP = L + K;                              // small key polynomials: s1 | s2
+    constexpr int GROUP = 15 / (2 * ETA);                  // terms whose biased nibbles can be added without a carry
+    constexpr int TABB = 2 * 8 * 256;                      // table bytes per polynomial: sign x alignment x 512 nibbles
+    static_assert(GROUP >= 1 && 2 * ETA * TAU < 256, "nibble / byte sums must not carry");
+    constexpr int G1BITS = GAMMA1 == (1 << 17) ? 17 : 19;
+    uint32_t* t0_sm = sm_words;                                   // K * 256: t0_hat * 256^-1
+    uint32_t* scr_all = t0_sm + K * N;                            // WARPS * SCRATCH_WORDS
+    uint32_t* hm_all = scr_all + WARPS * SCRATCH_WORDS;           // WARPS * K * 8 hint masks
+    uint16_t* terms_all = reinterpret_cast<uint16_t*>(hm_all + WARPS * K * 8);   // WARPS * 64 term offsets
+    uint8_t* tabs = reinterpret_cast<uint8_t*>(terms_all + WARPS * 64);          // NP * TABB
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (work_ctr != nullptr) {   // a CTA that starts when every slot is already claimed leaves at once (uniform decision)
+        __shared__ uint32_t late;
+        if (threadIdx.x == 0) late = *reinterpret_cast<volatile uint32_t*>(work_ctr) >= n_slots;
+        __syncthreads();
+        if (late) return;
+    }
+    for (int t = threadIdx.x; t < K * (N / 4); t += blockDim.x) {
+        int4 q = __ldg(reinterpret_cast<const int4*>(key_hat + (size_t)(L + K) * N) + t);
+        reinterpret_cast<uint4*>(t0_sm)[t] = make_uint4(mul_full(canon_signed(q.x), INV256), mul_full(canon_signed(q.y), INV256),
+                                                        mul_full(canon_signed(q.z), INV256), mul_full(canon_signed(q.w), INV256));
+    }
+    // tables: T[p][sign][a][m] = eta +- e_p[m + a]  (0 beyond the end) as nibbles, eight consecutive m per thread
+    for (int idx = threadIdx.x; idx < NP * 2 * 8 * 64; idx += blockDim.x) {
+        const int m = (idx & 63) * 8, al = (idx >> 6) & 7, sg = (idx >> 9) & 1, p = idx >> 10;
+        uint32_t word = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int j = m + q + al;
+            int e = 0;
+            if (j < 256) e = -(int)key_small[p * N + j];
+            else if (j < 512) e = (int)key_small[p * N + j - 256];
+            word |= (uint32_t)(ETA + (sg ? -e : e)) << (4 * q);
+        }
+        reinterpret_cast<uint32_t*>(tabs)[idx] = word;
+    }
+    __syncthreads();
+    uint32_t* scr = scr_all + warp * SCRATCH_WORDS;
+    uint32_t* hm = hm_all + warp * K * 8;
+    uint16_t* terms = terms_all + warp * 64;
+
+    // x[0..7] = (c * small_p)[8*lane .. 8*lane+7] from the term list of the current slot
+    auto sparse_mul = [&](int p, int32_t (&x)[8]) {
+        const uint8_t* tp = tabs + (size_t)p * TABB + 4 * lane;
+        uint32_t b0 = 0, b1 = 0, nacc = 0, tw = 0;
+#pragma unroll
+        for (int t = 0; t < TAU; t++) {
+            uint32_t u;
+            if ((t & 1) == 0) {   // term offsets are read two at a time
+                tw = (t + 1 < TAU) ? reinterpret_cast<const uint32_t*>(terms)[t >> 1] : (uint32_t)terms[t];
+                u = tw & 0xFFFFu;
+            } else {
+                u = tw >> 16;
+            }
+            nacc += *reinterpret_cast<const uint32_t*>(tp + u);
+            if (t % GROUP == GROUP - 1 || t == TAU - 1) {
+                b0 += nacc & 0x0F0F0F0Fu;          // coefficients 0, 2, 4, 6
+                b1 += (nacc >> 4) & 0x0F0F0F0Fu;   // coefficients 1, 3, 5, 7
+                nacc = 0;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = (int32_t)((((i & 1) ? b1 : b0) >> (8 * (i >> 1))) & 0xFFu) - TAU * ETA;
+    };
+
+    const uint32_t stride = gridDim.x * WARPS;
+    uint32_t claim = 0, a = blockIdx.x * WARPS + warp;
+    if (work_ctr != nullptr) {
+        if (lane == 0) claim = atomicAdd(work_ctr, 1u);
+        a = __shfl_sync(0xffffffffu, claim, 0);
+    }
+    for (; a < n_slots; a = work_ctr != nullptr ? __shfl_sync(0xffffffffu, claim, 0) : a + stride) {
+        if (work_ctr != nullptr && lane == 0) claim = atomicAdd(work_ctr, 1u);
+        // term list: offset of every non-zero coefficient's table row (sign, alignment, shift)
+        {
+            const uint2 cb = *reinterpret_cast<const uint2*>(c + (size_t)a * N + 8 * lane);
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t byte = ((i < 4 ? cb.x : cb.y) >> (8 * (i & 3))) & 0xFFu;
+                const uint32_t m = __ballot_sync(0xffffffffu, byte != 0);
+                if (byte != 0) {
+                    const int pos = 8 * lane + i, al = (-pos) & 7;
+                    terms[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((byte == 0xFFu ? 2048 : 0) + al * 256 + (256 - pos - al) / 2);
+                }
+                cnt += __popc(m);
+            }
+            __syncwarp();
+        }
+        // most selective check first (see sign_tail_kernel): r0 = LowBits(w) - c*s2, parked over w with the
+        // HighBits(w) != 0 flag for the survivors
+        bool bad = false;
+        int32_t* wa = w + (size_t)a * K * N;
+#pragma unroll 1
+        for (int i = 0; i < K && !bad; i++) {
+            int4* wp = reinterpret_cast<int4*>(wa + i * N) + 2 * lane;
+            const int4 w0 = wp[0], w1v = wp[1];
+            int32_t wv[8] = {w0.x, w0.y, w0.z, w0.w, w1v.x, w1v.y, w1v.z, w1v.w};
+            int32_t x[8];
+            sparse_mul(L + i, x);                   // c*s2_i
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                int32_t a0, w1;
+                decompose<GAMMA2>(wv[q], w1, a0);
+                const int32_t r0 = a0 - x[q];
+                bad |= (r0 >= GAMMA2 - BETA) || (r0 <= -(GAMMA2 - BETA));
+                wv[q] = r0 * 2 + (w1 != 0 ? 1 : 0);
+            }
+            bad = __any_sync(0xffffffffu, bad);
+            if (!bad) {
+                wp[0] = make_int4(wv[0], wv[1], wv[2], wv[3]);
+                wp[1] = make_int4(wv[4], wv[5], wv[6], wv[7]);
+            }
+        }
+        // z = y + c*s1, written over y
+        int32_t* ya = y + (size_t)a * L * N;
+#pragma unroll 1
+        for (int j = 0; j < L && !bad; j++) {
+            int4* yp = reinterpret_cast<int4*>(ya + j * N) + 2 * lane;
+            const int4 y0 = yp[0], y1 = yp[1];
+            int32_t x[8];
+            sparse_mul(j, x);                       // c*s1_j
+            const int32_t z[8] = {y0.x + x[0], y0.y + x[1], y0.z + x[2], y0.w + x[3], y1.x + x[4], y1.y + x[5], y1.z + x[6], y1.w + x[7]};
+#pragma unroll
+            for (int q = 0; q < 8; q++) bad |= (z[q] >= GAMMA1 - BETA) || (z[q] <= -(GAMMA1 - BETA));
+            yp[0] = make_int4(z[0], z[1], z[2], z[3]);
+            yp[1] = make_int4(z[4], z[5], z[6], z[7]);
+            bad = __any_sync(0xffffffffu, bad);
+        }
+        uint32_t nh = 0;
+        if (!bad) {
+            // survivors: c*t0 through the transform path; coefficient lane + 32 r per register from here on
+            __syncwarp();
+            uint32_t ch[8];
+            {
+                const int8_t* cp = c + (size_t)a * N + lane;
+#pragma unroll
+                for (int r = 0; r < 8; r++) ch[r] = (uint32_t)(int32_t)cp[32 * r];
+                FwdTw ftw;
+                load_fwd_tw(ftw, &TW_FWD, lane);
+                ntt_fwd_warp(ch, scr, ftw, lane);
+                __syncwarp();
+            }
+            InvTw itw;   // loaded here (survivors only) so the twiddle registers are free during the sparse phases
+            {
+                const TwTable* tab = &TW_INV;
+                asm volatile("" : "+l"(tab));
+                load_inv_tw(itw, tab, lane);
+            }
+            const int32_t* wi = wa + lane;
+#pragma unroll 1
+            for (int i = 0; i < K && !bad; i++) {
+                int32_t rv[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) rv[r] = wi[i * N + 32 * r];   // r0 * 2 + (w1 != 0), parked above (other lanes: after __syncwarp)
+                uint32_t x[8];
+                {
+                    const uint4* kp = reinterpret_cast<const uint4*>(t0_sm + i * N) + lane;
+                    const uint4 lo = kp[0], hi = kp[32];
+                    x[0] = mul_full(ch[0], lo.x); x[1] = mul_full(ch[1], lo.y); x[2] = mul_full(ch[2], lo.z); x[3] = mul_full(ch[3], lo.w);
+                    x[4] = mul_full(ch[4], hi.x); x[5] = mul_full(ch[5], hi.y); x[6] = mul_full(ch[6], hi.z); x[7] = mul_full(ch[7], hi.w);
+                    ntt_inv_warp<true>(x, scr, itw, lane);
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const int32_t ct0 = centre(x[r]);
+                    bad |= (ct0 >= GAMMA2) || (ct0 <= -GAMMA2);
+                    const int32_t v = (rv[r] >> 1) + ct0;
+                    const bool hint = (v > GAMMA2) || (v < -GAMMA2) || (v == -GAMMA2 && (rv[r] & 1));
+                    const uint32_t mask = __ballot_sync(0xffffffffu, hint);
+                    nh += __popc(mask);
+                    if (lane == 0) hm[i * 8 + r] = mask;
+                }
+                bad = __any_sync(0xffffffffu, bad);
+            }
+            bad = bad || nh > OMEGA;
+        }
+        __syncwarp();
+        if (!bad) {
+            // hint encoding: omega position bytes (ascending inside each polynomial), then k running counts
+            uint8_t* ho = h_slot + (size_t)a * (OMEGA + K);
+            for (int t = lane; t < OMEGA + K; t += 32) ho[t] = 0;
+            __syncwarp();
+            uint32_t run = 0;
+            for (int i = 0; i < K; i++) {
+                for (int r = 0; r < 8; r++) {
+                    uint32_t mask = hm[i * 8 + r];
+                    if ((mask >> lane) & 1u) ho[run + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)(32 * r + lane);
+                    run += __popc(mask);
+                }
+                if (lane == 0) ho[OMEGA + i] = (uint8_t)run;
+            }
+        }
+        if (lane == 0) accepted[a] = bad ? 0 : 1;
+        __syncwarp();
+        if (ra.zp != nullptr) {   // one slot per item: finish or re-queue the item here (no resolve pass)
+            const uint32_t item = ra.active[a];
+            if (bad) {
+                if (lane == 0) {
+                    ra.kappa[item] += 1;
+                    ra.next_active[atomicAdd(ra.next_count, 1u)] = item;
+                }
+            } else {
+                resolve_finish<L, G1BITS, OMEGA + K, true>(ra.zp, ra.h_out, ra.ct_out, ra.attempts, ra.kappa, ra.next_count, y, h_slot,
+                                                           ra.ct_slot, ra.done_list, item, a, 0u, nullptr, lane);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // S6: resolve, one warp per active item: the first accepted slot (smallest kappa) wins; its z is
 // packed (encoder.v:96-133: gamma1 - z, 18 or 20 bits) straight into the signature, h and c~ are
 // copied; items without an accepted slot advance kappa by `spec` and join the next round.
@@ -699,15 +930,48 @@ static cudaError_t launch_sign_tail_t(int32_t* y, uint8_t* h_slot, uint8_t* acce
     return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 8, 3>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr, ra);
 }
 
+template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA, int TAU, int ETA>
+static cudaError_t launch_sign_tail_sparse(int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat,
+                                           const int8_t* key_small, int32_t* w, const int8_t* c, uint32_t n_slots, int sm_count,
+                                           cudaStream_t st, uint32_t* work_ctr, const ResolveArgs& ra) {
+    constexpr int WARPS = 24;
+    constexpr size_t smem = (size_t)(K * N + WARPS * SCRATCH_WORDS + WARPS * K * 8) * 4 + (size_t)WARPS * 64 * 2 +
+                            (size_t)(L + K) * 2 * 8 * 256;
+    static_assert(smem <= 227 * 1024, "sparse tail tables do not fit in shared memory");
+    auto kern = sign_tail_sparse_kernel<K, L, G1, G2, BETA, OMEGA, TAU, ETA, WARPS>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    unsigned want = (n_slots + WARPS - 1) / WARPS;
+    unsigned cap = (unsigned)sm_count;
+    kern<<<want < cap ? want : cap, WARPS * 32, smem, st>>>(y, h_slot, accepted, key_hat, key_small, w, c, n_slots, work_ctr, ra);
+    return cudaGetLastError();
+}
+
+// key_small != nullptr selects the sparse-product tail (default); DIL_TAIL_SPARSE=0 or a null key_small the
+// transform-only tail
 cudaError_t launch_sign_tail(int level, int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat,
                              int32_t* w, const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st,
-                             uint32_t* work_ctr, const TailResolve* fused) {
+                             uint32_t* work_ctr, const TailResolve* fused, const int8_t* key_small) {
     if (n_slots == 0) return cudaSuccess;
     ResolveArgs ra;
     if (fused != nullptr) {
         ra.zp = fused->zp; ra.h_out = fused->h_out; ra.ct_out = fused->ct_out; ra.attempts = fused->attempts; ra.kappa = fused->kappa;
         ra.next_active = fused->next_active; ra.next_count = fused->next_count; ra.ct_slot = fused->ct_slot; ra.active = fused->active;
         ra.done_list = fused->done_list;
+    }
+    static int sparse = -1;
+    if (sparse < 0) { const char* e = std::getenv("DIL_TAIL_SPARSE"); sparse = (e && std::atoi(e) == 0) ? 0 : 1; }
+    if (sparse && key_small != nullptr) {
+        switch (level) {
+            case 2: return launch_sign_tail_sparse<4, 4, 1 << 17, (Q_I - 1) / 88, 78, 80, 39, 2>(y, h_slot, accepted, key_hat, key_small, w, c, n_slots, sm_count, st, work_ctr, ra);
+            case 3: break;   // eta = 4: nibble sums would carry; the transform tail below handles level 3
+            case 5: return launch_sign_tail_sparse<8, 7, 1 << 19, (Q_I - 1) / 32, 120, 75, 60, 2>(y, h_slot, accepted, key_hat, key_small, w, c, n_slots, sm_count, st, work_ctr, ra);
+            default: return cudaErrorInvalidValue;
+        }
     }
     switch (level) {
         case 2: return launch_sign_tail_t<4, 4, 1 << 17, (Q_I - 1) / 88, 78, 80>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr, ra);

@@ -130,6 +130,10 @@ int dil_sign_sizes(int level, size_t *z_bytes, size_t *h_bytes);
 int dil_sign_key_create(dil_engine_t *e, dil_sign_key_t **out, int level, const uint8_t *rho, const uint8_t *key,
                         const uint8_t *tr, const uint8_t *s1_packed, const uint8_t *s2_packed, const uint8_t *t0_packed);
 int dil_sign_key_destroy(dil_engine_t *e, dil_sign_key_t *k);
+/* host pointers.  When z, h, ctilde (and attempts, if given) are all pinned host memory the device can address
+ * (cudaHostAlloc / cudaHostRegister; z and ctilde 16-byte aligned), finished signatures are streamed into them
+ * round by round while the batch is still signing; pageable buffers take chunked copy-engine transfers.  The
+ * results are identical either way.  attempts may be NULL. */
 int dil_sign_batch_host(dil_engine_t *e, dil_sign_key_t *k, const uint8_t *msgs, const uint64_t *offsets, size_t n,
                         uint8_t *z, uint8_t *h, uint8_t *ctilde, uint32_t *attempts);
 /* device pointers (d_z 16-byte, d_ctilde 8-byte aligned); synchronises the stream once per rejection round */

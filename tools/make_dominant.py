@@ -5,7 +5,7 @@ import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1b"
 CLASSES = {"expand_mask": "expand_mask_kernel", "signcore": "matvec_shared_kernel", "challenge": "challenge_kernel",
-           "tail": "sign_tail_kernel"}
+           "tail": "sign_tail_sparse_kernel"}
 out = {}
 for cls, kern in CLASSES.items():
     path = os.path.join(ROOT, "profiles", f"{tag}_sign_{kern}.json")

@@ -10,7 +10,7 @@ python bench.py > $out/${tag}_bench_n1.log 2>&1; grep '^{' $out/${tag}_bench_n1.
 python bench.py --impl reference > $out/${tag}_bench_reference.log 2>&1; grep '^{' $out/${tag}_bench_reference.log > $out/${tag}_bench_reference.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches_bench.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $out/${tag}_bench_under_ncu.log 2>&1
-for k in expand_mask_kernel matvec_shared_kernel challenge_kernel sign_tail_kernel resolve_kernel; do
+for k in expand_mask_kernel matvec_shared_kernel challenge_kernel sign_tail_sparse_kernel resolve_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o $out/${tag}_$k python tools/sign_once.py 2 65536 > /dev/null 2>&1
 done
 ncu --set full --clock-control none --import-source on -k regex:drain_kernel -c 1 -f -o $out/${tag}_drain_kernel python tools/e2e_sign_bench.py 2 65536 1 > /dev/null 2>&1
