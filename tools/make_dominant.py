@@ -3,7 +3,7 @@
 summaries that tools/ncu_summary.py wrote:  python tools/make_dominant.py [tag]   (default tag r1b)"""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1b"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1c"
 CLASSES = {"expand_mask": "expand_mask_kernel", "signcore": "matvec_shared_kernel", "challenge": "challenge_kernel",
            "tail": "sign_tail_sparse_kernel"}
 out = {}
