@@ -1105,65 +1105,103 @@ __global__ void __launch_bounds__(256) unpack_z_kernel(int32_t* __restrict__ v, 
 }
 
 // per item: hint decode (omega position bytes + k running counts) with the standard well-formedness
-// checks -> 256-bit masks; c = SampleInBall(c~) written as the (L+1)-th polynomial of the item record
+// checks -> 256-bit masks; c = SampleInBall(c~) written as the (L+1)-th polynomial of the item record.
+// One thread per item, but everything that is indexed with data-dependent positions (hint bytes, hint masks,
+// the squeezed bytes and the challenge polynomial) lives in a private shared-memory row, and the warp moves
+// its 32 items' inputs and outputs cooperatively (coalesced) - as per-thread local arrays with per-thread
+// global rows this kernel cost more than the transform core of the whole verification.
+constexpr int VP_THREADS = 64;
 template <int K, int L, int OMEGA, int TAU>
-__global__ void __launch_bounds__(128) verify_prep_kernel(int32_t* __restrict__ v, uint32_t* __restrict__ hmask, uint32_t* __restrict__ bad,
-                                                          const uint8_t* __restrict__ h, const uint64_t* __restrict__ ctilde, uint32_t n) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const uint8_t* hp = h + (size_t)t * (OMEGA + K);
-    uint32_t m[K * 8];
-#pragma unroll
-    for (int i = 0; i < K * 8; i++) m[i] = 0;
-    bool b = false;
-    int idx = 0;
-    for (int i = 0; i < K; i++) {
-        int end = hp[OMEGA + i];
-        if (end < idx || end > OMEGA) { b = true; break; }
-        for (int j = idx; j < end; j++) {
-            int pos = hp[j];
-            if (j > idx && pos <= hp[j - 1]) b = true;
-            m[i * 8 + (pos >> 5)] |= 1u << (pos & 31);
-        }
-        idx = end;
+__global__ void __launch_bounds__(VP_THREADS) verify_prep_kernel(int32_t* __restrict__ v, uint32_t* __restrict__ hmask, uint32_t* __restrict__ bad,
+                                                                 const uint8_t* __restrict__ h, const uint64_t* __restrict__ ctilde, uint32_t n) {
+    constexpr int HB = OMEGA + K;
+    constexpr int HB_STRIDE = (HB + 3) / 4 * 4 + 4;      // bytes; breaks the power-of-two bank pattern
+    constexpr int M_STRIDE = K * 8 + 1;                  // words
+    __shared__ __align__(16) uint8_t c_sm[VP_THREADS * CH_C_STRIDE];
+    __shared__ __align__(16) uint8_t buf_sm[VP_THREADS * CH_BUF_STRIDE];
+    __shared__ __align__(4) uint8_t hp_sm[VP_THREADS * HB_STRIDE];
+    __shared__ uint32_t m_sm[VP_THREADS * M_STRIDE];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t base = blockIdx.x * VP_THREADS + warp * 32;   // first item of this warp
+    if (base >= n) return;
+    const uint32_t rows = n - base < 32 ? n - base : 32;
+    const uint32_t t = base + lane;
+    // stage the warp's hint strings (contiguous in global memory)
+    {
+        const uint8_t* src = h + (size_t)base * HB;
+        uint8_t* dstw = hp_sm + (size_t)warp * 32 * HB_STRIDE;
+        for (uint32_t i = lane; i < rows * HB; i += 32) dstw[(i / HB) * HB_STRIDE + (i % HB)] = src[i];
     }
-    for (int j = idx; j < OMEGA && !b; j++)
-        if (hp[j]) b = true;
-    for (int i = 0; i < K * 8; i++) hmask[(size_t)t * (K * 8) + i] = m[i];
-    if (b) bad[t] = 1;
-    // SampleInBall
-    uint64_t A[25];
+    uint8_t* c = c_sm + threadIdx.x * CH_C_STRIDE;
+    uint8_t* buf = buf_sm + threadIdx.x * CH_BUF_STRIDE;
+    const uint8_t* hp = hp_sm + threadIdx.x * HB_STRIDE;
+    uint32_t* m = m_sm + threadIdx.x * M_STRIDE;
+    __syncwarp();
+    if (t < n) {
 #pragma unroll
-    for (int i = 0; i < 25; i++) A[i] = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) A[i] = ctilde[(size_t)t * 4 + i];
-    A[4] = 0x1F;
-    A[16] = 0x80ULL << 56;
-    keccak_f1600(A);
-    uint64_t signs = A[0];
-    __align__(8) uint8_t buf[136];
-    __align__(4) int8_t c[N];
-#pragma unroll
-    for (int i = 0; i < 17; i++) reinterpret_cast<uint64_t*>(buf)[i] = A[i];
-    for (int i = 0; i < N; i++) c[i] = 0;
-    int pos = 8;
-    for (int i = N - TAU; i < N; i++) {
-        int bb;
-        do {
-            if (pos == 136) {
-                keccak_f1600(A);
-#pragma unroll
-                for (int q = 0; q < 17; q++) reinterpret_cast<uint64_t*>(buf)[q] = A[q];
-                pos = 0;
+        for (int i = 0; i < K * 8; i++) m[i] = 0;
+        bool b = false;
+        int idx = 0;
+        for (int i = 0; i < K; i++) {
+            int end = hp[OMEGA + i];
+            if (end < idx || end > OMEGA) { b = true; break; }
+            for (int j = idx; j < end; j++) {
+                int pos = hp[j];
+                if (j > idx && pos <= hp[j - 1]) b = true;
+                m[i * 8 + (pos >> 5)] |= 1u << (pos & 31);
             }
-            bb = buf[pos++];
-        } while (bb > i);
-        c[i] = c[bb];
-        c[bb] = (signs & 1) ? -1 : 1;
-        signs >>= 1;
+            idx = end;
+        }
+        for (int j = idx; j < OMEGA && !b; j++)
+            if (hp[j]) b = true;
+        if (b) bad[t] = 1;
+        // SampleInBall
+        uint64_t A[25];
+#pragma unroll
+        for (int i = 0; i < 25; i++) A[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) A[i] = ctilde[(size_t)t * 4 + i];
+        A[4] = 0x1F;
+        A[16] = 0x80ULL << 56;
+        keccak_f1600(A);
+        uint64_t signs = A[0];
+#pragma unroll
+        for (int i = 0; i < 17; i++) reinterpret_cast<uint64_t*>(buf)[i] = A[i];
+#pragma unroll
+        for (int i = 0; i < N / 16; i++) reinterpret_cast<uint4*>(c)[i] = make_uint4(0, 0, 0, 0);
+        int pos = 8;
+        for (int i = N - TAU; i < N; i++) {
+            int bb;
+            do {
+                if (pos == 136) {
+                    keccak_f1600(A);
+#pragma unroll
+                    for (int q = 0; q < 17; q++) reinterpret_cast<uint64_t*>(buf)[q] = A[q];
+                    pos = 0;
+                }
+                bb = buf[pos++];
+            } while (bb > i);
+            c[i] = c[bb];
+            c[bb] = (signs & 1) ? (uint8_t)0xFF : (uint8_t)1;
+            signs >>= 1;
+        }
     }
-    int32_t* dst = v + (size_t)t * ((L + 1) * N) + L * N;
-    for (int i = 0; i < N; i++) dst[i] = c[i];
+    __syncwarp();
+    // cooperative write-out: hint masks (contiguous for the warp's items) and c as int32 polynomials
+    {
+        uint32_t* dstm = hmask + (size_t)base * (K * 8);
+        const uint32_t* srcm = m_sm + (size_t)warp * 32 * M_STRIDE;
+        for (uint32_t i = lane; i < rows * (K * 8); i += 32) dstm[i] = srcm[(i / (K * 8)) * M_STRIDE + (i % (K * 8))];
+        const uint8_t* srcc = c_sm + (size_t)warp * 32 * CH_C_STRIDE;
+        for (uint32_t r = 0; r < rows; r++) {
+            int4* dst = reinterpret_cast<int4*>(v + (size_t)(base + r) * ((L + 1) * N) + L * N);
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const uint32_t wd = reinterpret_cast<const uint32_t*>(srcc + r * CH_C_STRIDE)[lane + 32 * q];
+                dst[lane + 32 * q] = make_int4((int8_t)(wd & 0xFF), (int8_t)((wd >> 8) & 0xFF), (int8_t)((wd >> 16) & 0xFF), (int8_t)(wd >> 24));
+            }
+        }
+    }
 }
 
 // w1' = UseHint(h, w') (usehint.v:134-155), packed; one thread per 16 coefficients
@@ -1287,11 +1325,11 @@ cudaError_t launch_unpack_z(int level, int32_t* v, uint32_t* bad, const uint8_t*
 cudaError_t launch_verify_prep(int level, int32_t* v, uint32_t* hmask, uint32_t* bad, const uint8_t* h, const uint64_t* ctilde,
                                uint32_t n, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    unsigned grid = (n + 127) / 128;
+    unsigned grid = (n + VP_THREADS - 1) / VP_THREADS;
     switch (level) {
-        case 2: verify_prep_kernel<4, 4, 80, 39><<<grid, 128, 0, st>>>(v, hmask, bad, h, ctilde, n); break;
-        case 3: verify_prep_kernel<6, 5, 55, 49><<<grid, 128, 0, st>>>(v, hmask, bad, h, ctilde, n); break;
-        case 5: verify_prep_kernel<8, 7, 75, 60><<<grid, 128, 0, st>>>(v, hmask, bad, h, ctilde, n); break;
+        case 2: verify_prep_kernel<4, 4, 80, 39><<<grid, VP_THREADS, 0, st>>>(v, hmask, bad, h, ctilde, n); break;
+        case 3: verify_prep_kernel<6, 5, 55, 49><<<grid, VP_THREADS, 0, st>>>(v, hmask, bad, h, ctilde, n); break;
+        case 5: verify_prep_kernel<8, 7, 75, 60><<<grid, VP_THREADS, 0, st>>>(v, hmask, bad, h, ctilde, n); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
