@@ -1,11 +1,27 @@
 // kernels.h — host-side launchers of the engine's CUDA kernels (internal to the library).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 
 #include <cstddef>
 #include <cstdint>
 
 namespace dil {
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device attribute: `done` remembers, per kernel,
+// on which devices it has been set (one bit per device ordinal), so engines on several GPUs of one process work.
+template <class Kern>
+inline cudaError_t ensure_dyn_smem(Kern kern, size_t smem, std::atomic<uint64_t>& done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+
 
 enum class EwOp : int { MUL = 0, MULACC = 1, ADD = 2, SUB = 3 };
 

@@ -268,12 +268,8 @@ static cudaError_t launch_shared_t(int32_t* w, const int32_t* a_hat, const uint8
                                    int sm_count, cudaStream_t st, uint32_t* work_ctr = nullptr, uint8_t* w1p = nullptr) {
     auto kern = matvec_shared_kernel<K, L, WARPS, EXPAND, NTT_IN, INTT_OUT, W1>;
     constexpr size_t smem = shared_smem_bytes<K, L>(WARPS);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
+    if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(smem), configured); e != cudaSuccess) return e;
     int ctas_per_sm = (int)((220 * 1024) / smem);
     if (ctas_per_sm > shared_min_ctas(K, L, WARPS)) ctas_per_sm = shared_min_ctas(K, L, WARPS);
     if (ctas_per_sm > MAX_CTAS) ctas_per_sm = MAX_CTAS;
@@ -311,12 +307,8 @@ static cudaError_t launch_item_t(int32_t* w, const uint8_t* rho, const int32_t* 
     constexpr int NW = (G * K * L + 31) / 32;
     auto kern = matvec_item_kernel<K, L, G, NTT_IN, INTT_OUT>;
     constexpr size_t smem = (size_t)(G * K * L * A_STRIDE + NW * SCRATCH_WORDS) * 4;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
+    if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(smem), configured); e != cudaSuccess) return e;
     constexpr int threads = NW * 32;
     kern<<<(unsigned)((batch + G - 1) / G), threads, smem, st>>>(w, rho, v, (uint32_t)batch, nullptr);
     return cudaGetLastError();
@@ -384,12 +376,8 @@ static cudaError_t launch_verify_item_t(int32_t* w, const uint8_t* rho, const in
     constexpr int NW = (G * K * L + 31) / 32;
     auto kern = matvec_item_kernel<K, L, G, true, true, true>;
     constexpr size_t smem = (size_t)(G * K * L * A_STRIDE + NW * SCRATCH_WORDS) * 4;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
+    if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(smem), configured); e != cudaSuccess) return e;
     kern<<<(unsigned)((batch + G - 1) / G), NW * 32, smem, st>>>(w, rho, v, (uint32_t)batch, extra);
     return cudaGetLastError();
 }

@@ -222,12 +222,8 @@ template <int WARPS, bool INVERSE>
 static cudaError_t launch_ntt_pair(int32_t* dst, const int32_t* src, size_t n_polys, int sm_count, cudaStream_t st) {
     using Smem = NttPairSmem<WARPS, 3>;
     auto kern = ntt_pair_kernel<WARPS, 3, INVERSE>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
+    if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(sizeof(Smem)), configured); e != cudaSuccess) return e;
     size_t n_pairs = (n_polys + 1) / 2;
     size_t want = (n_pairs + WARPS - 1) / WARPS;
     size_t cap = (size_t)sm_count;
@@ -245,12 +241,8 @@ template <int WARPS, int STAGES, int CTAS, bool INVERSE>
 static cudaError_t launch_ntt_cfg(int32_t* dst, const int32_t* src, size_t n_polys, int sm_count, cudaStream_t st) {
     using Smem = NttSmem<WARPS, STAGES>;
     auto kern = ntt_tma_kernel<WARPS, STAGES, CTAS, INVERSE>;
-    static bool configured = false;  // per-process; attribute is per-function and idempotent
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
+    if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(sizeof(Smem)), configured); e != cudaSuccess) return e;
     size_t want = (n_polys + WARPS - 1) / WARPS;
     size_t cap = (size_t)sm_count * CTAS;
     unsigned grid = (unsigned)(want < cap ? want : cap);

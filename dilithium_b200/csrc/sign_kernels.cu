@@ -825,12 +825,8 @@ static cudaError_t launch_expand_mask_t(int32_t* y, const uint64_t* rhop, const 
     constexpr int ROW = 32 * (G1B + 1) + 16;
     constexpr size_t smem = (size_t)4 * 32 * ROW;
     auto kern = expand_mask_kernel<L, G1B>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
+    if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(smem), configured); e != cudaSuccess) return e;
     uint32_t n_polys = n_slots * L;
     unsigned grid = (n_polys + 127) / 128;
     const unsigned cap = (unsigned)overlap_knob("DIL_EM_CTAS", 0) * 148u;   // 0: uncapped (one chunk per warp)
@@ -870,14 +866,14 @@ cudaError_t launch_drain(uint8_t* hz, uint8_t* hh, uint8_t* hct, uint32_t* hatt,
     // when the SMs are empty.  DIL_DRAIN_CTAS / DIL_DRAIN_SMEM_KB are tuning knobs.
     static int ctas = -1, smem_kb = -1;
     if (ctas < 0) {
-        const char* e = std::getenv("DIL_DRAIN_CTAS");
-        ctas = (e && std::atoi(e) > 0) ? std::atoi(e) : 4;
-        e = std::getenv("DIL_DRAIN_SMEM_KB");
+        const char* e = std::getenv("DIL_DRAIN_SMEM_KB");
         smem_kb = (e && std::atoi(e) >= 0) ? std::atoi(e) : 200;
         if (smem_kb > 226) smem_kb = 226;
-        cudaError_t er = cudaFuncSetAttribute(drain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kb * 1024);
-        if (er != cudaSuccess) { ctas = -1; return er; }
+        e = std::getenv("DIL_DRAIN_CTAS");
+        ctas = (e && std::atoi(e) > 0) ? std::atoi(e) : 4;
     }
+    static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
+    if (cudaError_t e = ensure_dyn_smem(drain_kernel, (size_t)smem_kb * 1024, configured); e != cudaSuccess) return e;
     unsigned grid = (n + 15) / 16 < (unsigned)ctas ? (n + 15) / 16 : (unsigned)ctas;
     drain_kernel<<<grid, 512, (size_t)smem_kb * 1024, st>>>(hz, hh, hct, hatt, zp, h, ct, att, list, n, zb, hb);
     return cudaGetLastError();
@@ -906,12 +902,8 @@ static cudaError_t launch_sign_tail_w(int32_t* y, uint8_t* h_slot, uint8_t* acce
     constexpr int ZB = L * 32 * ((G1 == (1 << 17) ? 17 : 19) + 1);
     constexpr size_t smem = (size_t)((L + 2 * K) * N + WARPS * SCRATCH_WORDS + WARPS * K * 8) * 4 + (size_t)WARPS * ZB;
     auto kern = sign_tail_kernel<K, L, G1, G2, BETA, OMEGA, WARPS, CTAS>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
+    if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(smem), configured); e != cudaSuccess) return e;
     unsigned want = (n_slots + WARPS - 1) / WARPS;
     unsigned cap = (unsigned)sm_count * CTAS;
     kern<<<want < cap ? want : cap, WARPS * 32, smem, st>>>(y, h_slot, accepted, key_hat, w, c, n_slots, work_ctr, ra);
@@ -939,12 +931,8 @@ static cudaError_t launch_sign_tail_sparse(int32_t* y, uint8_t* h_slot, uint8_t*
                             (size_t)(L + K) * 2 * 8 * 256;
     static_assert(smem <= 227 * 1024, "sparse tail tables do not fit in shared memory");
     auto kern = sign_tail_sparse_kernel<K, L, G1, G2, BETA, OMEGA, TAU, ETA, WARPS>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
+    if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(smem), configured); e != cudaSuccess) return e;
     unsigned want = (n_slots + WARPS - 1) / WARPS;
     unsigned cap = (unsigned)sm_count;
     kern<<<want < cap ? want : cap, WARPS * 32, smem, st>>>(y, h_slot, accepted, key_hat, key_small, w, c, n_slots, work_ctr, ra);
