@@ -28,6 +28,9 @@ __device__ __forceinline__ void decompose(int32_t a, int32_t& a1, int32_t& a0) {
     a0 -= (((Q_I - 1) / 2 - a0) >> 31) & Q_I;
 }
 
+// centred representative in (-Q/2, Q/2] of a canonical coefficient
+__device__ __forceinline__ int32_t centre(uint32_t a) { return (int32_t)a - (int32_t)((a > (Q - 1) / 2) ? Q : 0); }
+
 // HighBits only (w1), for a canonical coefficient
 template <int32_t GAMMA2>
 __device__ __forceinline__ uint32_t highbits(uint32_t a) {

@@ -347,6 +347,80 @@ struct ResolveArgs {
     uint32_t* done_list = nullptr;
 };
 
+// Survivors of the r0 and z checks: ct0_i = INTT(c_hat o t0_hat_i), ||ct0|| < gamma2, hint bits of
+// (r0 + ct0, HighBits(w)) as 32-bit ballot masks hm[i*8 + r] (bit = lane, coefficient lane + 32 r), their count in nh.
+// wi points at this lane's parked "r0 * 2 + (HighBits(w) != 0)" words (coefficient lane + 32 r at wi[i*N + 32 r]);
+// t0_sm holds t0_hat pre-multiplied by 256^-1.  Returns true when a bound is violated.  Executed by one warp.
+template <int K, int32_t GAMMA2>
+__device__ __forceinline__ bool tail_ct0_hints(const uint32_t (&ch)[8], const uint32_t* __restrict__ t0_sm, const int32_t* wi,
+                                               uint32_t* __restrict__ scr, const InvTw& itw, uint32_t* __restrict__ hm, int lane,
+                                               uint32_t& nh) {
+    bool bad = false;
+#pragma unroll 1
+    for (int i = 0; i < K && !bad; i++) {
+        int32_t rv[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) rv[r] = wi[i * N + 32 * r];
+        uint32_t x[8];
+        const uint4* kp = reinterpret_cast<const uint4*>(t0_sm + i * N) + lane;
+        const uint4 lo = kp[0], hi = kp[32];
+        x[0] = mul_full(ch[0], lo.x); x[1] = mul_full(ch[1], lo.y); x[2] = mul_full(ch[2], lo.z); x[3] = mul_full(ch[3], lo.w);
+        x[4] = mul_full(ch[4], hi.x); x[5] = mul_full(ch[5], hi.y); x[6] = mul_full(ch[6], hi.z); x[7] = mul_full(ch[7], hi.w);
+        ntt_inv_warp<true>(x, scr, itw, lane);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int32_t ct0 = centre(x[r]);
+            bad |= (ct0 >= GAMMA2) || (ct0 <= -GAMMA2);
+            const int32_t v = (rv[r] >> 1) + ct0;
+            const bool hint = (v > GAMMA2) || (v < -GAMMA2) || (v == -GAMMA2 && (rv[r] & 1));
+            const uint32_t mask = __ballot_sync(0xffffffffu, hint);
+            nh += __popc(mask);
+            if (lane == 0) hm[i * 8 + r] = mask;
+        }
+        bad = __any_sync(0xffffffffu, bad);
+    }
+    return bad;
+}
+
+// End of a slot: hint bytes of an accepted slot (omega position bytes, ascending inside each polynomial, then k
+// running counts), the accept flag, and - in rounds with one slot per item (ra.zp != nullptr) - the resolve step:
+// the accepted slot becomes the signature, a rejected item advances kappa and joins the next round.
+template <int K, int L, int G1BITS, int OMEGA, bool DIRECT>
+__device__ __forceinline__ void tail_finish(bool bad, uint32_t a, const int32_t* y, uint8_t* h_slot, uint8_t* __restrict__ accepted,
+                                            const uint32_t* __restrict__ hm, const ResolveArgs& ra, uint8_t* zstage, int lane) {
+    __syncwarp();
+    if (!bad) {
+        uint8_t* ho = h_slot + (size_t)a * (OMEGA + K);
+        for (int t = lane; t < OMEGA + K; t += 32) ho[t] = 0;
+        __syncwarp();
+        uint32_t run = 0;
+        for (int i = 0; i < K; i++) {
+            for (int r = 0; r < 8; r++) {
+                const uint32_t mask = hm[i * 8 + r];
+                if ((mask >> lane) & 1u) ho[run + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)(32 * r + lane);
+                run += __popc(mask);
+            }
+            if (lane == 0) ho[OMEGA + i] = (uint8_t)run;
+        }
+    }
+    if (lane == 0) accepted[a] = bad ? 0 : 1;
+    __syncwarp();
+    if (ra.zp != nullptr) {
+        const uint32_t item = ra.active[a];
+        if (bad) {
+            if (lane == 0) {
+                ra.kappa[item] += 1;
+                ra.next_active[atomicAdd(ra.next_count, 1u)] = item;
+            }
+        } else {
+            resolve_finish<L, G1BITS, OMEGA + K, DIRECT>(ra.zp, ra.h_out, ra.ct_out, ra.attempts, ra.kappa, ra.next_count, y, h_slot,
+                                                         ra.ct_slot, ra.done_list, item, a, 0u, zstage, lane);
+        }
+    }
+}
+
+
 // ---------------------------------------------------------------------------------------
 // S5: signature tail, one warp per active item.
 //   c_hat = NTT(c); z = y + INTT(c_hat o s1_hat); ||z|| < gamma1 - beta
@@ -355,7 +429,6 @@ struct ResolveArgs {
 // Key polynomials (s1_hat | s2_hat | t0_hat, NTT domain) live in shared memory per persistent CTA.
 // Rejected items are appended to the next round's active list.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ int32_t centre(uint32_t a) { return (int32_t)a - (int32_t)((a > (Q - 1) / 2) ? Q : 0); }
 
 template <int K, int L, int32_t GAMMA1, int32_t GAMMA2, int BETA, int OMEGA, int WARPS, int CTAS>
 __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
@@ -465,56 +538,8 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
             bad = __any_sync(0xffffffffu, bad);
         }
         uint32_t nh = 0;
-#pragma unroll 1
-        for (int i = 0; i < K && !bad; i++) {
-            int32_t rv[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++) rv[r] = wi[i * N + 32 * r];   // r0 * 2 + (w1 != 0), parked above by this lane
-            uint32_t x[8];
-            mul_inv(x, L + K + i);                  // c*t0_i
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const int32_t ct0 = centre(x[r]);
-                bad |= (ct0 >= GAMMA2) || (ct0 <= -GAMMA2);
-                const int32_t v = (rv[r] >> 1) + ct0;
-                const bool hint = (v > GAMMA2) || (v < -GAMMA2) || (v == -GAMMA2 && (rv[r] & 1));
-                const uint32_t mask = __ballot_sync(0xffffffffu, hint);
-                nh += __popc(mask);
-                if (lane == 0) hm[i * 8 + r] = mask;
-            }
-            bad = __any_sync(0xffffffffu, bad);
-        }
-        bad = bad || nh > OMEGA;
-        __syncwarp();
-        if (!bad) {
-            // hint encoding: omega position bytes (ascending inside each polynomial), then k running counts
-            uint8_t* ho = h_slot + (size_t)a * (OMEGA + K);
-            for (int t = lane; t < OMEGA + K; t += 32) ho[t] = 0;
-            __syncwarp();
-            uint32_t run = 0;
-            for (int i = 0; i < K; i++) {
-                for (int r = 0; r < 8; r++) {
-                    uint32_t mask = hm[i * 8 + r];
-                    if ((mask >> lane) & 1u) ho[run + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)(32 * r + lane);
-                    run += __popc(mask);
-                }
-                if (lane == 0) ho[OMEGA + i] = (uint8_t)run;
-            }
-        }
-        if (lane == 0) accepted[a] = bad ? 0 : 1;
-        __syncwarp();
-        if (ra.zp != nullptr) {   // one slot per item: finish or re-queue the item here (no resolve pass)
-            const uint32_t item = ra.active[a];
-            if (bad) {
-                if (lane == 0) {
-                    ra.kappa[item] += 1;
-                    ra.next_active[atomicAdd(ra.next_count, 1u)] = item;
-                }
-            } else {
-                resolve_finish<L, G1BITS, OMEGA + K>(ra.zp, ra.h_out, ra.ct_out, ra.attempts, ra.kappa, ra.next_count, y, h_slot, ra.ct_slot,
-                                                     ra.done_list, item, a, 0u, zstage_all + (size_t)warp * ZB, lane);
-            }
-        }
+        if (!bad) bad = tail_ct0_hints<K, GAMMA2>(ch, key_sm + (L + K) * N, wi, scr, itw, hm, lane, nh) || nh > OMEGA;
+        tail_finish<K, L, G1BITS, OMEGA, false>(bad, a, y, h_slot, accepted, hm, ra, zstage_all + (size_t)warp * ZB, lane);
     }
 }
 
@@ -686,65 +711,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sign_tail_sparse_kernel(
                 asm volatile("" : "+l"(tab));
                 load_inv_tw(itw, tab, lane);
             }
-            const int32_t* wi = wa + lane;
-#pragma unroll 1
-            for (int i = 0; i < K && !bad; i++) {
-                int32_t rv[8];
-#pragma unroll
-                for (int r = 0; r < 8; r++) rv[r] = wi[i * N + 32 * r];   // r0 * 2 + (w1 != 0), parked above (other lanes: after __syncwarp)
-                uint32_t x[8];
-                {
-                    const uint4* kp = reinterpret_cast<const uint4*>(t0_sm + i * N) + lane;
-                    const uint4 lo = kp[0], hi = kp[32];
-                    x[0] = mul_full(ch[0], lo.x); x[1] = mul_full(ch[1], lo.y); x[2] = mul_full(ch[2], lo.z); x[3] = mul_full(ch[3], lo.w);
-                    x[4] = mul_full(ch[4], hi.x); x[5] = mul_full(ch[5], hi.y); x[6] = mul_full(ch[6], hi.z); x[7] = mul_full(ch[7], hi.w);
-                    ntt_inv_warp<true>(x, scr, itw, lane);
-                    __syncwarp();
-                }
-#pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    const int32_t ct0 = centre(x[r]);
-                    bad |= (ct0 >= GAMMA2) || (ct0 <= -GAMMA2);
-                    const int32_t v = (rv[r] >> 1) + ct0;
-                    const bool hint = (v > GAMMA2) || (v < -GAMMA2) || (v == -GAMMA2 && (rv[r] & 1));
-                    const uint32_t mask = __ballot_sync(0xffffffffu, hint);
-                    nh += __popc(mask);
-                    if (lane == 0) hm[i * 8 + r] = mask;
-                }
-                bad = __any_sync(0xffffffffu, bad);
-            }
-            bad = bad || nh > OMEGA;
+            bad = tail_ct0_hints<K, GAMMA2>(ch, t0_sm, wa + lane, scr, itw, hm, lane, nh) || nh > OMEGA;
         }
-        __syncwarp();
-        if (!bad) {
-            // hint encoding: omega position bytes (ascending inside each polynomial), then k running counts
-            uint8_t* ho = h_slot + (size_t)a * (OMEGA + K);
-            for (int t = lane; t < OMEGA + K; t += 32) ho[t] = 0;
-            __syncwarp();
-            uint32_t run = 0;
-            for (int i = 0; i < K; i++) {
-                for (int r = 0; r < 8; r++) {
-                    uint32_t mask = hm[i * 8 + r];
-                    if ((mask >> lane) & 1u) ho[run + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)(32 * r + lane);
-                    run += __popc(mask);
-                }
-                if (lane == 0) ho[OMEGA + i] = (uint8_t)run;
-            }
-        }
-        if (lane == 0) accepted[a] = bad ? 0 : 1;
-        __syncwarp();
-        if (ra.zp != nullptr) {   // one slot per item: finish or re-queue the item here (no resolve pass)
-            const uint32_t item = ra.active[a];
-            if (bad) {
-                if (lane == 0) {
-                    ra.kappa[item] += 1;
-                    ra.next_active[atomicAdd(ra.next_count, 1u)] = item;
-                }
-            } else {
-                resolve_finish<L, G1BITS, OMEGA + K, true>(ra.zp, ra.h_out, ra.ct_out, ra.attempts, ra.kappa, ra.next_count, y, h_slot,
-                                                           ra.ct_slot, ra.done_list, item, a, 0u, nullptr, lane);
-            }
-        }
+        tail_finish<K, L, G1BITS, OMEGA, true>(bad, a, y, h_slot, accepted, hm, ra, nullptr, lane);
     }
 }
 
