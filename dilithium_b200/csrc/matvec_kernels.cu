@@ -55,14 +55,45 @@ cudaError_t launch_expand_a(int32_t* a_hat, const uint8_t* rho, size_t n_rho, in
 // W1 = true (signing): besides w the core also emits w1 = HighBits(w), bit-packed as encoder.v:96-133 (6 bits for
 // gamma2 = (Q-1)/88, i.e. K = 4, else 4 bits), into w1_item - the input of the challenge hash - so that no
 // separate pass has to read w again.
-template <int K, int LA, bool NTT_IN, bool INTT_OUT, bool EXTRA = false, bool W1 = false>
+// SPLIT = true (per-item kernel of level 5, two warps per item): both warps of the CTA call this together; warp
+// `part` transforms every second input and publishes it through yh_sm (layout C), and computes rows
+// [part*K/2, (part+1)*K/2) of the result - the single-warp latency of the per-item core is halved.
+template <int K, int LA, bool NTT_IN, bool INTT_OUT, bool EXTRA = false, bool W1 = false, bool SPLIT = false>
 __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const int32_t* __restrict__ v_item,
                                           const uint32_t* __restrict__ a_sm, uint32_t* __restrict__ scr, int lane,
                                           const int32_t* __restrict__ extra_item = nullptr,
-                                          uint8_t* __restrict__ w1_item = nullptr) {
+                                          uint8_t* __restrict__ w1_item = nullptr, uint32_t* __restrict__ yh_sm = nullptr,
+                                          int part = 0) {
     constexpr int L = LA + (EXTRA ? 1 : 0);   // number of input polynomials
     uint32_t yh[L][8];  // NTT-domain inputs in layout C
-    if constexpr (NTT_IN) {
+    if constexpr (NTT_IN && SPLIT) {
+        FwdTw ftw;
+        {
+            const TwTable* tab = &TW_FWD;
+            asm volatile("" : "+l"(tab));
+            load_fwd_tw(ftw, tab, lane);
+        }
+#pragma unroll 1
+        for (int j = part; j < L; j += 2) {
+            uint32_t x[8];
+            const int32_t* p = v_item + j * N + lane;
+#pragma unroll
+            for (int r = 0; r < 8; r++) x[r] = (uint32_t)p[32 * r];
+            ntt_fwd_warp(x, scr, ftw, lane);
+            __syncwarp();
+            uint4* o = reinterpret_cast<uint4*>(yh_sm + j * N) + lane;
+            o[0] = make_uint4(x[0], x[1], x[2], x[3]);
+            o[32] = make_uint4(x[4], x[5], x[6], x[7]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            const uint4* q = reinterpret_cast<const uint4*>(yh_sm + j * N) + lane;
+            const uint4 lo = q[0], hi = q[32];
+            yh[j][0] = lo.x; yh[j][1] = lo.y; yh[j][2] = lo.z; yh[j][3] = lo.w;
+            yh[j][4] = hi.x; yh[j][5] = hi.y; yh[j][6] = hi.z; yh[j][7] = hi.w;
+        }
+    } else if constexpr (NTT_IN) {
 #pragma unroll
         for (int j = 0; j < L; j++) {
             const int32_t* p = v_item + j * N + lane;
@@ -89,8 +120,9 @@ __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const in
             yh[j][4] = canon_signed(hi.x); yh[j][5] = canon_signed(hi.y); yh[j][6] = canon_signed(hi.z); yh[j][7] = canon_signed(hi.w);
         }
     }
+    const int i_begin = SPLIT ? part * (K / 2) : 0, i_end = SPLIT ? (part + 1) * (K / 2) : K;
 #pragma unroll 1
-    for (int i = 0; i < K; i++) {
+    for (int i = i_begin; i < i_end; i++) {
         uint64_t acc[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) acc[r] = 0;
@@ -227,6 +259,14 @@ __global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L, WARPS)) matv
 // the per-item core for its share of the G items.
 template <int K, int L>
 constexpr int item_group() { return K * L == 16 ? 4 : 1; }
+// level 5 (k*l = 56 Keccak threads = two warps for one item): both warps share the item's core
+template <int K, int L, int G, bool NTT_IN>
+__host__ __device__ constexpr bool item_split() { return G == 1 && (K * L + 31) / 32 == 2 && K % 2 == 0 && NTT_IN; }
+template <int K, int L, int G, bool NTT_IN, bool EXTRA>
+constexpr size_t item_smem_bytes() {
+    constexpr int NW = (G * K * L + 31) / 32;
+    return (size_t)(G * K * L * A_STRIDE + NW * SCRATCH_WORDS + (item_split<K, L, G, NTT_IN>() ? (L + (EXTRA ? 1 : 0)) * N : 0)) * 4;
+}
 
 template <int K, int L, int G, bool NTT_IN, bool INTT_OUT, bool EXTRA = false>
 __global__ void __launch_bounds__(((G * K * L + 31) / 32) * 32) matvec_item_kernel(int32_t* __restrict__ w,
@@ -235,8 +275,10 @@ __global__ void __launch_bounds__(((G * K * L + 31) / 32) * 32) matvec_item_kern
                                                                                  const int32_t* __restrict__ extra = nullptr) {
     extern __shared__ __align__(16) uint32_t smem_u32v[];
     constexpr int NW = (G * K * L + 31) / 32;
+    constexpr bool SPLIT = item_split<K, L, G, NTT_IN>();         // two warps share one item's core
     uint32_t* a_sm = smem_u32v;                                   // G * K*L * A_STRIDE
     uint32_t* scr_all = smem_u32v + G * K * L * A_STRIDE;         // NW * SCRATCH_WORDS
+    uint32_t* yh_sm = scr_all + NW * SCRATCH_WORDS;               // SPLIT: (L [+1]) * 256 transformed inputs
     const int t = threadIdx.x;
     const size_t item0 = (size_t)blockIdx.x * G;
     if (t < G * K * L) {
@@ -249,12 +291,19 @@ __global__ void __launch_bounds__(((G * K * L + 31) / 32) * 32) matvec_item_kern
     }
     __syncthreads();
     const int warp = t >> 5, lane = t & 31;
+    if constexpr (SPLIT) {
+        if (item0 < batch)   // uniform for the CTA: both warps enter (the core synchronises the CTA once)
+            item_core<K, L, NTT_IN, INTT_OUT, EXTRA, false, true>(w + item0 * K * N, v + item0 * (L + (EXTRA ? 1 : 0)) * N, a_sm,
+                                                                 scr_all + warp * SCRATCH_WORDS, lane,
+                                                                 EXTRA ? extra + item0 * K * N : nullptr, nullptr, yh_sm, warp);
+    } else {
     for (int g = warp; g < G; g += NW) {
         const size_t item = item0 + g;
         if (item < batch)
             item_core<K, L, NTT_IN, INTT_OUT, EXTRA>(w + item * K * N, v + item * (L + (EXTRA ? 1 : 0)) * N,
                                                      a_sm + g * K * L * A_STRIDE, scr_all + warp * SCRATCH_WORDS, lane,
                                                      EXTRA ? extra + item * K * N : nullptr);
+    }
     }
 }
 
@@ -306,7 +355,7 @@ static cudaError_t launch_item_t(int32_t* w, const uint8_t* rho, const int32_t* 
     constexpr int G = item_group<K, L>();
     constexpr int NW = (G * K * L + 31) / 32;
     auto kern = matvec_item_kernel<K, L, G, NTT_IN, INTT_OUT>;
-    constexpr size_t smem = (size_t)(G * K * L * A_STRIDE + NW * SCRATCH_WORDS) * 4;
+    constexpr size_t smem = item_smem_bytes<K, L, G, NTT_IN, false>();
     static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
     if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(smem), configured); e != cudaSuccess) return e;
     constexpr int threads = NW * 32;
@@ -375,7 +424,7 @@ static cudaError_t launch_verify_item_t(int32_t* w, const uint8_t* rho, const in
     constexpr int G = item_group<K, L>();
     constexpr int NW = (G * K * L + 31) / 32;
     auto kern = matvec_item_kernel<K, L, G, true, true, true>;
-    constexpr size_t smem = (size_t)(G * K * L * A_STRIDE + NW * SCRATCH_WORDS) * 4;
+    constexpr size_t smem = item_smem_bytes<K, L, G, true, true>();
     static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
     if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(smem), configured); e != cudaSuccess) return e;
     kern<<<(unsigned)((batch + G - 1) / G), NW * 32, smem, st>>>(w, rho, v, (uint32_t)batch, extra);
