@@ -33,4 +33,12 @@ assert vk.verify(msgs, z, h, c).all()
 zp, hp, cp, ap = sk.sign(msgs, pinned=True)
 assert np.array_equal(z, zp) and np.array_equal(h, hp) and np.array_equal(c, cp) and np.array_equal(att, ap)
 keys = eng.keygen(2, np.arange(64 * 32, dtype=np.uint8).reshape(64, 32))
+# level 5: per-item-rho kernel with the two-warp split core (key generation and per-key verification use it)
+K5 = ol.kat(5)
+keys5 = eng.keygen(5, np.arange(16 * 32, dtype=np.uint8).reshape(16, 32))
+sk5 = d.SignKey(eng, 5, K5["rho"][0], K5["k"][0], K5["tr"][0], K5["s1"][0], K5["s2"][0], K5["t0"][0])
+m5 = msgs[:16]
+z5, h5, c5, _ = sk5.sign(m5)
+ok5 = eng.verify_multi(5, np.repeat(K5["rho"][:1], 16, axis=0), np.repeat(K5["t1"][:1], 16, axis=0), m5, z5, h5, c5)
+assert ok5.all()
 print("tour ok", eng.launch_count)
