@@ -385,7 +385,19 @@ int dil_sign_batch_dev(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* d_msgs
     std::lock_guard<std::mutex> g(k->mu);
     DeviceGuard dg(e->device);
     if (!dg.ok) return DIL_ERR_CUDA;
-    return sign_rounds(e, k, d_msgs, d_offsets, n, d_z, d_h, d_ctilde, d_attempts, (cudaStream_t)stream);
+    // very large batches are signed in 2^20-message pieces so that the per-attempt workspace (about
+    // 9.5 / 13 / 17 KB per message at levels 2 / 3 / 5) stays bounded; DIL_SIGN_DEV_CHUNK overrides (tests)
+    const char* ev = std::getenv("DIL_SIGN_DEV_CHUNK");
+    const size_t chunk = ev && std::atol(ev) > 0 ? (size_t)std::atol(ev) : ((size_t)1 << 20);
+    const size_t zb = (size_t)k->P.l * k->P.z_bytes, hb = (size_t)k->P.omega + k->P.k;
+    for (size_t lo = 0; lo < n;) {
+        const size_t m = n - lo <= chunk + chunk / 4 ? n - lo : chunk;
+        int rc = sign_rounds(e, k, d_msgs, d_offsets + lo, m, d_z + lo * zb, d_h + lo * hb, d_ctilde + lo * 32, d_attempts + lo,
+                             (cudaStream_t)stream);
+        if (rc) return rc;
+        lo += m;
+    }
+    return DIL_OK;
 }
 
 int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs, const uint64_t* offsets, size_t n,

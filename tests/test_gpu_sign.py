@@ -88,3 +88,29 @@ def test_sign_streaming_host_path(eng, monkeypatch):
             assert np.array_equal(r, b), (level, n, name, "streaming, split batch")
             assert np.array_equal(r, c), (level, n, name, "pinned buffers, copy path")
         key.close()
+
+
+def test_sign_dev_split_batch(eng, monkeypatch):
+    """dil_sign_batch_dev signs very large batches in pieces (bounded workspace); with a small piece size the
+    result must equal the single-piece result bit for bit."""
+    import torch
+    import dilithium_b200 as d
+    level, n = 2, 9001
+    K = ol.kat(level)
+    key = d.SignKey(eng, level, K["rho"][2], K["k"][2], K["tr"][2], K["s1"][2], K["s2"][2], K["t0"][2])
+    msgs = torch.randint(0, 256, (n * 24,), dtype=torch.uint8, device="cuda")
+    off = torch.arange(n + 1, dtype=torch.int64, device="cuda") * 24
+    outs = []
+    for chunk in (None, "2048"):
+        if chunk:
+            monkeypatch.setenv("DIL_SIGN_DEV_CHUNK", chunk)
+        z = torch.zeros((n, key.z_bytes), dtype=torch.uint8, device="cuda"); h = torch.zeros((n, key.h_bytes), dtype=torch.uint8, device="cuda")
+        c = torch.zeros((n, 32), dtype=torch.uint8, device="cuda"); att = torch.zeros(n, dtype=torch.int32, device="cuda")
+        key.sign_dev(msgs, off, n, z, h, c, att)
+        torch.cuda.synchronize()
+        outs.append((z, h, c, att))
+    monkeypatch.delenv("DIL_SIGN_DEV_CHUNK")
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert int(outs[0][3].min()) >= 1
+    key.close()
