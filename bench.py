@@ -80,6 +80,12 @@ KECCAK_PEAK_GPS = 4.27   # G Keccak-f[1600]/s: pure-permutation micro-benchmark 
                          # profiles/r1b_keccak_pipe_bench.txt): the ALU-pipe speed of light for the hash kernels
 
 
+def class_kernel_name(kernel_class, level):
+    if kernel_class == "tail" and level == 3:   # eta = 4: the sparse products do not apply
+        return "sign_tail_kernel (NTT(c), c*s2 / c*s1 / c*t0 through transforms, norm checks, MakeHint, resolve)"
+    return CLASS_KERNEL[kernel_class]
+
+
 def keccak_roofline(kernel_class, level, slots, ms):
     """For the Keccak-bound classes: achieved permutations/s against the measured pure-Keccak peak."""
     k, l = LEVEL_DIMS[level]
@@ -394,7 +400,7 @@ def run_engine(args):
             "step_profile_ms": {n: round(ms, 4) for n, (ms, _) in prof.items()},
             "step_profile_note": f"device time per kernel class in one step (sum {prof_total:.3f} ms of {ms_step:.3f} ms wall); "
                                  "the rest is launch latency and one 4-byte D2H + stream sync per rejection round",
-            "roofline": {"kernel": CLASS_KERNEL[dominant], "class": dominant, "bound": "hbm", "achieved": dom_achieved, "peak": peak,
+            "roofline": {"kernel": class_kernel_name(dominant, level), "class": dominant, "bound": "hbm", "achieved": dom_achieved, "peak": peak,
                          "unit": "GB/s", "frac": dom_achieved / peak,
                          "traffic": (ncu_traffic(dominant) / 65536.0 * dom_units / max(rounds, 1)) if ncu_traffic(dominant) else None,
                          "traffic_note": "ncu dram bytes of a 65536-slot launch scaled to this step's average launch size",
