@@ -53,6 +53,8 @@ SIGNATURES = {
     "dil_sign_batch_host": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void]),
     "dil_sign_batch_dev": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void, c_void]),
     "dil_sign_last_rounds": (ctypes.c_uint32, [c_void]),
+    "dil_sign_last_slots": (ctypes.c_uint64, [c_void]),
+    "dil_sign_key_set_tuning": (c_int, [c_void, c_void]),
     "dil_sign_set_profile": (c_int, [c_void, c_int]),
     "dil_sign_get_profile": (c_int, [c_void, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
     "dil_verify_key_create": (c_int, [c_void, ctypes.POINTER(c_void), c_int, c_void, c_void]),

@@ -19,7 +19,7 @@ namespace {
 
 int fail_cuda(dil_engine* e, cudaError_t err, const char* what) {
     if (e) {
-        std::lock_guard<std::mutex> g(e->mu);
+        std::lock_guard<std::mutex> g(e->err_mu);
         e->last_error = std::string(what) + ": " + cudaGetErrorString(err);
     }
     return DIL_ERR_CUDA;
@@ -51,6 +51,7 @@ int stage(dil_engine* e, int slot, size_t bytes, void** out) {
         e->staging_bytes[slot] = 0;
         cudaError_t err = cudaMalloc(&e->staging[slot], bytes);
         if (err != cudaSuccess) {
+            std::lock_guard<std::mutex> g(e->err_mu);
             e->last_error = std::string("cudaMalloc staging: ") + cudaGetErrorString(err);
             return DIL_ERR_ALLOC;
         }
@@ -93,6 +94,7 @@ int dil_engine_destroy(dil_engine_t* e) {
         DeviceGuard g(e->device);
         for (auto& p : e->staging)
             if (p) cudaFree(p);
+        if (e->arena_done) cudaEventDestroy(e->arena_done);
         if (e->host_stream) cudaStreamDestroy(e->host_stream);
         if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     }
@@ -111,7 +113,14 @@ const char* dil_status_string(int status) {
         default: return "unknown status";
     }
 }
-const char* dil_last_error(const dil_engine_t* e) { return e ? e->last_error.c_str() : ""; }
+const char* dil_last_error(const dil_engine_t* e) {
+    // a per-thread copy: the engine's string may be rewritten by a failing call on another thread
+    static thread_local std::string copy;
+    if (!e) return "";
+    std::lock_guard<std::mutex> g(const_cast<dil_engine*>(e)->err_mu);
+    copy = e->last_error;
+    return copy.c_str();
+}
 int dil_engine_device(const dil_engine_t* e) { return e ? e->device : -1; }
 int dil_engine_sm_count(const dil_engine_t* e) { return e ? e->sm_count : 0; }
 uint64_t dil_engine_launch_count(const dil_engine_t* e) { return e ? e->launches.load() : 0; }
@@ -213,7 +222,8 @@ int dil_polyvec_matrix_pointwise_dev(dil_engine_t* e, int32_t* w, const int32_t*
 #define D2H(dst, src, bytes) \
     if ((err = cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail_cuda_locked(e, err, "D2H")
 
-static int fail_cuda_locked(dil_engine* e, cudaError_t err, const char* what) {
+static int fail_cuda_locked(dil_engine* e, cudaError_t err, const char* what) {   // caller holds e->mu (not err_mu)
+    std::lock_guard<std::mutex> g(e->err_mu);
     e->last_error = std::string(what) + ": " + cudaGetErrorString(err);
     return DIL_ERR_CUDA;
 }

@@ -11,11 +11,13 @@ struct dil_engine {
     int device = -1;
     int sm_count = 0;
     std::atomic<uint64_t> launches{0};
-    std::mutex mu;           // guards staging + last_error
+    std::mutex mu;           // guards staging (host-pointer calls serialise on it)
+    std::mutex err_mu;       // guards last_error (set from any entry point, whichever lock it holds)
     void* staging[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t staging_bytes[4] = {0, 0, 0, 0};
     cudaStream_t host_stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // D2H of finished chunks overlaps compute of the next chunk
+    cudaEvent_t arena_done = nullptr;     // recorded after the last kernel that uses staging[3] (multi-key verification arena)
     std::string last_error;
 };
 

@@ -25,6 +25,29 @@ inline cudaError_t ensure_dyn_smem(Kern kern, size_t smem, std::atomic<uint64_t>
 
 enum class EwOp : int { MUL = 0, MULACC = 1, ADD = 2, SUB = 3 };
 
+// Device-resident state of the rejection-round loop of one signing batch.  The host enqueues whole rounds ahead of
+// time without knowing how many items are still active: every kernel of a round reads the round's size from here,
+// plan_kernel (the last launch of a round) turns the re-queued items into the next round, and launches of a round
+// that finds nothing left exit at once.  combined_top.v:2217-2228 restarts ONE signature with the next kappa; this
+// is that loop for a whole batch, kept on the device.
+struct RoundCtl {
+    uint32_t n_active;     // items of the current round                       (written between rounds only)
+    uint32_t spec;         // speculative attempt slots per item, >= 1
+    uint32_t n_slots;      // n_active * spec
+    uint32_t cur;          // which of the two active lists holds the current round's items
+    uint32_t next_count;   // items re-queued for the next round so far        (atomic, during a round)
+    uint32_t ctr_core;     // work counter of the sign core                    (atomic)
+    uint32_t ctr_tail;     // work counter of the tail                         (atomic)
+    uint32_t done;         // finished items of the batch = length of the completion-ordered done list (atomic)
+    uint32_t rounds;       // rounds that had work
+    uint32_t total_slots;  // attempt slots processed so far
+    uint32_t slot_cap;     // slot capacity of the workspace for this batch    (policy constants)
+    uint32_t spec_target;  // once fewer items remain, a round is filled up to this many slots ...
+    uint32_t spec_max;     // ... with at most this many slots per item
+    uint32_t pad[3];
+    uint32_t done_snap[64];   // `done` at the end of round r (index r mod 64): what the host path's drain of round r may copy
+};
+
 cudaError_t launch_ntt_fwd(int32_t* dst, const int32_t* src, size_t n_polys, int sm_count, cudaStream_t st);
 cudaError_t launch_ntt_inv(int32_t* dst, const int32_t* src, size_t n_polys, int sm_count, cudaStream_t st);
 cudaError_t launch_elementwise(EwOp op, int32_t* c, const int32_t* a, const int32_t* b, size_t n_polys, int sm_count,
@@ -34,43 +57,45 @@ cudaError_t launch_matvec(int32_t* w, const int32_t* a_hat, const int32_t* v, in
 cudaError_t launch_expand_a(int32_t* a_hat, const uint8_t* rho, size_t n_rho, int k, int l, int sm_count, cudaStream_t st);
 cudaError_t launch_matvec_expand(int32_t* w, const uint8_t* rho, const int32_t* v, int k, int l, size_t batch,
                                  unsigned flags, int sm_count, cudaStream_t st);
+// batch_dev != nullptr: the number of items is read from device memory (round loop); `batch` then only sizes the grid
 cudaError_t launch_signcore(int32_t* w, const int32_t* a_hat, const int32_t* y, int k, int l, size_t batch, int sm_count,
-                            cudaStream_t st, uint32_t* work_ctr = nullptr, uint8_t* w1p = nullptr);
+                            cudaStream_t st, uint32_t* work_ctr = nullptr, uint8_t* w1p = nullptr,
+                            const uint32_t* batch_dev = nullptr);
 
 // ---- sign pipeline (sign_kernels.cu) ----
-cudaError_t launch_sign_init(uint64_t* mu, uint64_t* rhop, uint16_t* kappa, const uint8_t* tr, const uint8_t* key,
-                             const uint8_t* msgs, const uint64_t* offsets, uint32_t n, cudaStream_t st);
-cudaError_t launch_expand_mask(int level, int32_t* y, const uint64_t* rhop, const uint16_t* kappa, const uint32_t* active,
-                               uint32_t n_slots, uint32_t spec, cudaStream_t st);
-cudaError_t launch_pack_w1(int level, uint32_t* w1p, const int32_t* w, uint32_t n_slots, cudaStream_t st);
-cudaError_t launch_challenge(int level, int8_t* c, uint64_t* ct_slot, const uint64_t* mu, const uint64_t* w1p,
-                             const uint32_t* active, uint32_t n_slots, uint32_t spec, cudaStream_t st);
-// Outputs and queues of the resolve step, handed to the tail kernel in rounds with one slot per item: the tail
-// then finishes (packs the signature) or re-queues its item itself and launch_resolve is skipped.
-struct TailResolve {
-    uint8_t* zp;
-    uint8_t* h_out;
-    uint64_t* ct_out;
+// Buffers of one signing batch that the round kernels share (all device pointers).
+struct SignBufs {
+    RoundCtl* ctl;
+    uint32_t* active[2];       // item lists of the current / next round
+    uint32_t* done_list;       // finished items in completion order
+    uint64_t *mu, *rhop;       // per item: mu[8], rho'[8]
+    uint16_t* kappa;           // per item: next attempt number
+    int32_t *y, *w;            // per slot: l / k polynomials
+    uint64_t* w1p;             // per slot: packed HighBits(w)
+    int8_t* c;                 // per slot: challenge polynomial
+    uint64_t* ct_slot;         // per slot: c~
+    uint8_t *h_slot, *accepted;
+    uint8_t *zp, *h_out;       // per item outputs: packed z, hint bytes
+    uint64_t* ct_out;          //                   c~
     uint32_t* attempts;
-    uint16_t* kappa;
-    uint32_t* next_active;
-    uint32_t* next_count;
-    const uint64_t* ct_slot;
-    const uint32_t* active;
-    uint32_t* done_list;
+    bool track_done;           // host path: record completion order for the per-round drain
 };
-cudaError_t launch_sign_tail(int level, int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat,
-                             int32_t* w, const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st,
-                             uint32_t* work_ctr = nullptr, const TailResolve* fused = nullptr, const int8_t* key_small = nullptr);
-cudaError_t launch_resolve(int level, uint8_t* zp, uint8_t* h_out, uint64_t* ct_out, uint32_t* attempts, uint16_t* kappa,
-                           uint32_t* next_active, uint32_t* next_count, const int32_t* zslot, const uint8_t* h_slot,
-                           const uint64_t* ct_slot, const uint8_t* accepted, const uint32_t* active, uint32_t n_items,
-                           uint32_t spec, uint32_t* done_list, cudaStream_t st);
-cudaError_t launch_drain(uint8_t* hz, uint8_t* hh, uint8_t* hct, uint32_t* hatt, const uint8_t* zp, const uint8_t* h,
-                         const uint8_t* ct, const uint32_t* att, const uint32_t* list, uint32_t n, uint32_t zb, uint32_t hb,
-                         cudaStream_t st);
-cudaError_t launch_iota(uint32_t* dst, uint32_t n, cudaStream_t st);
-cudaError_t launch_publish_count(uint32_t* host_dst_dev, const uint32_t* src, cudaStream_t st);
+cudaError_t launch_sign_begin(const SignBufs& b, uint32_t n, uint32_t slot_cap, uint32_t spec_target, uint32_t spec_max, cudaStream_t st);
+cudaError_t launch_sign_init(uint64_t* mu, uint64_t* rhop, uint16_t* kappa, const uint8_t* tr, const uint8_t* key, size_t key_stride,
+                             const uint8_t* msgs, const uint64_t* offsets, uint32_t n, cudaStream_t st);
+// cap_slots / cap_items bound the round's size (the kernels read the real size from b.ctl) and size the grids
+cudaError_t launch_expand_mask(int level, const SignBufs& b, uint32_t cap_slots, cudaStream_t st);
+// ExpandMask + sign core in one kernel (mask_core.cu): y, w and the packed HighBits(w) of every slot of the round
+cudaError_t launch_mask_core(int level, const SignBufs& b, const int32_t* a_hat, uint32_t cap_slots, int sm_count, cudaStream_t st);
+cudaError_t launch_challenge(int level, const SignBufs& b, uint32_t cap_slots, cudaStream_t st);
+cudaError_t launch_sign_tail(int level, const SignBufs& b, const int32_t* key_hat, const int8_t* key_small, uint32_t cap_slots,
+                             int sm_count, cudaStream_t st);
+cudaError_t launch_resolve(int level, const SignBufs& b, uint32_t cap_items, cudaStream_t st);
+cudaError_t launch_plan(RoundCtl* ctl, uint32_t round, cudaStream_t st);
+// copies round `round`'s finished signatures (done list entries [done_snap[round-1], done_snap[round])) to the host
+cudaError_t launch_drain(uint8_t* hz, uint8_t* hh, uint8_t* hct, uint32_t* hatt, const SignBufs& b, uint32_t round, uint32_t zb,
+                         uint32_t hb, cudaStream_t st);
+cudaError_t launch_publish_ctl(uint32_t* host_dst_dev, const RoundCtl* ctl, cudaStream_t st);
 // ---- verify pipeline ----
 cudaError_t launch_verify_core(int32_t* w, const int32_t* a_ext, const int32_t* v, int level, size_t batch, int sm_count,
                                cudaStream_t st);

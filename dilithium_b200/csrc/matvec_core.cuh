@@ -1,0 +1,172 @@
+// matvec_core.cuh - the per-item core shared by the fused kernels: w = [INTT] ( A_hat * v_hat ) for one item, executed
+// by one warp with A_hat in shared memory (matvec_kernels.cu: sign / verify / keygen cores; mask_core.cu: the signing
+// core with ExpandMask fused in front).  MULT_A_Y -> NTTI_W of rtl_src/combined_top.v:1875-1933.
+#pragma once
+#include "ntt_core.cuh"
+#include "rounding.cuh"
+
+namespace dil {
+
+constexpr int A_STRIDE = 260;  // words per A polynomial in shared memory (pad 4: spreads the
+                               // sampler's same-index stores over 8 bank groups, keeps 16-B alignment)
+
+#ifdef __CUDACC__
+
+// Rows [i_begin, i_end) of the product for one item whose NTT-domain inputs yh are already in registers (layout C).
+// a_sm: k*l polynomials in shared memory (stride A_STRIDE), pre-multiplied by 256^-1 when INTT_OUT.
+// EXTRA: the last input is multiplied by a per-item column extra_item[i] from global memory instead of a matrix column.
+// W1: also emit w1 = HighBits(w), bit-packed as encoder.v:96-133 (6 bits for gamma2 = (Q-1)/88, i.e. K = 4, else 4 bits).
+template <int K, int LA, bool INTT_OUT, bool EXTRA, bool W1>
+__device__ __forceinline__ void item_rows(int32_t* __restrict__ w_item, const uint32_t (&yh)[LA + (EXTRA ? 1 : 0)][8],
+                                          const uint32_t* __restrict__ a_sm, uint32_t* __restrict__ scr, int lane,
+                                          const int32_t* __restrict__ extra_item, uint8_t* __restrict__ w1_item, int i_begin,
+                                          int i_end) {
+    constexpr int L = LA + (EXTRA ? 1 : 0);
+#pragma unroll 1
+    for (int i = i_begin; i < i_end; i++) {
+        uint64_t acc[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) acc[r] = 0;
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            uint4 lo, hi;
+            if (EXTRA && j == LA) {
+                const int4* ep = reinterpret_cast<const int4*>(extra_item + i * N) + lane;
+                int4 elo = __ldg(ep), ehi = __ldg(ep + 32);
+                auto sc = [](int32_t x) -> uint32_t { return INTT_OUT ? mul_full(canon_signed(x), INV256) : canon_signed(x); };
+                lo = make_uint4(sc(elo.x), sc(elo.y), sc(elo.z), sc(elo.w));
+                hi = make_uint4(sc(ehi.x), sc(ehi.y), sc(ehi.z), sc(ehi.w));
+            } else {
+                const uint4* ap = reinterpret_cast<const uint4*>(a_sm + (i * LA + j) * A_STRIDE) + lane;
+                lo = ap[0];
+                hi = ap[32];
+            }
+            acc[0] += (uint64_t)lo.x * yh[j][0]; acc[1] += (uint64_t)lo.y * yh[j][1];
+            acc[2] += (uint64_t)lo.z * yh[j][2]; acc[3] += (uint64_t)lo.w * yh[j][3];
+            acc[4] += (uint64_t)hi.x * yh[j][4]; acc[5] += (uint64_t)hi.y * yh[j][5];
+            acc[6] += (uint64_t)hi.z * yh[j][6]; acc[7] += (uint64_t)hi.w * yh[j][7];
+        }
+        uint32_t x[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) x[r] = reduce49(acc[r]);
+        if constexpr (INTT_OUT) {
+            InvTw itw;
+            {
+                const TwTable* tab = &TW_INV;
+                asm volatile("" : "+l"(tab));
+                load_inv_tw(itw, tab, lane);
+            }
+            ntt_inv_warp<true>(x, scr, itw, lane);   // a_sm carries the 256^-1 factor
+            __syncwarp();
+            int32_t* o = w_item + i * N + lane;
+#pragma unroll
+            for (int r = 0; r < 8; r++) o[32 * r] = (int32_t)x[r];
+            if constexpr (W1) {
+                static_assert(INTT_OUT, "w1 is defined on the time-domain w");
+                constexpr int32_t G2 = K == 4 ? (Q_I - 1) / 88 : (Q_I - 1) / 32;
+                // this lane holds coefficients lane + 32 r: stage HighBits as bytes, re-read 8 consecutive ones
+                uint8_t* sb = reinterpret_cast<uint8_t*>(scr);
+#pragma unroll
+                for (int r = 0; r < 8; r++) sb[32 * r + lane] = (uint8_t)highbits<G2>(x[r]);
+                __syncwarp();
+                const uint2 q = reinterpret_cast<const uint2*>(sb)[lane];
+                if constexpr (G2 == (Q_I - 1) / 32) {
+                    auto p4 = [](uint32_t v) { return (v & 0xFu) | ((v >> 4) & 0xF0u) | ((v >> 8) & 0xF00u) | ((v >> 12) & 0xF000u); };
+                    reinterpret_cast<uint32_t*>(w1_item + i * 128)[lane] = p4(q.x) | (p4(q.y) << 16);
+                } else {
+                    auto p6 = [](uint32_t v) { return (v & 0x3Fu) | ((v >> 2) & 0xFC0u) | ((v >> 4) & 0x3F000u) | ((v >> 6) & 0xFC0000u); };
+                    const uint32_t a = p6(q.x), b = p6(q.y);   // 24 bits each
+                    uint16_t* d = reinterpret_cast<uint16_t*>(w1_item + i * 192 + 6 * lane);
+                    d[0] = (uint16_t)a;
+                    d[1] = (uint16_t)((a >> 16) | (b << 8));
+                    d[2] = (uint16_t)(b >> 8);
+                }
+                __syncwarp();   // the scratch is reused by the next transform
+            }
+        } else {
+            int4* o = reinterpret_cast<int4*>(w_item + i * N) + lane;
+            o[0] = make_int4((int)x[0], (int)x[1], (int)x[2], (int)x[3]);
+            o[32] = make_int4((int)x[4], (int)x[5], (int)x[6], (int)x[7]);
+        }
+    }
+}
+
+// ---- per-item core, executed by one warp ----
+// v_item: l polys (global), w_item: k polys (global), a_sm: k*l polys in shared memory (stride A_STRIDE)
+// EXTRA = true (verification with per-item public keys): v_item holds L+1 polynomials, and the last one is
+// multiplied by a per-item column extra_item[i] read from global memory (-NTT(t1_i * 2^13)) instead of a
+// shared-memory matrix column.
+// W1 = true (signing): besides w the core also emits w1 = HighBits(w), bit-packed as encoder.v:96-133 (6 bits for
+// gamma2 = (Q-1)/88, i.e. K = 4, else 4 bits), into w1_item - the input of the challenge hash - so that no
+// separate pass has to read w again.
+// SPLIT = true (per-item kernel of level 5, two warps per item): both warps of the CTA call this together; warp
+// `part` transforms every second input and publishes it through yh_sm (layout C), and computes rows
+// [part*K/2, (part+1)*K/2) of the result - the single-warp latency of the per-item core is halved.
+template <int K, int LA, bool NTT_IN, bool INTT_OUT, bool EXTRA = false, bool W1 = false, bool SPLIT = false>
+__device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const int32_t* __restrict__ v_item,
+                                          const uint32_t* __restrict__ a_sm, uint32_t* __restrict__ scr, int lane,
+                                          const int32_t* __restrict__ extra_item = nullptr,
+                                          uint8_t* __restrict__ w1_item = nullptr, uint32_t* __restrict__ yh_sm = nullptr,
+                                          int part = 0) {
+    constexpr int L = LA + (EXTRA ? 1 : 0);   // number of input polynomials
+    uint32_t yh[L][8];  // NTT-domain inputs in layout C
+    if constexpr (NTT_IN && SPLIT) {
+        FwdTw ftw;
+        {
+            const TwTable* tab = &TW_FWD;
+            asm volatile("" : "+l"(tab));
+            load_fwd_tw(ftw, tab, lane);
+        }
+#pragma unroll 1
+        for (int j = part; j < L; j += 2) {
+            uint32_t x[8];
+            const int32_t* p = v_item + j * N + lane;
+#pragma unroll
+            for (int r = 0; r < 8; r++) x[r] = (uint32_t)p[32 * r];
+            ntt_fwd_warp(x, scr, ftw, lane);
+            __syncwarp();
+            uint4* o = reinterpret_cast<uint4*>(yh_sm + j * N) + lane;
+            o[0] = make_uint4(x[0], x[1], x[2], x[3]);
+            o[32] = make_uint4(x[4], x[5], x[6], x[7]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            const uint4* q = reinterpret_cast<const uint4*>(yh_sm + j * N) + lane;
+            const uint4 lo = q[0], hi = q[32];
+            yh[j][0] = lo.x; yh[j][1] = lo.y; yh[j][2] = lo.z; yh[j][3] = lo.w;
+            yh[j][4] = hi.x; yh[j][5] = hi.y; yh[j][6] = hi.z; yh[j][7] = hi.w;
+        }
+    } else if constexpr (NTT_IN) {
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            const int32_t* p = v_item + j * N + lane;
+#pragma unroll
+            for (int r = 0; r < 8; r++) yh[j][r] = (uint32_t)p[32 * r];  // layout A: 128-B line per access
+        }
+        FwdTw ftw;
+        {   // 2 KiB table, L1 resident; reloaded per item (opaque pointer defeats hoisting) to keep registers low
+            const TwTable* tab = &TW_FWD;
+            asm volatile("" : "+l"(tab));
+            load_fwd_tw(ftw, tab, lane);
+        }
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            ntt_fwd_warp(yh[j], scr, ftw, lane);
+            __syncwarp();
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            const int4* p = reinterpret_cast<const int4*>(v_item + j * N) + lane;
+            int4 lo = p[0], hi = p[32];
+            yh[j][0] = canon_signed(lo.x); yh[j][1] = canon_signed(lo.y); yh[j][2] = canon_signed(lo.z); yh[j][3] = canon_signed(lo.w);
+            yh[j][4] = canon_signed(hi.x); yh[j][5] = canon_signed(hi.y); yh[j][6] = canon_signed(hi.z); yh[j][7] = canon_signed(hi.w);
+        }
+    }
+    const int i_begin = SPLIT ? part * (K / 2) : 0, i_end = SPLIT ? (part + 1) * (K / 2) : K;
+    item_rows<K, LA, INTT_OUT, EXTRA, W1>(w_item, yh, a_sm, scr, lane, extra_item, w1_item, i_begin, i_end);
+}
+
+#endif  // __CUDACC__
+}  // namespace dil

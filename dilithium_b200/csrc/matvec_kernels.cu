@@ -14,18 +14,12 @@
 // HBM traffic per item is (l + k) KiB (+32 B of rho); A never touches HBM.
 #include <cuda_runtime.h>
 
-#include <cstdlib>
-
 #include "dilithium_b200.h"
 #include "keccak.cuh"
 #include "kernels.h"
-#include "ntt_core.cuh"
-#include "rounding.cuh"
+#include "matvec_core.cuh"
 
 namespace dil {
-
-constexpr int A_STRIDE = 260;  // words per A polynomial in shared memory (pad 4: spreads the
-                               // sampler's same-index stores over 8 bank groups, keeps 16-B alignment)
 
 // ---- materialising ExpandA (keys, tests): one thread per polynomial ----
 __global__ void __launch_bounds__(64) expand_a_kernel(int32_t* __restrict__ a_hat, const uint8_t* __restrict__ rho,
@@ -47,149 +41,6 @@ cudaError_t launch_expand_a(int32_t* a_hat, const uint8_t* rho, size_t n_rho, in
     return cudaGetLastError();
 }
 
-// ---- per-item core, executed by one warp ----
-// v_item: l polys (global), w_item: k polys (global), a_sm: k*l polys in shared memory (stride A_STRIDE)
-// EXTRA = true (verification with per-item public keys): v_item holds L+1 polynomials, and the last one is
-// multiplied by a per-item column extra_item[i] read from global memory (-NTT(t1_i * 2^13)) instead of a
-// shared-memory matrix column.
-// W1 = true (signing): besides w the core also emits w1 = HighBits(w), bit-packed as encoder.v:96-133 (6 bits for
-// gamma2 = (Q-1)/88, i.e. K = 4, else 4 bits), into w1_item - the input of the challenge hash - so that no
-// separate pass has to read w again.
-// SPLIT = true (per-item kernel of level 5, two warps per item): both warps of the CTA call this together; warp
-// `part` transforms every second input and publishes it through yh_sm (layout C), and computes rows
-// [part*K/2, (part+1)*K/2) of the result - the single-warp latency of the per-item core is halved.
-template <int K, int LA, bool NTT_IN, bool INTT_OUT, bool EXTRA = false, bool W1 = false, bool SPLIT = false>
-__device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const int32_t* __restrict__ v_item,
-                                          const uint32_t* __restrict__ a_sm, uint32_t* __restrict__ scr, int lane,
-                                          const int32_t* __restrict__ extra_item = nullptr,
-                                          uint8_t* __restrict__ w1_item = nullptr, uint32_t* __restrict__ yh_sm = nullptr,
-                                          int part = 0) {
-    constexpr int L = LA + (EXTRA ? 1 : 0);   // number of input polynomials
-    uint32_t yh[L][8];  // NTT-domain inputs in layout C
-    if constexpr (NTT_IN && SPLIT) {
-        FwdTw ftw;
-        {
-            const TwTable* tab = &TW_FWD;
-            asm volatile("" : "+l"(tab));
-            load_fwd_tw(ftw, tab, lane);
-        }
-#pragma unroll 1
-        for (int j = part; j < L; j += 2) {
-            uint32_t x[8];
-            const int32_t* p = v_item + j * N + lane;
-#pragma unroll
-            for (int r = 0; r < 8; r++) x[r] = (uint32_t)p[32 * r];
-            ntt_fwd_warp(x, scr, ftw, lane);
-            __syncwarp();
-            uint4* o = reinterpret_cast<uint4*>(yh_sm + j * N) + lane;
-            o[0] = make_uint4(x[0], x[1], x[2], x[3]);
-            o[32] = make_uint4(x[4], x[5], x[6], x[7]);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < L; j++) {
-            const uint4* q = reinterpret_cast<const uint4*>(yh_sm + j * N) + lane;
-            const uint4 lo = q[0], hi = q[32];
-            yh[j][0] = lo.x; yh[j][1] = lo.y; yh[j][2] = lo.z; yh[j][3] = lo.w;
-            yh[j][4] = hi.x; yh[j][5] = hi.y; yh[j][6] = hi.z; yh[j][7] = hi.w;
-        }
-    } else if constexpr (NTT_IN) {
-#pragma unroll
-        for (int j = 0; j < L; j++) {
-            const int32_t* p = v_item + j * N + lane;
-#pragma unroll
-            for (int r = 0; r < 8; r++) yh[j][r] = (uint32_t)p[32 * r];  // layout A: 128-B line per access
-        }
-        FwdTw ftw;
-        {   // 2 KiB table, L1 resident; reloaded per item (opaque pointer defeats hoisting) to keep registers low
-            const TwTable* tab = &TW_FWD;
-            asm volatile("" : "+l"(tab));
-            load_fwd_tw(ftw, tab, lane);
-        }
-#pragma unroll
-        for (int j = 0; j < L; j++) {
-            ntt_fwd_warp(yh[j], scr, ftw, lane);
-            __syncwarp();
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < L; j++) {
-            const int4* p = reinterpret_cast<const int4*>(v_item + j * N) + lane;
-            int4 lo = p[0], hi = p[32];
-            yh[j][0] = canon_signed(lo.x); yh[j][1] = canon_signed(lo.y); yh[j][2] = canon_signed(lo.z); yh[j][3] = canon_signed(lo.w);
-            yh[j][4] = canon_signed(hi.x); yh[j][5] = canon_signed(hi.y); yh[j][6] = canon_signed(hi.z); yh[j][7] = canon_signed(hi.w);
-        }
-    }
-    const int i_begin = SPLIT ? part * (K / 2) : 0, i_end = SPLIT ? (part + 1) * (K / 2) : K;
-#pragma unroll 1
-    for (int i = i_begin; i < i_end; i++) {
-        uint64_t acc[8];
-#pragma unroll
-        for (int r = 0; r < 8; r++) acc[r] = 0;
-#pragma unroll
-        for (int j = 0; j < L; j++) {
-            uint4 lo, hi;
-            if (EXTRA && j == LA) {
-                const int4* ep = reinterpret_cast<const int4*>(extra_item + i * N) + lane;
-                int4 elo = __ldg(ep), ehi = __ldg(ep + 32);
-                auto sc = [](int32_t x) -> uint32_t { return INTT_OUT ? mul_full(canon_signed(x), INV256) : canon_signed(x); };
-                lo = make_uint4(sc(elo.x), sc(elo.y), sc(elo.z), sc(elo.w));
-                hi = make_uint4(sc(ehi.x), sc(ehi.y), sc(ehi.z), sc(ehi.w));
-            } else {
-                const uint4* ap = reinterpret_cast<const uint4*>(a_sm + (i * LA + j) * A_STRIDE) + lane;
-                lo = ap[0];
-                hi = ap[32];
-            }
-            acc[0] += (uint64_t)lo.x * yh[j][0]; acc[1] += (uint64_t)lo.y * yh[j][1];
-            acc[2] += (uint64_t)lo.z * yh[j][2]; acc[3] += (uint64_t)lo.w * yh[j][3];
-            acc[4] += (uint64_t)hi.x * yh[j][4]; acc[5] += (uint64_t)hi.y * yh[j][5];
-            acc[6] += (uint64_t)hi.z * yh[j][6]; acc[7] += (uint64_t)hi.w * yh[j][7];
-        }
-        uint32_t x[8];
-#pragma unroll
-        for (int r = 0; r < 8; r++) x[r] = reduce49(acc[r]);
-        if constexpr (INTT_OUT) {
-            InvTw itw;
-            {
-                const TwTable* tab = &TW_INV;
-                asm volatile("" : "+l"(tab));
-                load_inv_tw(itw, tab, lane);
-            }
-            ntt_inv_warp<true>(x, scr, itw, lane);   // a_sm carries the 256^-1 factor
-            __syncwarp();
-            int32_t* o = w_item + i * N + lane;
-#pragma unroll
-            for (int r = 0; r < 8; r++) o[32 * r] = (int32_t)x[r];
-            if constexpr (W1) {
-                static_assert(INTT_OUT, "w1 is defined on the time-domain w");
-                constexpr int32_t G2 = K == 4 ? (Q_I - 1) / 88 : (Q_I - 1) / 32;
-                // this lane holds coefficients lane + 32 r: stage HighBits as bytes, re-read 8 consecutive ones
-                uint8_t* sb = reinterpret_cast<uint8_t*>(scr);
-#pragma unroll
-                for (int r = 0; r < 8; r++) sb[32 * r + lane] = (uint8_t)highbits<G2>(x[r]);
-                __syncwarp();
-                const uint2 q = reinterpret_cast<const uint2*>(sb)[lane];
-                if constexpr (G2 == (Q_I - 1) / 32) {
-                    auto p4 = [](uint32_t v) { return (v & 0xFu) | ((v >> 4) & 0xF0u) | ((v >> 8) & 0xF00u) | ((v >> 12) & 0xF000u); };
-                    reinterpret_cast<uint32_t*>(w1_item + i * 128)[lane] = p4(q.x) | (p4(q.y) << 16);
-                } else {
-                    auto p6 = [](uint32_t v) { return (v & 0x3Fu) | ((v >> 2) & 0xFC0u) | ((v >> 4) & 0x3F000u) | ((v >> 6) & 0xFC0000u); };
-                    const uint32_t a = p6(q.x), b = p6(q.y);   // 24 bits each
-                    uint16_t* d = reinterpret_cast<uint16_t*>(w1_item + i * 192 + 6 * lane);
-                    d[0] = (uint16_t)a;
-                    d[1] = (uint16_t)((a >> 16) | (b << 8));
-                    d[2] = (uint16_t)(b >> 8);
-                }
-                __syncwarp();   // the scratch is reused by the next transform
-            }
-        } else {
-            int4* o = reinterpret_cast<int4*>(w_item + i * N) + lane;
-            o[0] = make_int4((int)x[0], (int)x[1], (int)x[2], (int)x[3]);
-            o[32] = make_int4((int)x[4], (int)x[5], (int)x[6], (int)x[7]);
-        }
-    }
-}
-
 // ---- shared-A persistent kernel ----
 // register budget: 2 CTAs/SM (<= 128 registers) for every level's shape, 1 for the 8 x 8 verification core.
 // (3 CTAs/SM at 80 registers was measured 5-9 % slower for levels 2/3: the kernel is bound by the
@@ -201,7 +52,9 @@ __global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L, WARPS)) matv
                                                                    const uint8_t* __restrict__ rho,
                                                                    const int32_t* __restrict__ v, uint32_t batch,
                                                                    uint32_t* __restrict__ work_ctr,
-                                                                   uint8_t* __restrict__ w1p = nullptr) {
+                                                                   uint8_t* __restrict__ w1p = nullptr,
+                                                                   const uint32_t* __restrict__ batch_dev = nullptr) {
+    if (batch_dev != nullptr) batch = *batch_dev;   // round loop of batched signing: the size lives on the device
     constexpr int W1_ROW = K * (K == 4 ? 192 : 128);   // packed w1 bytes per item
     extern __shared__ __align__(16) uint32_t smem_u32v[];
     uint32_t* a_sm = smem_u32v;                               // K*L*A_STRIDE
@@ -314,7 +167,8 @@ constexpr size_t shared_smem_bytes(int warps) {
 
 template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT, int MAX_CTAS = 8, bool W1 = false>
 static cudaError_t launch_shared_t(int32_t* w, const int32_t* a_hat, const uint8_t* rho, const int32_t* v, size_t batch,
-                                   int sm_count, cudaStream_t st, uint32_t* work_ctr = nullptr, uint8_t* w1p = nullptr) {
+                                   int sm_count, cudaStream_t st, uint32_t* work_ctr = nullptr, uint8_t* w1p = nullptr,
+                                   const uint32_t* batch_dev = nullptr) {
     auto kern = matvec_shared_kernel<K, L, WARPS, EXPAND, NTT_IN, INTT_OUT, W1>;
     constexpr size_t smem = shared_smem_bytes<K, L>(WARPS);
     static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
@@ -326,7 +180,7 @@ static cudaError_t launch_shared_t(int32_t* w, const int32_t* a_hat, const uint8
     size_t want = (batch + WARPS - 1) / WARPS;
     size_t cap = (size_t)sm_count * ctas_per_sm;
     unsigned grid = (unsigned)(want < cap ? want : cap);
-    kern<<<grid, WARPS * 32, smem, st>>>(w, a_hat, rho, v, (uint32_t)batch, work_ctr, w1p);
+    kern<<<grid, WARPS * 32, smem, st>>>(w, a_hat, rho, v, (uint32_t)batch, work_ctr, w1p, batch_dev);
     return cudaGetLastError();
 }
 
@@ -335,16 +189,8 @@ static cudaError_t launch_shared_flags(int32_t* w, const int32_t* a_hat, const u
                                        bool ntt_in, bool intt_out, int sm_count, cudaStream_t st,
                                        uint32_t* work_ctr = nullptr) {
     constexpr int WARPS = 8;
-    if (ntt_in && intt_out) {
-        // one 16-warp CTA per SM measured 3-5 % faster than two 8-warp CTAs (DIL_SC_WARPS=8 selects the latter)
-        static int big = -1;
-        if (big < 0) { const char* e = std::getenv("DIL_SC_WARPS"); big = (e && std::atoi(e) == 8) ? 0 : 1; }
-        static int half = -1;   // overlap experiment: one 8-warp CTA per SM (half an SM's registers)
-        if (half < 0) { const char* e = std::getenv("DIL_SC_HALF"); half = (e && std::atoi(e)) ? 1 : 0; }
-        if (half) return launch_shared_t<K, L, 8, EXPAND, true, true, 1>(w, a_hat, rho, v, batch, sm_count, st, work_ctr);
-        if (big) return launch_shared_t<K, L, 16, EXPAND, true, true>(w, a_hat, rho, v, batch, sm_count, st, work_ctr);
-        return launch_shared_t<K, L, WARPS, EXPAND, true, true>(w, a_hat, rho, v, batch, sm_count, st, work_ctr);
-    }
+    // one 16-warp CTA per SM measured 3-5 % faster than two 8-warp CTAs for the fully fused shape
+    if (ntt_in && intt_out) return launch_shared_t<K, L, 16, EXPAND, true, true>(w, a_hat, rho, v, batch, sm_count, st, work_ctr);
     if (ntt_in) return launch_shared_t<K, L, WARPS, EXPAND, true, false>(w, a_hat, rho, v, batch, sm_count, st);
     if (intt_out) return launch_shared_t<K, L, WARPS, EXPAND, false, true>(w, a_hat, rho, v, batch, sm_count, st);
     return launch_shared_t<K, L, WARPS, EXPAND, false, false>(w, a_hat, rho, v, batch, sm_count, st);
@@ -388,31 +234,21 @@ cudaError_t launch_matvec_expand(int32_t* w, const uint8_t* rho, const int32_t* 
     return cudaErrorInvalidValue;
 }
 
-// w1p != nullptr: also emit the packed w1 = HighBits(w) per item (signing); done inside the core by the default
-// 16-warp kernel, by a separate pack_w1 pass for the experiment shapes selected with DIL_SC_WARPS / DIL_SC_HALF / DIL_W1_FUSED=0
+// w1p != nullptr: also emit the packed w1 = HighBits(w) per item (signing)
 template <int K, int L>
 static cudaError_t launch_signcore_t(int32_t* w, const int32_t* a_hat, const int32_t* y, size_t batch, int sm_count, cudaStream_t st,
-                                     uint32_t* work_ctr, uint8_t* w1p, int level) {
-    static int fused = -1;
-    if (fused < 0) {
-        const char* e = std::getenv("DIL_W1_FUSED");
-        const char* a = std::getenv("DIL_SC_WARPS");
-        const char* b = std::getenv("DIL_SC_HALF");
-        fused = !(e && std::atoi(e) == 0) && !(a && std::atoi(a) == 8) && !(b && std::atoi(b));
-    }
-    if (w1p != nullptr && fused)
-        return launch_shared_t<K, L, 16, false, true, true, 8, true>(w, a_hat, nullptr, y, batch, sm_count, st, work_ctr, w1p);
-    cudaError_t e = launch_shared_flags<K, L, false>(w, a_hat, nullptr, y, batch, true, true, sm_count, st, work_ctr);
-    if (e != cudaSuccess || w1p == nullptr) return e;
-    return launch_pack_w1(level, reinterpret_cast<uint32_t*>(w1p), w, (uint32_t)batch, st);
+                                     uint32_t* work_ctr, uint8_t* w1p, const uint32_t* batch_dev) {
+    if (w1p != nullptr)
+        return launch_shared_t<K, L, 16, false, true, true, 8, true>(w, a_hat, nullptr, y, batch, sm_count, st, work_ctr, w1p, batch_dev);
+    return launch_shared_t<K, L, 16, false, true, true>(w, a_hat, nullptr, y, batch, sm_count, st, work_ctr, nullptr, batch_dev);
 }
 
 cudaError_t launch_signcore(int32_t* w, const int32_t* a_hat, const int32_t* y, int k, int l, size_t batch, int sm_count,
-                            cudaStream_t st, uint32_t* work_ctr, uint8_t* w1p) {
+                            cudaStream_t st, uint32_t* work_ctr, uint8_t* w1p, const uint32_t* batch_dev) {
     if (batch == 0) return cudaSuccess;
-    if (k == 4 && l == 4) return launch_signcore_t<4, 4>(w, a_hat, y, batch, sm_count, st, work_ctr, w1p, 2);
-    if (k == 6 && l == 5) return launch_signcore_t<6, 5>(w, a_hat, y, batch, sm_count, st, work_ctr, w1p, 3);
-    if (k == 8 && l == 7) return launch_signcore_t<8, 7>(w, a_hat, y, batch, sm_count, st, work_ctr, w1p, 5);
+    if (k == 4 && l == 4) return launch_signcore_t<4, 4>(w, a_hat, y, batch, sm_count, st, work_ctr, w1p, batch_dev);
+    if (k == 6 && l == 5) return launch_signcore_t<6, 5>(w, a_hat, y, batch, sm_count, st, work_ctr, w1p, batch_dev);
+    if (k == 8 && l == 7) return launch_signcore_t<8, 7>(w, a_hat, y, batch, sm_count, st, work_ctr, w1p, batch_dev);
     return cudaErrorInvalidValue;
 }
 

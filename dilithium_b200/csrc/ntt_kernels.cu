@@ -250,12 +250,11 @@ static cudaError_t launch_ntt_cfg(int32_t* dst, const int32_t* src, size_t n_pol
     return cudaGetLastError();
 }
 
-static int ntt_cfg() {
-    static int cfg = -1;
-    if (cfg < 0) {
+static int ntt_cfg() {   // development knob, read once (thread-safe static initialisation)
+    static const int cfg = [] {
         const char* e = std::getenv("DIL_NTT_CFG");
-        cfg = e ? std::atoi(e) : 0;
-    }
+        return e ? std::atoi(e) : 0;
+    }();
     return cfg;
 }
 

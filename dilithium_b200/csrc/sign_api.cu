@@ -3,10 +3,13 @@
 // I/O order of rtl_tb/tb_sign_top.v:171-335 (inputs rho, mlen, tr, M, K, s1, s2, t0; outputs z,
 // h, c~).  Key material is expanded once per key (ExpandA + NTT of s1, s2, t0: the LOAD_RHO /
 // NTT_S1 / NTT_S2 / NTT_T0 states, combined_top.v:1560-1767); each round then runs
-// ExpandMask -> fused sign core -> w1 pack -> challenge -> tail over the active items.
+// ExpandMask -> fused sign core (+ w1 pack) -> challenge -> tail (-> resolve) over the active items.
+// The rejection loop itself lives on the device (RoundCtl, kernels.h): the host enqueues rounds ahead
+// of time and looks at the state once per burst of rounds.
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,27 +30,31 @@ struct dil_sign_key {
     int32_t* a_hat = nullptr;    // k*l polys
     int32_t* key_hat = nullptr;  // s1_hat (l) | s2_hat (k) | t0_hat (k)
     int8_t* key_small = nullptr; // s1 (l) | s2 (k) in the time domain, coefficients in [-eta, eta] (sparse c*s products)
-    uint8_t* seeds = nullptr;    // tr[32] | K[32]
+    uint8_t* seeds = nullptr;    // tr[32] | K[32] | rho[32]
     // workspace (grow-only, sized for `cap` items)
     std::mutex mu;
     size_t cap = 0;
     uint64_t *mu_d = nullptr, *rhop = nullptr, *w1p = nullptr;
     uint16_t* kappa = nullptr;
-    uint32_t *active[2] = {nullptr, nullptr}, *count = nullptr;   // [0] next round's size, [1] sign-core work counter, [2] tail work counter, [3] finished items
+    uint32_t* active[2] = {nullptr, nullptr};
+    dil::RoundCtl* ctl = nullptr;    // device-resident round state
     uint32_t* done_list = nullptr;   // finished items in completion order (host path: per-round drain)
     int32_t *y = nullptr, *w = nullptr;
     int8_t* c = nullptr;
     uint8_t *h_slot = nullptr, *accepted = nullptr;
     uint64_t* ct_slot = nullptr;
     size_t slots = 0;            // slot capacity of y/w/c/w1p/h_slot/ct_slot/accepted
-    uint32_t* count_host = nullptr;      // mapped pinned word the device publishes the next round's size into
-    uint32_t* count_host_dev = nullptr;  // its device alias
+    uint32_t* ctl_host = nullptr;      // mapped pinned copy of the first 16 words of the round state
+    uint32_t* ctl_host_dev = nullptr;  // its device alias
+    cudaEvent_t round_ev = nullptr;    // orders the copy stream's drains after the rounds they copy
     // host-variant staging
     uint8_t *msgs_d = nullptr, *zp_d = nullptr, *h_d = nullptr, *ct_d = nullptr;
     uint64_t* off_d = nullptr;
     uint32_t* att_d = nullptr;
     size_t msgs_cap = 0, out_cap = 0;
     uint32_t last_rounds = 0;
+    uint64_t last_slots = 0;
+    dil_sign_tuning tune{};      // zero = defaults
     // optional per-kernel-class device timing (CUDA events on the launching stream)
     bool profile = false;
     cudaEvent_t ev[16] = {};
@@ -58,8 +65,14 @@ struct dil_sign_key {
 namespace {
 
 int fail(dil_engine* e, cudaError_t err, const char* what) {
+    std::lock_guard<std::mutex> g(e->err_mu);
     e->last_error = std::string(what) + ": " + cudaGetErrorString(err);
     return DIL_ERR_CUDA;
+}
+int fail_msg(dil_engine* e, int status, const std::string& msg) {
+    std::lock_guard<std::mutex> g(e->err_mu);
+    e->last_error = msg;
+    return status;
 }
 #define CK(expr)                                                   \
     do {                                                           \
@@ -82,39 +95,50 @@ cudaError_t dmalloc(T** p, size_t count) {
     return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
 }
 
-// Straggler speculation: once fewer than SPEC_SLOT_TARGET items are still active the GPU is no
-// longer saturated by distinct items, so each remaining item tries up to SPEC_MAX consecutive kappa
-// values per round in parallel slots; the smallest accepted kappa wins, which is exactly the
-// sequential result of combined_top.v:2217-2228 (restart with the next kappa).
-constexpr size_t SPEC_SLOT_TARGET_DEFAULT = 32768;
-// at most one warp lane per speculative slot in resolve_kernel; DIL_SPEC_MAX overrides (tuning knob)
-static size_t spec_max() {
-    static size_t v = 0;
-    if (!v) {
-        const char* e = std::getenv("DIL_SPEC_MAX");
-        v = e && std::atol(e) > 0 && std::atol(e) <= 32 ? (size_t)std::atol(e) : 32;
-    }
-    return v;
+// secrets (s1, s2, t0, K, rho', y) never outlive their buffers: wipe, then free
+void wipe_free(void* p, size_t bytes) {
+    if (!p) return;
+    cudaMemset(p, 0, bytes);
+    cudaFree(p);
 }
-#define SPEC_MAX spec_max()
-static size_t spec_slot_target() {   // DIL_SPEC_TARGET overrides (tuning knob)
-    static size_t v = 0;
-    if (!v) {
-        const char* e = std::getenv("DIL_SPEC_TARGET");
-        v = e && std::atol(e) > 0 ? (size_t)std::atol(e) : SPEC_SLOT_TARGET_DEFAULT;
-    }
-    return v;
+void wipe_host(void* p, size_t bytes) {
+    volatile unsigned char* q = static_cast<volatile unsigned char*>(p);
+    for (size_t i = 0; i < bytes; i++) q[i] = 0;
 }
-#define SPEC_SLOT_TARGET spec_slot_target()
+
+// message offsets come from the caller: offsets[0] == 0 and non-decreasing, otherwise a kernel would read out of bounds
+bool offsets_ok(const uint64_t* off, size_t n) {
+    if (off[0] != 0) return false;
+    for (size_t i = 0; i < n; i++)
+        if (off[i + 1] < off[i]) return false;
+    return true;
+}
+
+// Straggler speculation: once fewer than spec_target items are still active the GPU is no longer saturated by
+// distinct items, so each remaining item tries up to spec_max consecutive kappa values per round in parallel
+// slots; the smallest accepted kappa wins, which is exactly the sequential result of combined_top.v:2217-2228
+// (restart with the next kappa).  The policy itself runs on the device (spec_policy, sign_kernels.cu).
+constexpr uint32_t SPEC_TARGET_DEFAULT = 32768, SPEC_MAX_DEFAULT = 32;
+uint32_t spec_target(const dil_sign_key* k) { return k->tune.spec_target ? k->tune.spec_target : SPEC_TARGET_DEFAULT; }
+uint32_t spec_max(const dil_sign_key* k) {
+    return k->tune.spec_max && k->tune.spec_max <= 32 ? k->tune.spec_max : SPEC_MAX_DEFAULT;   // one warp lane per slot in resolve
+}
+size_t slots_for(const dil_sign_key* k, size_t n) {
+    const size_t T = spec_target(k), M = spec_max(k);
+    return n > T ? n : (n * M < T ? n * M : T);
+}
 
 void free_ws(dil_sign_key* k) {
-    void* ptrs[] = {k->mu_d, k->rhop, k->w1p, k->kappa, k->active[0], k->active[1], k->count, k->y, k->w, k->c,
-                    k->h_slot, k->accepted, k->ct_slot, k->done_list};
+    const LevelParams& P = k->P;
+    wipe_free(k->rhop, k->cap * 64);
+    wipe_free(k->y, k->slots * (size_t)P.l * 1024);
+    void* ptrs[] = {k->mu_d, k->w1p, k->kappa, k->active[0], k->active[1], k->ctl, k->w, k->c, k->h_slot, k->accepted, k->ct_slot, k->done_list};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     k->mu_d = k->rhop = k->w1p = k->ct_slot = nullptr;
     k->kappa = nullptr;
-    k->active[0] = k->active[1] = k->count = k->done_list = nullptr;
+    k->active[0] = k->active[1] = k->done_list = nullptr;
+    k->ctl = nullptr;
     k->y = k->w = nullptr;
     k->c = nullptr;
     k->h_slot = k->accepted = nullptr;
@@ -122,19 +146,19 @@ void free_ws(dil_sign_key* k) {
 }
 
 int ensure_ws(dil_engine* e, dil_sign_key* k, size_t n) {
-    if (n <= k->cap) return DIL_OK;
+    const size_t slots = slots_for(k, n);
+    if (n <= k->cap && slots <= k->slots) return DIL_OK;
     free_ws(k);
     const LevelParams& P = k->P;
     cudaError_t err = cudaSuccess;
     auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
     // slots: every item of a round owns `spec` speculative attempt slots (spec = 1 in the big rounds)
-    const size_t slots = n > SPEC_SLOT_TARGET ? n : (n * SPEC_MAX < SPEC_SLOT_TARGET ? n * SPEC_MAX : SPEC_SLOT_TARGET);
     A(dmalloc(&k->mu_d, n * 8));
     A(dmalloc(&k->rhop, n * 8));
     A(dmalloc(&k->kappa, n));
     A(dmalloc(&k->active[0], n));
     A(dmalloc(&k->active[1], n));
-    A(dmalloc(&k->count, 4));
+    A(dmalloc(&k->ctl, 1));
     A(dmalloc(&k->done_list, n));
     A(dmalloc(&k->w1p, slots * (size_t)(P.k * P.w1_bytes / 8)));
     A(dmalloc(&k->y, slots * (size_t)P.l * 256));
@@ -143,10 +167,14 @@ int ensure_ws(dil_engine* e, dil_sign_key* k, size_t n) {
     A(dmalloc(&k->h_slot, slots * (size_t)(P.omega + P.k)));
     A(dmalloc(&k->accepted, slots));
     A(dmalloc(&k->ct_slot, slots * 4));
+    if (err == cudaSuccess && !k->ctl_host) {
+        A(cudaHostAlloc(reinterpret_cast<void**>(&k->ctl_host), 64, cudaHostAllocMapped));
+        if (err == cudaSuccess) A(cudaHostGetDevicePointer(reinterpret_cast<void**>(&k->ctl_host_dev), k->ctl_host, 0));
+    }
+    if (err == cudaSuccess && !k->round_ev) A(cudaEventCreateWithFlags(&k->round_ev, cudaEventDisableTiming));
     if (err != cudaSuccess) {
         free_ws(k);
-        e->last_error = std::string("sign workspace: ") + cudaGetErrorString(err);
-        return DIL_ERR_ALLOC;
+        return fail_msg(e, DIL_ERR_ALLOC, std::string("sign workspace: ") + cudaGetErrorString(err));
     }
     k->cap = n;
     k->slots = slots;
@@ -164,17 +192,34 @@ struct DrainTarget {
     cudaEvent_t idle = nullptr;   // recorded on `stream` after the last drain of a batch
 };
 
+// Expected number of active items at the start of every round of a batch of n items (the device decides what really
+// happens; this only sizes the first burst of launches and their grids): an attempt is rejected with probability
+// 1 - 1/repetitions, the scheme's expected repetitions being 4.25 / 5.1 / 3.85 at levels 2 / 3 / 5.
+std::vector<double> expected_trajectory(const dil_sign_key* k, size_t n) {
+    const double q = k->P.level == 2 ? 0.765 : (k->P.level == 3 ? 0.804 : 0.74);
+    const size_t T = spec_target(k), M = spec_max(k), cap = slots_for(k, n);
+    std::vector<double> tr;
+    double rem = (double)n;
+    while (rem >= 0.3 && tr.size() < 200) {
+        tr.push_back(rem);
+        size_t spec = 1;
+        if (rem < (double)T) {
+            const double room = (double)(cap < T ? cap : T) / (rem < 1 ? 1 : rem);
+            spec = room < 1 ? 1 : (room > (double)M ? M : (size_t)room);
+        }
+        rem *= std::pow(q, (double)spec);
+    }
+    return tr;
+}
+
 // the round loop; all pointers are device pointers
 int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uint64_t* d_off, size_t n, uint8_t* d_zp,
                 uint8_t* d_h, uint8_t* d_ct, uint32_t* d_att, cudaStream_t st, const DrainTarget* drain = nullptr) {
     const LevelParams& P = k->P;
     int rc = ensure_ws(e, k, n);
     if (rc) return rc;
-    if (drain) {
-        // the previous batch's last drains still read done_list: let them finish before it is rewritten
-        CK(cudaStreamWaitEvent(st, drain->idle, 0));
-        CK(cudaMemsetAsync(k->count + 3, 0, 4, st));
-    }
+    // the previous batch's last drains still read the done list and the round state: let them finish first
+    if (drain) CK(cudaStreamWaitEvent(st, drain->idle, 0));
     uint64_t launches = 0;
     const bool prof = k->profile;
     if (prof) {
@@ -183,94 +228,114 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
             if (!k->ev[i]) CK(cudaEventCreate(&k->ev[i]));
     }
 #define PROF_BEGIN(cls) do { if (prof) CK(cudaEventRecord(k->ev[2 * (cls)], st)); } while (0)
-#define PROF_END(cls, units) do { if (prof) { CK(cudaEventRecord(k->ev[2 * (cls) + 1], st)); k->prof_slots[cls] += (units); } } while (0)
-    CK(dil::launch_iota(k->active[0], (uint32_t)n, st));
+#define PROF_END(cls) do { if (prof) CK(cudaEventRecord(k->ev[2 * (cls) + 1], st)); } while (0)
+    dil::SignBufs b{};
+    b.ctl = k->ctl; b.active[0] = k->active[0]; b.active[1] = k->active[1]; b.done_list = k->done_list;
+    b.mu = k->mu_d; b.rhop = k->rhop; b.kappa = k->kappa; b.y = k->y; b.w = k->w; b.w1p = k->w1p; b.c = k->c;
+    b.ct_slot = k->ct_slot; b.h_slot = k->h_slot; b.accepted = k->accepted;
+    b.zp = d_zp; b.h_out = d_h; b.ct_out = reinterpret_cast<uint64_t*>(d_ct); b.attempts = d_att;
+    b.track_done = drain != nullptr;
+    const uint32_t cap_slots = (uint32_t)slots_for(k, n);
+    CK(dil::launch_sign_begin(b, (uint32_t)n, cap_slots, spec_target(k), spec_max(k), st));
     PROF_BEGIN(0);
-    CK(dil::launch_sign_init(k->mu_d, k->rhop, k->kappa, k->seeds, k->seeds + 32, d_msgs, d_off, (uint32_t)n, st));
-    PROF_END(0, n);
+    CK(dil::launch_sign_init(k->mu_d, k->rhop, k->kappa, k->seeds, k->seeds + 32, 0, d_msgs, d_off, (uint32_t)n, st));
+    PROF_END(0);
     launches += 2;
     if (prof) {
         CK(cudaStreamSynchronize(st));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, k->ev[0], k->ev[1]));
         k->prof_ms[0] += ms;
+        k->prof_slots[0] += n;
     }
-    uint32_t n_active = (uint32_t)n, rounds = 0;
-    int cur = 0;
-    // DIL_SIGN_STATIC=1: static warp-stride distribution in the two persistent kernels (A/B measurements)
-    const char* dyn_env = std::getenv("DIL_SIGN_STATIC");
-    const bool dyn = !(dyn_env && std::atoi(dyn_env) != 0);
-    // DIL_RESOLVE_FUSED=0: always run the separate resolve pass (A/B measurements)
-    const char* fuse_env = std::getenv("DIL_RESOLVE_FUSED");
-    const bool fuse_ok = !(fuse_env && std::atoi(fuse_env) == 0);
-    while (n_active > 0) {
-        if (++rounds > 4000) {
-            e->last_error = "sign: rejection loop did not terminate";
-            return DIL_ERR_CUDA;
-        }
-        size_t spec = 1;
-        if (n_active < SPEC_SLOT_TARGET) {
-            size_t room = (k->slots < SPEC_SLOT_TARGET ? k->slots : SPEC_SLOT_TARGET) / n_active;
-            spec = room < 1 ? 1 : (room > SPEC_MAX ? SPEC_MAX : room);
-        }
-        const uint32_t n_slots = (uint32_t)(n_active * spec);
-        CK(cudaMemsetAsync(k->count, 0, 12, st));   // next round's size and the two work counters
-        PROF_BEGIN(1);
-        CK(dil::launch_expand_mask(P.level, k->y, k->rhop, k->kappa, k->active[cur], n_slots, (uint32_t)spec, st));
-        PROF_END(1, n_slots);
-        PROF_BEGIN(2);
-        // the core also emits the packed w1 = HighBits(w) (class 3, "pack_w1", is only timed separately when the
-        // unfused experiment path is selected; it then appears inside class 2)
-        CK(dil::launch_signcore(k->w, k->a_hat, k->y, P.k, P.l, n_slots, e->sm_count, st, dyn ? k->count + 1 : nullptr,
-                                reinterpret_cast<uint8_t*>(k->w1p)));
-        PROF_END(2, n_slots);
-        PROF_BEGIN(4);
-        CK(dil::launch_challenge(P.level, k->c, k->ct_slot, k->mu_d, k->w1p, k->active[cur], n_slots, (uint32_t)spec, st));
-        PROF_END(4, n_slots);
-        // without speculation (one slot per item) the tail finishes or re-queues its item itself: no resolve pass
-        const bool fuse_resolve = spec == 1 && fuse_ok;
-        dil::TailResolve tr{d_zp, d_h, reinterpret_cast<uint64_t*>(d_ct), d_att, k->kappa, k->active[cur ^ 1], k->count, k->ct_slot,
-                            k->active[cur], drain ? k->done_list : nullptr};
-        PROF_BEGIN(5);
-        CK(dil::launch_sign_tail(P.level, k->y, k->h_slot, k->accepted, k->key_hat, k->w, k->c, n_slots, e->sm_count, st,
-                                 dyn ? k->count + 2 : nullptr, fuse_resolve ? &tr : nullptr, k->key_small));
-        PROF_END(5, n_slots);
-        if (!fuse_resolve) {
-            PROF_BEGIN(6);
-            CK(dil::launch_resolve(P.level, d_zp, d_h, reinterpret_cast<uint64_t*>(d_ct), d_att, k->kappa, k->active[cur ^ 1], k->count,
-                                   k->y, k->h_slot, k->ct_slot, k->accepted, k->active[cur], n_active, (uint32_t)spec,
-                                   drain ? k->done_list : nullptr, st));
-            PROF_END(6, n_active);
-            launches++;
-        }
-        launches += 4;
-        if (!k->count_host) {
-            CK(cudaHostAlloc(reinterpret_cast<void**>(&k->count_host), 64, cudaHostAllocMapped));
-            CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&k->count_host_dev), k->count_host, 0));
-        }
-        CK(dil::launch_publish_count(k->count_host_dev, k->count, st));
-        CK(cudaStreamSynchronize(st));
-        const uint32_t next = *reinterpret_cast<volatile uint32_t*>(k->count_host);
-        if (prof)
-            for (int cls = 1; cls <= 6; cls++) {
-                if (cls == 3) continue;   // w1 packing is part of the sign core (class 2)
-                if (cls == 6 && fuse_resolve) continue;   // resolve ran inside the tail (class 5)
-                float ms = 0;
-                CK(cudaEventElapsedTime(&ms, k->ev[2 * cls], k->ev[2 * cls + 1]));
-                k->prof_ms[cls] += ms;
+    // Rounds are enqueued in bursts without waiting for their outcome; a round that finds no active items costs
+    // a handful of empty launches.  The host reads the round state (posted write into mapped memory) once per burst.
+    // Grid sizes are hints (every kernel strides or claims work dynamically, so any grid is correct): the expected
+    // number of active items plus a margin, never more than the last count the host has seen.
+    const std::vector<double> traj = expected_trajectory(k, n);
+    const uint32_t T = spec_target(k), M = spec_max(k);
+    uint32_t enq = 0, seen = (uint32_t)n, seen_at = 0;   // last observed item count and the round it belongs to
+    volatile uint32_t* hc = k->ctl_host;
+    int burst = prof ? 1 : (int)traj.size() + 1;
+    for (;;) {
+        for (int i = 0; i < burst; i++, enq++) {
+            uint32_t ci = seen;   // hint: items of this round
+            if (enq > seen_at) {
+                const size_t ti = enq < traj.size() ? enq : traj.size() - 1, ts = seen_at < traj.size() ? seen_at : traj.size() - 1;
+                const double ratio = traj[ts] > 0 ? traj[ti] / traj[ts] : 1.0;
+                const double guess = (double)seen * ratio * 1.25 + 512.0;
+                if (guess < (double)seen) ci = (uint32_t)guess;
             }
-        if (drain && next < n_active) {
-            // the stream was just synchronised, so this round's signatures are final in the staging arrays
-            CK(dil::launch_drain(drain->z, drain->h, drain->ct, drain->att, d_zp, d_h, d_ct, d_att, k->done_list + (n - n_active),
-                                 n_active - next, (uint32_t)(P.l * P.z_bytes), (uint32_t)(P.omega + P.k), drain->stream));
-            launches++;
+            const uint64_t cs64 = ci >= T ? ci : ((uint64_t)ci * M < cap_slots ? (uint64_t)ci * M : cap_slots);
+            const uint32_t cs = (uint32_t)(cs64 < ci ? ci : cs64);   // hint: slots of this round
+            if (!k->tune.unfused_mask) {
+                // ExpandMask, the transforms and the mat-vec in one kernel (mask_core.cu); timed as class 2
+                PROF_BEGIN(1);
+                PROF_END(1);
+                PROF_BEGIN(2);
+                CK(dil::launch_mask_core(P.level, b, k->a_hat, cs, e->sm_count, st));
+                PROF_END(2);
+                launches--;
+            } else {
+                PROF_BEGIN(1);
+                CK(dil::launch_expand_mask(P.level, b, cs, st));
+                PROF_END(1);
+                PROF_BEGIN(2);
+                // the core also emits the packed w1 = HighBits(w)
+                CK(dil::launch_signcore(k->w, k->a_hat, k->y, P.k, P.l, cs, e->sm_count, st, &k->ctl->ctr_core,
+                                        reinterpret_cast<uint8_t*>(k->w1p), &k->ctl->n_slots));
+                PROF_END(2);
+            }
+            PROF_BEGIN(4);
+            CK(dil::launch_challenge(P.level, b, cs, st));
+            PROF_END(4);
+            // rounds with one slot per item: the tail finishes or re-queues its item itself and resolve returns at once
+            PROF_BEGIN(5);
+            CK(dil::launch_sign_tail(P.level, b, k->key_hat, k->key_small, cs, e->sm_count, st));
+            PROF_END(5);
+            PROF_BEGIN(6);
+            // only a first round of >= spec_target items is known to run without speculation; later rounds decide on the device
+            if (!(enq == 0 && n >= T)) { CK(dil::launch_resolve(P.level, b, ci < T ? ci : T, st)); launches++; }
+            PROF_END(6);
+            CK(dil::launch_plan(k->ctl, enq, st));
+            launches += 5;
+            if (drain) {
+                CK(cudaEventRecord(k->round_ev, st));
+                CK(cudaStreamWaitEvent(drain->stream, k->round_ev, 0));
+                CK(dil::launch_drain(drain->z, drain->h, drain->ct, drain->att, b, enq, (uint32_t)(P.l * P.z_bytes),
+                                     (uint32_t)(P.omega + P.k), drain->stream));
+                launches++;
+            }
+            if (prof) {
+                // per-class device time of this round; the slots it processed = growth of total_slots
+                CK(dil::launch_publish_ctl(k->ctl_host_dev, k->ctl, st));
+                CK(cudaStreamSynchronize(st));
+                const uint64_t total = hc[9];
+                for (int cls = 1; cls <= 6; cls++) {
+                    if (cls == 3) continue;   // w1 packing is part of the sign core (class 2)
+                    float ms = 0;
+                    CK(cudaEventElapsedTime(&ms, k->ev[2 * cls], k->ev[2 * cls + 1]));
+                    k->prof_ms[cls] += ms;
+                    k->prof_slots[cls] = total;
+                }
+                seen = hc[0];
+                seen_at = enq + 1;
+            }
         }
-        n_active = next;
-        cur ^= 1;
+        if (!prof) {
+            CK(dil::launch_publish_ctl(k->ctl_host_dev, k->ctl, st));
+            CK(cudaStreamSynchronize(st));
+            seen = hc[0];
+            seen_at = enq;
+        }
+        if (seen == 0) break;
+        if (enq > 4000) return fail_msg(e, DIL_ERR_CUDA, "sign: rejection loop did not terminate");
+        burst = prof ? 1 : 2;
     }
     if (drain) CK(cudaEventRecord(drain->idle, drain->stream));
     e->launches += launches;
-    k->last_rounds = rounds;
+    k->last_rounds = hc[8];
+    k->last_slots = hc[9];
     return DIL_OK;
 }
 
@@ -334,11 +399,16 @@ int dil_sign_key_create(dil_engine_t* e, dil_sign_key_t** out, int level, const 
         A(dil::launch_ntt_fwd(k->key_hat, k->key_hat, nkey, e->sm_count, st));
         A(cudaStreamSynchronize(st));
     }
+    // host copies of the secret key leave no residue
+    wipe_host(seeds, sizeof seeds);
+    wipe_host(polys.data(), polys.size() * 4);
+    wipe_host(small.data(), small.size());
+    wipe_host(tmp.data(), tmp.size() * 4);
     if (err != cudaSuccess) {
         if (k->a_hat) cudaFree(k->a_hat);
-        if (k->key_hat) cudaFree(k->key_hat);
-        if (k->key_small) cudaFree(k->key_small);
-        if (k->seeds) cudaFree(k->seeds);
+        wipe_free(k->key_hat, (size_t)nkey * 1024);
+        wipe_free(k->key_small, (size_t)(P.l + P.k) * 256);
+        wipe_free(k->seeds, 96);
         delete k;
         return fail(e, err, "dil_sign_key_create");
     }
@@ -350,19 +420,33 @@ int dil_sign_key_create(dil_engine_t* e, dil_sign_key_t** out, int level, const 
 int dil_sign_key_destroy(dil_engine_t* e, dil_sign_key_t* k) {
     if (!k) return DIL_OK;
     DeviceGuard dg(k->device);
+    const LevelParams& P = k->P;
     free_ws(k);
-    void* ptrs[] = {k->a_hat, k->key_hat, k->key_small, k->seeds, k->msgs_d, k->zp_d, k->h_d, k->ct_d, k->off_d, k->att_d};
+    wipe_free(k->key_hat, (size_t)(P.l + 2 * P.k) * 1024);
+    wipe_free(k->key_small, (size_t)(P.l + P.k) * 256);
+    wipe_free(k->seeds, 96);
+    void* ptrs[] = {k->a_hat, k->msgs_d, k->zp_d, k->h_d, k->ct_d, k->off_d, k->att_d};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& ev : k->ev)
         if (ev) cudaEventDestroy(ev);
-    if (k->count_host) cudaFreeHost(k->count_host);
+    if (k->round_ev) cudaEventDestroy(k->round_ev);
+    if (k->ctl_host) cudaFreeHost(k->ctl_host);
     (void)e;
     delete k;
     return DIL_OK;
 }
 
 uint32_t dil_sign_last_rounds(const dil_sign_key_t* k) { return k ? k->last_rounds : 0; }
+uint64_t dil_sign_last_slots(const dil_sign_key_t* k) { return k ? k->last_slots : 0; }
+
+int dil_sign_key_set_tuning(dil_sign_key_t* k, const dil_sign_tuning* t) {
+    if (!k) return DIL_ERR_ARG;
+    if (t && t->spec_max > 32) return DIL_ERR_ARG;
+    std::lock_guard<std::mutex> g(k->mu);
+    k->tune = t ? *t : dil_sign_tuning{};
+    return DIL_OK;
+}
 
 int dil_sign_set_profile(dil_sign_key_t* k, int on) {
     if (!k) return DIL_ERR_ARG;
@@ -386,9 +470,8 @@ int dil_sign_batch_dev(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* d_msgs
     DeviceGuard dg(e->device);
     if (!dg.ok) return DIL_ERR_CUDA;
     // very large batches are signed in 2^20-message pieces so that the per-attempt workspace (about
-    // 9.5 / 13 / 17 KB per message at levels 2 / 3 / 5) stays bounded; DIL_SIGN_DEV_CHUNK overrides (tests)
-    const char* ev = std::getenv("DIL_SIGN_DEV_CHUNK");
-    const size_t chunk = ev && std::atol(ev) > 0 ? (size_t)std::atol(ev) : ((size_t)1 << 20);
+    // 9.5 / 13 / 17 KB per message at levels 2 / 3 / 5) stays bounded
+    const size_t chunk = k->tune.dev_chunk ? k->tune.dev_chunk : ((size_t)1 << 20);
     const size_t zb = (size_t)k->P.l * k->P.z_bytes, hb = (size_t)k->P.omega + k->P.k;
     for (size_t lo = 0; lo < n;) {
         const size_t m = n - lo <= chunk + chunk / 4 ? n - lo : chunk;
@@ -405,6 +488,7 @@ int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs,
     if (!e || !k) return DIL_ERR_ARG;
     if (n == 0) return DIL_OK;
     if (!msgs || !offsets || !z || !h || !ctilde || n > 0x07FFFFFFu) return DIL_ERR_ARG;
+    if (!offsets_ok(offsets, n)) return DIL_ERR_ARG;
     std::lock_guard<std::mutex> g(k->mu);
     DeviceGuard dg(e->device);
     if (!dg.ok) return DIL_ERR_CUDA;
@@ -434,7 +518,6 @@ int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs,
         CK(dmalloc(&k->att_d, n));
         k->out_cap = n;
     }
-    const auto t_begin = std::chrono::steady_clock::now();
     CK(cudaMemcpyAsync(k->msgs_d, msgs, offsets[n], cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(k->off_d, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
     cudaStream_t cs = e->copy_stream;
@@ -442,12 +525,8 @@ int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs,
     // cudaHostRegister; torch's pinned tensors are), finished signatures leave round by round (DrainTarget)
     // and the transfer hides behind the remaining rounds.  Pageable buffers take the chunked copy path below.
     {
-        // DIL_SIGN_DRAIN=0 forces the chunked copy path (A/B measurements); DIL_SIGN_CHUNK overrides the batch
-        // size of the streaming path (tests use it to cover the multi-batch case at small sizes)
-        const char* ev = std::getenv("DIL_SIGN_DRAIN");
-        const bool want = !(ev && std::atoi(ev) == 0);
-        ev = std::getenv("DIL_SIGN_CHUNK");
-        const size_t CHUNK = ev && std::atol(ev) > 0 ? (size_t)std::atol(ev) : 262144;
+        const bool want = !k->tune.host_copy_path;
+        const size_t CHUNK = k->tune.host_chunk ? k->tune.host_chunk : 262144;
         DrainTarget dt;
         auto dev_alias = [&](const void* p, size_t align) -> void* {
             cudaPointerAttributes a{};
@@ -476,14 +555,7 @@ int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs,
                 lo += m;
             }
             cudaError_t e2 = cudaStreamSynchronize(st);
-            const auto t_compute = std::chrono::steady_clock::now();
             cudaError_t e1 = cudaStreamSynchronize(cs);
-            if (std::getenv("DIL_SIGN_TRACE")) {
-                const auto t_end = std::chrono::steady_clock::now();
-                auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-                std::fprintf(stderr, "[dil] sign host path: signing done at %.3f ms, drain done at %.3f ms\n", ms(t_begin, t_compute),
-                             ms(t_begin, t_end));
-            }
             cudaEventDestroy(dt.idle);
             if (rc) return rc;
             if (e1 != cudaSuccess) return fail(e, e1, "sign drain sync");
@@ -519,10 +591,11 @@ int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs,
         if (er != cudaSuccess) rc = fail(e, er, "sign D2H");
     }
     cudaError_t er2 = cudaStreamSynchronize(cs);
+    cudaError_t er3 = cudaStreamSynchronize(st);
     cudaEventDestroy(done);
     if (rc) return rc;
     if (er2 != cudaSuccess) return fail(e, er2, "sign D2H sync");
-    CK(cudaStreamSynchronize(st));
+    if (er3 != cudaSuccess) return fail(e, er3, "sign sync");
     return DIL_OK;
 }
 
@@ -542,6 +615,9 @@ struct dil_verify_key {
     uint64_t *mu_d = nullptr, *w1p = nullptr;
     int32_t *v = nullptr, *w = nullptr;
     uint32_t *hmask = nullptr, *bad = nullptr;
+    // The workspace above is shared by every call on this key.  _dev calls only enqueue, so a later call (possibly on
+    // another stream) first waits for the previous user's last kernel: ws_done is recorded after it.
+    cudaEvent_t ws_done = nullptr;
     // host-variant staging
     uint8_t *msgs_d = nullptr, *z_d = nullptr, *h_d = nullptr, *ct_d = nullptr, *ok_d = nullptr;
     uint64_t* off_d = nullptr;
@@ -568,8 +644,7 @@ int ensure_vws(dil_engine* e, dil_verify_key* k, size_t n) {
     A(dmalloc(&k->bad, n));
     if (err != cudaSuccess) {
         free_vws(k);
-        e->last_error = std::string("verify workspace: ") + cudaGetErrorString(err);
-        return DIL_ERR_ALLOC;
+        return fail_msg(e, DIL_ERR_ALLOC, std::string("verify workspace: ") + cudaGetErrorString(err));
     }
     k->cap = n;
     return DIL_OK;
@@ -580,6 +655,8 @@ int verify_run(dil_engine* e, dil_verify_key* k, const uint8_t* d_msgs, const ui
     int rc = ensure_vws(e, k, n);
     if (rc) return rc;
     const uint32_t nn = (uint32_t)n;
+    if (!k->ws_done) CK(cudaEventCreateWithFlags(&k->ws_done, cudaEventDisableTiming));
+    else CK(cudaStreamWaitEvent(st, k->ws_done, 0));   // the previous batch may still be running on another stream
     CK(cudaMemsetAsync(k->bad, 0, n * 4, st));
     CK(dil::launch_verify_mu(k->mu_d, k->seeds, d_msgs, d_off, nn, 0, st));
     CK(dil::launch_unpack_z(P.level, k->v, k->bad, d_z, nn, st));
@@ -587,6 +664,7 @@ int verify_run(dil_engine* e, dil_verify_key* k, const uint8_t* d_msgs, const ui
     CK(dil::launch_verify_core(k->w, k->a_ext, k->v, P.level, n, e->sm_count, st));
     CK(dil::launch_usehint_pack(P.level, reinterpret_cast<uint32_t*>(k->w1p), k->w, k->hmask, nn, st));
     CK(dil::launch_verify_hash(P.level, d_ok, k->mu_d, k->w1p, reinterpret_cast<const uint64_t*>(d_ct), k->bad, nn, st));
+    CK(cudaEventRecord(k->ws_done, st));
     e->launches += 6;
     return DIL_OK;
 }
@@ -658,6 +736,7 @@ int dil_verify_key_destroy(dil_engine_t* e, dil_verify_key_t* k) {
     DeviceGuard dg(k->device);
     free_vws(k);
     vfree(k->a_ext); vfree(k->seeds); vfree(k->msgs_d); vfree(k->z_d); vfree(k->h_d); vfree(k->ct_d); vfree(k->ok_d); vfree(k->off_d);
+    if (k->ws_done) cudaEventDestroy(k->ws_done);
     delete k;
     return DIL_OK;
 }
@@ -744,8 +823,7 @@ extern "C" int dil_keygen_batch_host(dil_engine_t* e, int level, const uint8_t* 
     uint8_t* base = nullptr;
     cudaError_t aerr = cudaMalloc(reinterpret_cast<void**>(&base), total);
     if (aerr != cudaSuccess) {
-        e->last_error = std::string("keygen arena: ") + cudaGetErrorString(aerr);
-        return DIL_ERR_ALLOC;
+        return fail_msg(e, DIL_ERR_ALLOC, std::string("keygen arena: ") + cudaGetErrorString(aerr));
     }
     auto P8 = [&](Seg s) { return base + s.off; };
     auto P32 = [&](Seg s) { return reinterpret_cast<int32_t*>(base + s.off); };
@@ -793,8 +871,7 @@ int arena_reserve(dil_engine* e, size_t bytes, uint8_t** base) {
         e->staging_bytes[3] = 0;
         cudaError_t err = cudaMalloc(&e->staging[3], bytes);
         if (err != cudaSuccess) {
-            e->last_error = std::string("verify arena: ") + cudaGetErrorString(err);
-            return DIL_ERR_ALLOC;
+            return fail_msg(e, DIL_ERR_ALLOC, std::string("verify arena: ") + cudaGetErrorString(err));
         }
         e->staging_bytes[3] = bytes;
     }
@@ -823,6 +900,9 @@ cudaError_t verify_multi_run(dil_engine* e, const LevelParams& P, uint8_t* work,
     auto PU64 = [&](size_t o) { return reinterpret_cast<uint64_t*>(work + o); };
     cudaError_t err = cudaSuccess;
     auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+    // the arena is shared by every multi-key call on this engine: wait for its previous user (possibly another stream)
+    if (!e->arena_done) A(cudaEventCreateWithFlags(&e->arena_done, cudaEventDisableTiming));
+    else A(cudaStreamWaitEvent(st, e->arena_done, 0));
     A(cudaMemsetAsync(work + m.bad, 0, n * 4, st));
     A(dil::launch_tr_batch(work + m.tr, d_rho, d_t1p, (uint32_t)(K * 320), nn, st));
     A(dil::launch_verify_mu(PU64(m.mu), work + m.tr, d_msgs, d_off, nn, 32, st));
@@ -833,6 +913,7 @@ cudaError_t verify_multi_run(dil_engine* e, const LevelParams& P, uint8_t* work,
     A(dil::launch_verify_core_item(P32(m.w), d_rho, P32(m.v), P32(m.t1n), P.level, n, st));
     A(dil::launch_usehint_pack(P.level, PU32(m.w1p), P32(m.w), PU32(m.hm), nn, st));
     A(dil::launch_verify_hash(P.level, d_ok, PU64(m.mu), PU64(m.w1p), reinterpret_cast<const uint64_t*>(d_ct), PU32(m.bad), nn, st));
+    if (err == cudaSuccess) A(cudaEventRecord(e->arena_done, st));
     return err;
 }
 }  // namespace
@@ -883,6 +964,7 @@ extern "C" int dil_verify_multi_host(dil_engine_t* e, int level, const uint8_t* 
     if (rc) return rc;
     cudaError_t err = cudaSuccess;
     auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+    if (e->arena_done) A(cudaStreamWaitEvent(st, e->arena_done, 0));   // a _dev call on another stream may still use the arena
     A(cudaMemcpyAsync(base + o_rho, rho, n * 32, cudaMemcpyHostToDevice, st));
     A(cudaMemcpyAsync(base + o_t1p, t1p, n * t1b, cudaMemcpyHostToDevice, st));
     A(cudaMemcpyAsync(base + o_msgs, msgs, offsets[n], cudaMemcpyHostToDevice, st));

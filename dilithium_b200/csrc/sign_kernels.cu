@@ -13,8 +13,6 @@
 // items are compacted into the next round's active list.
 #include <cuda_runtime.h>
 
-#include <cstdlib>
-
 #include "dil_params.h"
 #include "keccak.cuh"
 #include "kernels.h"
@@ -23,23 +21,21 @@
 
 namespace dil {
 
-// development knobs for the pipe-overlap experiment: cap CTAs per SM of a kernel class
-static int overlap_knob(const char* name, int dflt) {
-    const char* e = std::getenv(name);
-    return e ? std::atoi(e) : dflt;
-}
-
 // ---------------------------------------------------------------------------------------
 // S0: mu = SHAKE256(tr || M)[0:64], rho' = SHAKE256(K || mu)[0:64]; one thread per item
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) sign_init_kernel(uint64_t* __restrict__ mu, uint64_t* __restrict__ rhop,
                                                         uint16_t* __restrict__ kappa, const uint8_t* __restrict__ tr,
-                                                        const uint8_t* __restrict__ key, const uint8_t* __restrict__ msgs,
+                                                        const uint8_t* __restrict__ key, size_t key_stride,
+                                                        const uint8_t* __restrict__ msgs,
                                                         const uint64_t* __restrict__ offsets, uint32_t n) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
+    tr += (size_t)t * key_stride;     // stride 0: one key for the batch; otherwise one (tr, K) record per item
+    key += (size_t)t * key_stride;
     const uint8_t* m = msgs + offsets[t];
-    const size_t mlen = (size_t)(offsets[t + 1] - offsets[t]);
+    // the host entry points validate the offsets; a non-monotonic pair in device memory reads as an empty message
+    const size_t mlen = offsets[t + 1] >= offsets[t] ? (size_t)(offsets[t + 1] - offsets[t]) : 0;
     uint64_t A[25];
     shake256_absorb_lanes(A, 32 + mlen, [&](size_t idx) -> uint64_t {
         if (idx < 4) return load_lane_bytes(tr, idx * 8, 32);
@@ -77,8 +73,10 @@ __global__ void __launch_bounds__(128) sign_init_kernel(uint64_t* __restrict__ m
 // ---------------------------------------------------------------------------------------
 template <int L, int GAMMA1_BITS>
 __global__ void __launch_bounds__(128) expand_mask_kernel(int32_t* __restrict__ y, const uint64_t* __restrict__ rhop,
-                                                          const uint16_t* __restrict__ kappa, const uint32_t* __restrict__ active,
-                                                          uint32_t n_slots, uint32_t spec) {
+                                                          const uint16_t* __restrict__ kappa, const uint32_t* __restrict__ active0,
+                                                          const uint32_t* __restrict__ active1, const RoundCtl* __restrict__ ctl) {
+    const uint32_t n_slots = ctl->n_slots, spec = ctl->spec;
+    const uint32_t* __restrict__ active = ctl->cur ? active1 : active0;
     constexpr int ZB = 32 * (GAMMA1_BITS + 1);       // packed bytes per poly: 576 / 640
     constexpr int ROW = ZB + 16;                      // row stride in shared memory
     constexpr int LANES = ZB / 8;                     // 72 / 80 lanes of output needed
@@ -150,46 +148,6 @@ __global__ void __launch_bounds__(128) expand_mask_kernel(int32_t* __restrict__ 
     }
 }
 
-// S3: w1 = HighBits(w), bit-packed (encoder.v:96-133: 6 bits for gamma2=(Q-1)/88, else 4).
-// One thread per 16 coefficients -> 12 or 8 bytes.
-template <int32_t GAMMA2>
-__global__ void __launch_bounds__(256) pack_w1_kernel(uint32_t* __restrict__ w1p, const int32_t* __restrict__ w, size_t n_groups) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_groups) return;
-    const int4* src = reinterpret_cast<const int4*>(w) + t * 4;
-    int32_t h[16];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        int4 v = src[q];
-        int32_t a0;
-        decompose<GAMMA2>(v.x, h[4 * q + 0], a0);
-        decompose<GAMMA2>(v.y, h[4 * q + 1], a0);
-        decompose<GAMMA2>(v.z, h[4 * q + 2], a0);
-        decompose<GAMMA2>(v.w, h[4 * q + 3], a0);
-    }
-    if constexpr (GAMMA2 == (Q_I - 1) / 32) {
-        uint32_t o0 = 0, o1 = 0;
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            o0 |= (uint32_t)h[c] << (4 * c);
-            o1 |= (uint32_t)h[8 + c] << (4 * c);
-        }
-        w1p[t * 2] = o0;
-        w1p[t * 2 + 1] = o1;
-    } else {
-        uint64_t lo = 0;
-        uint32_t hi = 0;
-#pragma unroll
-        for (int c = 0; c < 10; c++) lo |= (uint64_t)h[c] << (6 * c);           // bits 0..59
-        lo |= (uint64_t)h[10] << 60;                                              // bits 60..65
-        hi = ((uint32_t)h[10] >> 4) | ((uint32_t)h[11] << 2) | ((uint32_t)h[12] << 8) | ((uint32_t)h[13] << 14) |
-             ((uint32_t)h[14] << 20) | ((uint32_t)h[15] << 26);
-        w1p[t * 3] = (uint32_t)lo;
-        w1p[t * 3 + 1] = (uint32_t)(lo >> 32);
-        w1p[t * 3 + 2] = hi;
-    }
-}
-
 // ---------------------------------------------------------------------------------------
 // S4: c~ = SHAKE256(mu || w1_packed)[0:32]; c = SampleInBall(c~) (gen_c.v:163-222, :317-343).
 // One thread per active item; c is written as 256 int8 in {-1,0,1}.
@@ -203,7 +161,10 @@ constexpr int CH_BUF_STRIDE = 144;   // 136 squeezed bytes + 8
 template <int K, int W1_BYTES, int TAU>
 __global__ void __launch_bounds__(CH_THREADS) challenge_kernel(int8_t* __restrict__ c_out, uint64_t* __restrict__ ctilde,
                                                                const uint64_t* __restrict__ mu, const uint64_t* __restrict__ w1p,
-                                                               const uint32_t* __restrict__ active, uint32_t n_slots, uint32_t spec) {
+                                                               const uint32_t* __restrict__ active0, const uint32_t* __restrict__ active1,
+                                                               const RoundCtl* __restrict__ ctl) {
+    const uint32_t n_slots = ctl->n_slots, spec = ctl->spec;
+    const uint32_t* __restrict__ active = ctl->cur ? active1 : active0;
     __shared__ __align__(16) uint8_t c_sm[CH_THREADS * CH_C_STRIDE];
     __shared__ __align__(16) uint8_t buf_sm[CH_THREADS * CH_BUF_STRIDE];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -269,13 +230,13 @@ __global__ void __launch_bounds__(CH_THREADS) challenge_kernel(int8_t* __restric
 // Accepted slot `a` of `item` (its s-th speculative attempt) becomes the signature: z is packed
 // (encoder.v:96-133: gamma1 - z, 18 or 20 bits) through a per-warp shared staging row and leaves as
 // 16-byte vectors, h and c~ are copied, the attempt count is recorded and the item joins the
-// completion-ordered done list (next_count[3] counts finished items over the whole batch; the host path
+// completion-ordered done list (RoundCtl::done counts finished items over the whole batch; the host path
 // drains each round's finished signatures while later rounds still sign).  Executed by one warp.
 // ---------------------------------------------------------------------------------------
 template <int L, int GAMMA1_BITS, int HB, bool DIRECT = false>
 __device__ __forceinline__ void resolve_finish(uint8_t* __restrict__ zp, uint8_t* __restrict__ h_out, uint64_t* __restrict__ ct_out,
                                                uint32_t* __restrict__ attempts, const uint16_t* __restrict__ kappa,
-                                               uint32_t* __restrict__ next_count, const int32_t* zslot,
+                                               uint32_t* __restrict__ done_ctr, const int32_t* zslot,
                                                const uint8_t* h_slot, const uint64_t* __restrict__ ct_slot,
                                                uint32_t* __restrict__ done_list, uint32_t item, uint32_t a, uint32_t s,
                                                uint8_t* dstp, int lane) {
@@ -327,25 +288,45 @@ __device__ __forceinline__ void resolve_finish(uint8_t* __restrict__ zp, uint8_t
     if (lane < 4) ct_out[(size_t)item * 4 + lane] = ct_slot[(size_t)a * 4 + lane];
     if (lane == 0) {
         attempts[item] = (uint32_t)kappa[item] + s + 1;
-        if (done_list) done_list[atomicAdd(next_count + 3, 1u)] = item;
+        if (done_list) done_list[atomicAdd(done_ctr, 1u)] = item;
     }
     __syncwarp();
 }
 
-// Resolve arguments for the rounds without speculation (one slot per item), where the tail kernel
-// finishes or re-queues its item itself and no separate resolve pass runs (zp == nullptr: not fused).
+// Kernel argument of the tail kernels: where signatures go and how items are re-queued.  In rounds with one slot
+// per item (ctl->spec == 1) the tail finishes or re-queues its item itself and the resolve pass has nothing to do.
 struct ResolveArgs {
     uint8_t* zp = nullptr;
     uint8_t* h_out = nullptr;
     uint64_t* ct_out = nullptr;
     uint32_t* attempts = nullptr;
     uint16_t* kappa = nullptr;
-    uint32_t* next_active = nullptr;
-    uint32_t* next_count = nullptr;
+    uint32_t* active0 = nullptr;
+    uint32_t* active1 = nullptr;
+    RoundCtl* ctl = nullptr;
     const uint64_t* ct_slot = nullptr;
-    const uint32_t* active = nullptr;
     uint32_t* done_list = nullptr;
 };
+// the same, resolved against the round state at kernel start
+struct ResolveCtx {
+    uint8_t* zp;
+    uint8_t* h_out;
+    uint64_t* ct_out;
+    uint32_t* attempts;
+    uint16_t* kappa;
+    uint32_t* next_active;
+    uint32_t* next_count;
+    uint32_t* done_ctr;
+    const uint64_t* ct_slot;
+    const uint32_t* active;
+    uint32_t* done_list;
+    bool fused;
+};
+__device__ __forceinline__ ResolveCtx resolve_ctx(const ResolveArgs& ra) {
+    const bool cur = ra.ctl->cur != 0;
+    return ResolveCtx{ra.zp, ra.h_out, ra.ct_out, ra.attempts, ra.kappa, cur ? ra.active0 : ra.active1, &ra.ctl->next_count, &ra.ctl->done,
+                      ra.ct_slot, cur ? ra.active1 : ra.active0, ra.done_list, ra.ctl->spec == 1};
+}
 
 // Survivors of the r0 and z checks: ct0_i = INTT(c_hat o t0_hat_i), ||ct0|| < gamma2, hint bits of
 // (r0 + ct0, HighBits(w)) as 32-bit ballot masks hm[i*8 + r] (bit = lane, coefficient lane + 32 r), their count in nh.
@@ -384,11 +365,11 @@ __device__ __forceinline__ bool tail_ct0_hints(const uint32_t (&ch)[8], const ui
 }
 
 // End of a slot: hint bytes of an accepted slot (omega position bytes, ascending inside each polynomial, then k
-// running counts), the accept flag, and - in rounds with one slot per item (ra.zp != nullptr) - the resolve step:
+// running counts), the accept flag, and - in rounds with one slot per item (ra.fused) - the resolve step:
 // the accepted slot becomes the signature, a rejected item advances kappa and joins the next round.
 template <int K, int L, int G1BITS, int OMEGA, bool DIRECT>
 __device__ __forceinline__ void tail_finish(bool bad, uint32_t a, const int32_t* y, uint8_t* h_slot, uint8_t* __restrict__ accepted,
-                                            const uint32_t* __restrict__ hm, const ResolveArgs& ra, uint8_t* zstage, int lane) {
+                                            const uint32_t* __restrict__ hm, const ResolveCtx& ra, uint8_t* zstage, int lane) {
     __syncwarp();
     if (!bad) {
         uint8_t* ho = h_slot + (size_t)a * (OMEGA + K);
@@ -406,7 +387,7 @@ __device__ __forceinline__ void tail_finish(bool bad, uint32_t a, const int32_t*
     }
     if (lane == 0) accepted[a] = bad ? 0 : 1;
     __syncwarp();
-    if (ra.zp != nullptr) {
+    if (ra.fused) {
         const uint32_t item = ra.active[a];
         if (bad) {
             if (lane == 0) {
@@ -414,7 +395,7 @@ __device__ __forceinline__ void tail_finish(bool bad, uint32_t a, const int32_t*
                 ra.next_active[atomicAdd(ra.next_count, 1u)] = item;
             }
         } else {
-            resolve_finish<L, G1BITS, OMEGA + K, DIRECT>(ra.zp, ra.h_out, ra.ct_out, ra.attempts, ra.kappa, ra.next_count, y, h_slot,
+            resolve_finish<L, G1BITS, OMEGA + K, DIRECT>(ra.zp, ra.h_out, ra.ct_out, ra.attempts, ra.kappa, ra.done_ctr, y, h_slot,
                                                          ra.ct_slot, ra.done_list, item, a, 0u, zstage, lane);
         }
     }
@@ -434,7 +415,10 @@ template <int K, int L, int32_t GAMMA1, int32_t GAMMA2, int BETA, int OMEGA, int
 __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
     int32_t* __restrict__ y /* in: y, out: z (in place) */, uint8_t* __restrict__ h_slot, uint8_t* __restrict__ accepted,
     const int32_t* __restrict__ key_hat, int32_t* __restrict__ w /* in: w; scratch afterwards */, const int8_t* __restrict__ c,
-    uint32_t n_slots, uint32_t* __restrict__ work_ctr, const ResolveArgs ra) {
+    const ResolveArgs rargs) {
+    const uint32_t n_slots = rargs.ctl->n_slots;
+    uint32_t* const work_ctr = &rargs.ctl->ctr_tail;
+    const ResolveCtx ra = resolve_ctx(rargs);
     extern __shared__ __align__(16) uint32_t sm_words[];
     constexpr int NKEY = L + 2 * K;
     constexpr int G1BITS = GAMMA1 == (1 << 17) ? 17 : 19;
@@ -444,7 +428,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
     uint32_t* hm_all = scr_all + WARPS * SCRATCH_WORDS;  // WARPS * K * 8 hint masks
     uint8_t* zstage_all = reinterpret_cast<uint8_t*>(hm_all + WARPS * K * 8);   // WARPS * ZB (fused resolve)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (work_ctr != nullptr) {   // a CTA that starts when every slot is already claimed leaves at once (uniform decision)
+    {   // a CTA that starts when every slot is already claimed (or in a round without work) leaves at once (uniform decision)
         __shared__ uint32_t late;
         if (threadIdx.x == 0) late = *reinterpret_cast<volatile uint32_t*>(work_ctr) >= n_slots;
         __syncthreads();
@@ -464,17 +448,13 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
     InvTw itw;
     load_inv_tw(itw, &TW_INV, lane);
 
-    // Slots are claimed dynamically when the caller passes a (zeroed) work counter: the work per slot varies
-    // by an order of magnitude (early exits below), and SMs may run at different speeds or be partly taken by
-    // other streams' kernels; the claim for the next slot is issued before the current one is processed.
-    const uint32_t stride = gridDim.x * WARPS;
-    uint32_t claim = 0, a = blockIdx.x * WARPS + warp;
-    if (work_ctr != nullptr) {
+    // Slots are claimed dynamically from the round's work counter: the work per slot varies by an order of
+    // magnitude (early exits below), and SMs may run at different speeds or be partly taken by other streams'
+    // kernels; the claim for the next slot is issued before the current one is processed.
+    uint32_t claim = 0;
+    if (lane == 0) claim = atomicAdd(work_ctr, 1u);
+    for (uint32_t a = __shfl_sync(0xffffffffu, claim, 0); a < n_slots; a = __shfl_sync(0xffffffffu, claim, 0)) {
         if (lane == 0) claim = atomicAdd(work_ctr, 1u);
-        a = __shfl_sync(0xffffffffu, claim, 0);
-    }
-    for (; a < n_slots; a = work_ctr != nullptr ? __shfl_sync(0xffffffffu, claim, 0) : a + stride) {
-        if (work_ctr != nullptr && lane == 0) claim = atomicAdd(work_ctr, 1u);
         // c_hat in layout C
         uint32_t ch[8];
         {
@@ -560,7 +540,10 @@ template <int K, int L, int32_t GAMMA1, int32_t GAMMA2, int BETA, int OMEGA, int
 __global__ void __launch_bounds__(WARPS * 32, 1) sign_tail_sparse_kernel(
     int32_t* __restrict__ y /* in: y, out: z (in place) */, uint8_t* __restrict__ h_slot, uint8_t* __restrict__ accepted,
     const int32_t* __restrict__ key_hat, const int8_t* __restrict__ key_small, int32_t* __restrict__ w /* in: w; scratch afterwards */,
-    const int8_t* __restrict__ c, uint32_t n_slots, uint32_t* __restrict__ work_ctr, const ResolveArgs ra) {
+    const int8_t* __restrict__ c, const ResolveArgs rargs) {
+    const uint32_t n_slots = rargs.ctl->n_slots;
+    uint32_t* const work_ctr = &rargs.ctl->ctr_tail;
+    const ResolveCtx ra = resolve_ctx(rargs);
     extern __shared__ __align__(16) uint32_t sm_words[];
     constexpr int NP = L + K;                              // small key polynomials: s1 | s2
     constexpr int GROUP = 15 / (2 * ETA);                  // terms whose biased nibbles can be added without a carry
@@ -573,7 +556,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sign_tail_sparse_kernel(
     uint16_t* terms_all = reinterpret_cast<uint16_t*>(hm_all + WARPS * K * 8);   // WARPS * 64 term offsets
     uint8_t* tabs = reinterpret_cast<uint8_t*>(terms_all + WARPS * 64);          // NP * TABB
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (work_ctr != nullptr) {   // a CTA that starts when every slot is already claimed leaves at once (uniform decision)
+    {   // a CTA that starts when every slot is already claimed (or in a round without work) leaves at once (uniform decision)
         __shared__ uint32_t late;
         if (threadIdx.x == 0) late = *reinterpret_cast<volatile uint32_t*>(work_ctr) >= n_slots;
         __syncthreads();
@@ -627,14 +610,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sign_tail_sparse_kernel(
         for (int i = 0; i < 8; i++) x[i] = (int32_t)((((i & 1) ? b1 : b0) >> (8 * (i >> 1))) & 0xFFu) - TAU * ETA;
     };
 
-    const uint32_t stride = gridDim.x * WARPS;
-    uint32_t claim = 0, a = blockIdx.x * WARPS + warp;
-    if (work_ctr != nullptr) {
+    uint32_t claim = 0;
+    if (lane == 0) claim = atomicAdd(work_ctr, 1u);
+    for (uint32_t a = __shfl_sync(0xffffffffu, claim, 0); a < n_slots; a = __shfl_sync(0xffffffffu, claim, 0)) {
         if (lane == 0) claim = atomicAdd(work_ctr, 1u);
-        a = __shfl_sync(0xffffffffu, claim, 0);
-    }
-    for (; a < n_slots; a = work_ctr != nullptr ? __shfl_sync(0xffffffffu, claim, 0) : a + stride) {
-        if (work_ctr != nullptr && lane == 0) claim = atomicAdd(work_ctr, 1u);
         // term list: offset of every non-zero coefficient's table row (sign, alignment, shift)
         {
             const uint2 cb = *reinterpret_cast<const uint2*>(c + (size_t)a * N + 8 * lane);
@@ -723,42 +702,44 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sign_tail_sparse_kernel(
 // copied; items without an accepted slot advance kappa by `spec` and join the next round.
 // ---------------------------------------------------------------------------------------
 template <int L, int GAMMA1_BITS, int HB>
-__global__ void __launch_bounds__(256) resolve_kernel(uint8_t* __restrict__ zp, uint8_t* __restrict__ h_out,
-                                                      uint64_t* __restrict__ ct_out, uint32_t* __restrict__ attempts,
-                                                      uint16_t* __restrict__ kappa, uint32_t* __restrict__ next_active,
-                                                      uint32_t* __restrict__ next_count, const int32_t* __restrict__ zslot,
-                                                      const uint8_t* __restrict__ h_slot, const uint64_t* __restrict__ ct_slot,
-                                                      const uint8_t* __restrict__ accepted, const uint32_t* __restrict__ active,
-                                                      uint32_t n_items, uint32_t spec, uint32_t* __restrict__ done_list) {
+__global__ void __launch_bounds__(256) resolve_kernel(const ResolveArgs rargs, const int32_t* __restrict__ zslot,
+                                                      const uint8_t* __restrict__ h_slot, const uint8_t* __restrict__ accepted) {
+    const uint32_t spec = rargs.ctl->spec, n_items = rargs.ctl->n_active;
+    if (spec == 1) return;   // the tail resolved this round's items itself
     const int lane = threadIdx.x & 31;
-    const uint32_t idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (idx >= n_items) return;
-    const uint32_t item = active[idx];
-    const uint32_t a0 = idx * spec;
-    uint32_t acc = (lane < (int)spec) ? accepted[a0 + lane] : 0;
-    uint32_t mask = __ballot_sync(0xffffffffu, acc != 0);
-    if (mask == 0) {
-        if (lane == 0) {
-            kappa[item] += (uint16_t)spec;
-            next_active[atomicAdd(next_count, 1u)] = item;
-        }
-        return;
-    }
-    const uint32_t s = __ffs(mask) - 1;
+    const ResolveCtx ra = resolve_ctx(rargs);
     constexpr int ZB = L * 32 * (GAMMA1_BITS + 1);
     __shared__ __align__(16) uint8_t zstage[8][ZB];
-    resolve_finish<L, GAMMA1_BITS, HB>(zp, h_out, ct_out, attempts, kappa, next_count, zslot, h_slot, ct_slot, done_list, item, a0 + s, s,
-                                       zstage[threadIdx.x >> 5], lane);
+    for (uint32_t idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); idx < n_items; idx += gridDim.x * (blockDim.x >> 5)) {
+        const uint32_t item = ra.active[idx];
+        const uint32_t a0 = idx * spec;
+        const uint32_t acc = (lane < (int)spec) ? accepted[a0 + lane] : 0;
+        const uint32_t mask = __ballot_sync(0xffffffffu, acc != 0);
+        if (mask == 0) {
+            if (lane == 0) {
+                ra.kappa[item] += (uint16_t)spec;
+                ra.next_active[atomicAdd(ra.next_count, 1u)] = item;
+            }
+            continue;
+        }
+        const uint32_t s = __ffs(mask) - 1;
+        resolve_finish<L, GAMMA1_BITS, HB>(ra.zp, ra.h_out, ra.ct_out, ra.attempts, ra.kappa, ra.done_ctr, zslot, h_slot, ra.ct_slot,
+                                           ra.done_list, item, a0 + s, s, zstage[threadIdx.x >> 5], lane);
+    }
 }
 
-// Copies the finished signatures named by list[0..n) from the device staging arrays into the caller's
+// Copies the signatures finished by one round from the device staging arrays into the caller's
 // pinned host buffers (mapped into the device address space): posted PCIe writes, 512 contiguous bytes
 // per warp store.  Runs on the copy stream next to the following rejection rounds (launch_drain).
 __global__ void __launch_bounds__(512, 4) drain_kernel(uint8_t* __restrict__ hz, uint8_t* __restrict__ hh, uint8_t* __restrict__ hct,
                                                         uint32_t* __restrict__ hatt, const uint8_t* __restrict__ zp,
                                                         const uint8_t* __restrict__ h, const uint8_t* __restrict__ ct,
-                                                        const uint32_t* __restrict__ att, const uint32_t* __restrict__ list,
-                                                        uint32_t n, uint32_t zb, uint32_t hb) {
+                                                        const uint32_t* __restrict__ att, const uint32_t* __restrict__ done_list,
+                                                        const RoundCtl* __restrict__ ctl, uint32_t round, uint32_t zb, uint32_t hb) {
+    // round r finished the done-list entries [done_snap[r-1], done_snap[r]); both were written by plan_kernel launches
+    // that precede this kernel in stream order (the copy stream waits on an event recorded after round r)
+    const uint32_t lo = round == 0 ? 0u : ctl->done_snap[(round - 1) & 63], n = ctl->done_snap[round & 63] - lo;
+    const uint32_t* __restrict__ list = done_list + lo;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t nv = zb >> 4;
@@ -779,122 +760,145 @@ __global__ void __launch_bounds__(512, 4) drain_kernel(uint8_t* __restrict__ hz,
 }
 
 // ---------------------------------------------------------------------------------------
+// Round control (device side of the rejection loop)
+// ---------------------------------------------------------------------------------------
+// slots per item for a round of n items: 1 while the GPU is saturated by distinct items, then fill up to the target
+__device__ __forceinline__ uint32_t spec_policy(const RoundCtl* ctl, uint32_t n) {
+    if (n == 0 || n >= ctl->spec_target) return 1;
+    const uint32_t room = (ctl->slot_cap < ctl->spec_target ? ctl->slot_cap : ctl->spec_target) / n;
+    return room < 1 ? 1 : (room > ctl->spec_max ? ctl->spec_max : room);
+}
+
+// start of a batch: active list 0 = all items, round 0 planned
+__global__ void sign_begin_kernel(RoundCtl* __restrict__ ctl, uint32_t* __restrict__ active0, uint32_t n, uint32_t slot_cap,
+                                  uint32_t spec_target, uint32_t spec_max) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) active0[t] = t;
+    if (t == 0) {
+        ctl->slot_cap = slot_cap; ctl->spec_target = spec_target; ctl->spec_max = spec_max;
+        ctl->n_active = n; ctl->cur = 0;
+        const uint32_t sp = spec_policy(ctl, n);
+        ctl->spec = sp; ctl->n_slots = n * sp;
+        ctl->next_count = 0; ctl->ctr_core = 0; ctl->ctr_tail = 0; ctl->done = 0; ctl->rounds = 0; ctl->total_slots = 0;
+    }
+}
+
+// end of round `round`: the re-queued items become the next round
+__global__ void plan_kernel(RoundCtl* __restrict__ ctl, uint32_t round) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (ctl->n_active != 0) { ctl->rounds += 1; ctl->total_slots += ctl->n_slots; }
+    ctl->done_snap[round & 63] = ctl->done;
+    const uint32_t n = ctl->next_count;
+    const uint32_t sp = spec_policy(ctl, n);
+    ctl->n_active = n; ctl->spec = sp; ctl->n_slots = n * sp; ctl->cur ^= 1u;
+    ctl->next_count = 0; ctl->ctr_core = 0; ctl->ctr_tail = 0;
+}
+
+// the first 16 words of the round state into mapped pinned host memory: posted PCIe writes, so the host never
+// queues a D2H copy behind bulk signature transfers
+__global__ void publish_ctl_kernel(volatile uint32_t* host_dst, const RoundCtl* ctl) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(ctl);
+    if (threadIdx.x < 16) host_dst[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
-cudaError_t launch_sign_init(uint64_t* mu, uint64_t* rhop, uint16_t* kappa, const uint8_t* tr, const uint8_t* key,
+cudaError_t launch_sign_begin(const SignBufs& b, uint32_t n, uint32_t slot_cap, uint32_t spec_target, uint32_t spec_max, cudaStream_t st) {
+    sign_begin_kernel<<<(n + 255) / 256, 256, 0, st>>>(b.ctl, b.active[0], n, slot_cap, spec_target, spec_max);
+    return cudaGetLastError();
+}
+cudaError_t launch_plan(RoundCtl* ctl, uint32_t round, cudaStream_t st) {
+    plan_kernel<<<1, 32, 0, st>>>(ctl, round);
+    return cudaGetLastError();
+}
+cudaError_t launch_publish_ctl(uint32_t* host_dst_dev, const RoundCtl* ctl, cudaStream_t st) {
+    publish_ctl_kernel<<<1, 32, 0, st>>>(host_dst_dev, ctl);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sign_init(uint64_t* mu, uint64_t* rhop, uint16_t* kappa, const uint8_t* tr, const uint8_t* key, size_t key_stride,
                              const uint8_t* msgs, const uint64_t* offsets, uint32_t n, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    sign_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(mu, rhop, kappa, tr, key, msgs, offsets, n);
+    sign_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(mu, rhop, kappa, tr, key, key_stride, msgs, offsets, n);
     return cudaGetLastError();
 }
 
 template <int L, int G1B>
-static cudaError_t launch_expand_mask_t(int32_t* y, const uint64_t* rhop, const uint16_t* kappa, const uint32_t* active,
-                                        uint32_t n_slots, uint32_t spec, cudaStream_t st) {
+static cudaError_t launch_expand_mask_t(const SignBufs& b, uint32_t cap_slots, cudaStream_t st) {
     constexpr int ROW = 32 * (G1B + 1) + 16;
     constexpr size_t smem = (size_t)4 * 32 * ROW;
     auto kern = expand_mask_kernel<L, G1B>;
     static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
     if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(smem), configured); e != cudaSuccess) return e;
-    uint32_t n_polys = n_slots * L;
-    unsigned grid = (n_polys + 127) / 128;
-    const unsigned cap = (unsigned)overlap_knob("DIL_EM_CTAS", 0) * 148u;   // 0: uncapped (one chunk per warp)
-    if (cap && grid > cap) grid = cap;
-    kern<<<grid, 128, smem, st>>>(y, rhop, kappa, active, n_slots, spec);
+    const uint32_t n_polys = cap_slots * L;
+    kern<<<(n_polys + 127) / 128, 128, smem, st>>>(b.y, b.rhop, b.kappa, b.active[0], b.active[1], b.ctl);
     return cudaGetLastError();
 }
 
-cudaError_t launch_expand_mask(int level, int32_t* y, const uint64_t* rhop, const uint16_t* kappa, const uint32_t* active,
-                               uint32_t n_slots, uint32_t spec, cudaStream_t st) {
-    if (n_slots == 0) return cudaSuccess;
+cudaError_t launch_expand_mask(int level, const SignBufs& b, uint32_t cap_slots, cudaStream_t st) {
+    if (cap_slots == 0) return cudaSuccess;
     switch (level) {
-        case 2: return launch_expand_mask_t<4, 17>(y, rhop, kappa, active, n_slots, spec, st);
-        case 3: return launch_expand_mask_t<5, 19>(y, rhop, kappa, active, n_slots, spec, st);
-        case 5: return launch_expand_mask_t<7, 19>(y, rhop, kappa, active, n_slots, spec, st);
+        case 2: return launch_expand_mask_t<4, 17>(b, cap_slots, st);
+        case 3: return launch_expand_mask_t<5, 19>(b, cap_slots, st);
+        case 5: return launch_expand_mask_t<7, 19>(b, cap_slots, st);
     }
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_pack_w1(int level, uint32_t* w1p, const int32_t* w, uint32_t n_slots, cudaStream_t st) {
-    if (n_slots == 0) return cudaSuccess;
-    const LevelParams P = level_params(level);
-    size_t n_groups = (size_t)n_slots * P.k * (N / 16);
-    unsigned grid = (unsigned)((n_groups + 255) / 256);
-    if (level == 2) pack_w1_kernel<(Q_I - 1) / 88><<<grid, 256, 0, st>>>(w1p, w, n_groups);
-    else pack_w1_kernel<(Q_I - 1) / 32><<<grid, 256, 0, st>>>(w1p, w, n_groups);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_drain(uint8_t* hz, uint8_t* hh, uint8_t* hct, uint32_t* hatt, const uint8_t* zp, const uint8_t* h,
-                         const uint8_t* ct, const uint32_t* att, const uint32_t* list, uint32_t n, uint32_t zb, uint32_t hb,
-                         cudaStream_t st) {
-    if (n == 0) return cudaSuccess;
+cudaError_t launch_drain(uint8_t* hz, uint8_t* hh, uint8_t* hct, uint32_t* hatt, const SignBufs& b, uint32_t round, uint32_t zb,
+                         uint32_t hb, cudaStream_t st) {
     // A handful of 16-warp CTAs, each asking for enough (unused) dynamic shared memory that the shared-memory
     // using signing kernels cannot be co-resident: the drain owns its few SMs instead of slowing every SM's
-    // memory pipeline with PCIe-paced stores.  Launched right after a round's stream synchronisation, i.e.
-    // when the SMs are empty.  DIL_DRAIN_CTAS / DIL_DRAIN_SMEM_KB are tuning knobs.
-    static int ctas = -1, smem_kb = -1;
-    if (ctas < 0) {
-        const char* e = std::getenv("DIL_DRAIN_SMEM_KB");
-        smem_kb = (e && std::atoi(e) >= 0) ? std::atoi(e) : 200;
-        if (smem_kb > 226) smem_kb = 226;
-        e = std::getenv("DIL_DRAIN_CTAS");
-        ctas = (e && std::atoi(e) > 0) ? std::atoi(e) : 4;
-    }
+    // memory pipeline with PCIe-paced stores (thin many-CTA drains cost the signing kernels 20 %).
+    constexpr int CTAS = 4, SMEM_KB = 200;
     static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
-    if (cudaError_t e = ensure_dyn_smem(drain_kernel, (size_t)smem_kb * 1024, configured); e != cudaSuccess) return e;
-    unsigned grid = (n + 15) / 16 < (unsigned)ctas ? (n + 15) / 16 : (unsigned)ctas;
-    drain_kernel<<<grid, 512, (size_t)smem_kb * 1024, st>>>(hz, hh, hct, hatt, zp, h, ct, att, list, n, zb, hb);
+    if (cudaError_t e = ensure_dyn_smem(drain_kernel, (size_t)SMEM_KB * 1024, configured); e != cudaSuccess) return e;
+    drain_kernel<<<CTAS, 512, (size_t)SMEM_KB * 1024, st>>>(hz, hh, hct, hatt, b.zp, b.h_out, reinterpret_cast<const uint8_t*>(b.ct_out),
+                                                            b.attempts, b.done_list, b.ctl, round, zb, hb);
     return cudaGetLastError();
 }
 
-cudaError_t launch_challenge(int level, int8_t* c, uint64_t* ct_slot, const uint64_t* mu, const uint64_t* w1p,
-                             const uint32_t* active, uint32_t n_slots, uint32_t spec, cudaStream_t st) {
-    if (n_slots == 0) return cudaSuccess;
+cudaError_t launch_challenge(int level, const SignBufs& b, uint32_t cap_slots, cudaStream_t st) {
+    if (cap_slots == 0) return cudaSuccess;
     // 64-thread CTAs: 1024 CTAs for a 65536-slot round spread evenly over 148 SMs
-    unsigned grid = (n_slots + CH_THREADS - 1) / CH_THREADS;
-    const unsigned ccap = (unsigned)overlap_knob("DIL_CH_CTAS", 0) * 148u;
-    if (ccap && grid > ccap) grid = ccap;
+    const unsigned grid = (cap_slots + CH_THREADS - 1) / CH_THREADS;
     switch (level) {
-        case 2: challenge_kernel<4, 192, 39><<<grid, CH_THREADS, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
-        case 3: challenge_kernel<6, 128, 49><<<grid, CH_THREADS, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
-        case 5: challenge_kernel<8, 128, 60><<<grid, CH_THREADS, 0, st>>>(c, ct_slot, mu, w1p, active, n_slots, spec); break;
+        case 2: challenge_kernel<4, 192, 39><<<grid, CH_THREADS, 0, st>>>(b.c, b.ct_slot, b.mu, b.w1p, b.active[0], b.active[1], b.ctl); break;
+        case 3: challenge_kernel<6, 128, 49><<<grid, CH_THREADS, 0, st>>>(b.c, b.ct_slot, b.mu, b.w1p, b.active[0], b.active[1], b.ctl); break;
+        case 5: challenge_kernel<8, 128, 60><<<grid, CH_THREADS, 0, st>>>(b.c, b.ct_slot, b.mu, b.w1p, b.active[0], b.active[1], b.ctl); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
-template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA, int WARPS, int CTAS>
-static cudaError_t launch_sign_tail_w(int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat, int32_t* w,
-                                      const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st, uint32_t* work_ctr,
-                                      const ResolveArgs& ra) {
+static ResolveArgs resolve_args(const SignBufs& b) {
+    ResolveArgs ra;
+    ra.zp = b.zp; ra.h_out = b.h_out; ra.ct_out = b.ct_out; ra.attempts = b.attempts; ra.kappa = b.kappa;
+    ra.active0 = b.active[0]; ra.active1 = b.active[1]; ra.ctl = b.ctl; ra.ct_slot = b.ct_slot;
+    ra.done_list = b.track_done ? b.done_list : nullptr;
+    return ra;
+}
+
+// transform-only tail (any eta): one 24-warp CTA per SM
+template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA>
+static cudaError_t launch_sign_tail_t(const SignBufs& b, const int32_t* key_hat, uint32_t cap_slots, int sm_count, cudaStream_t st) {
+    constexpr int WARPS = 24, CTAS = 1;
     constexpr int ZB = L * 32 * ((G1 == (1 << 17) ? 17 : 19) + 1);
     constexpr size_t smem = (size_t)((L + 2 * K) * N + WARPS * SCRATCH_WORDS + WARPS * K * 8) * 4 + (size_t)WARPS * ZB;
     auto kern = sign_tail_kernel<K, L, G1, G2, BETA, OMEGA, WARPS, CTAS>;
     static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
     if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(smem), configured); e != cudaSuccess) return e;
-    unsigned want = (n_slots + WARPS - 1) / WARPS;
+    unsigned want = (cap_slots + WARPS - 1) / WARPS;
     unsigned cap = (unsigned)sm_count * CTAS;
-    kern<<<want < cap ? want : cap, WARPS * 32, smem, st>>>(y, h_slot, accepted, key_hat, w, c, n_slots, work_ctr, ra);
+    kern<<<want < cap ? want : cap, WARPS * 32, smem, st>>>(b.y, b.h_slot, b.accepted, key_hat, b.w, b.c, resolve_args(b));
     return cudaGetLastError();
 }
 
-template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA>
-static cudaError_t launch_sign_tail_t(int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat, int32_t* w,
-                                      const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st, uint32_t* work_ctr,
-                                      const ResolveArgs& ra) {
-    // one 24-warp CTA per SM is marginally faster than three 8-warp CTAs (DIL_TAIL_WARPS=8 selects the latter)
-    static int big = -1;
-    if (big < 0) { const char* e = std::getenv("DIL_TAIL_WARPS"); big = (e && std::atoi(e) == 8) ? 0 : 1; }
-    if (overlap_knob("DIL_TAIL_HALF", 0)) return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 12, 1>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr, ra);
-    if (big) return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 24, 1>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr, ra);
-    return launch_sign_tail_w<K, L, G1, G2, BETA, OMEGA, 8, 3>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr, ra);
-}
-
 template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA, int TAU, int ETA>
-static cudaError_t launch_sign_tail_sparse(int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat,
-                                           const int8_t* key_small, int32_t* w, const int8_t* c, uint32_t n_slots, int sm_count,
-                                           cudaStream_t st, uint32_t* work_ctr, const ResolveArgs& ra) {
+static cudaError_t launch_sign_tail_sparse(const SignBufs& b, const int32_t* key_hat, const int8_t* key_small, uint32_t cap_slots,
+                                           int sm_count, cudaStream_t st) {
     constexpr int WARPS = 24;
     constexpr size_t smem = (size_t)(K * N + WARPS * SCRATCH_WORDS + WARPS * K * 8) * 4 + (size_t)WARPS * 64 * 2 +
                             (size_t)(L + K) * 2 * 8 * 256;
@@ -902,79 +906,45 @@ static cudaError_t launch_sign_tail_sparse(int32_t* y, uint8_t* h_slot, uint8_t*
     auto kern = sign_tail_sparse_kernel<K, L, G1, G2, BETA, OMEGA, TAU, ETA, WARPS>;
     static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
     if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(smem), configured); e != cudaSuccess) return e;
-    unsigned want = (n_slots + WARPS - 1) / WARPS;
+    unsigned want = (cap_slots + WARPS - 1) / WARPS;
     unsigned cap = (unsigned)sm_count;
-    kern<<<want < cap ? want : cap, WARPS * 32, smem, st>>>(y, h_slot, accepted, key_hat, key_small, w, c, n_slots, work_ctr, ra);
+    kern<<<want < cap ? want : cap, WARPS * 32, smem, st>>>(b.y, b.h_slot, b.accepted, key_hat, key_small, b.w, b.c, resolve_args(b));
     return cudaGetLastError();
 }
 
-// key_small != nullptr selects the sparse-product tail (default); DIL_TAIL_SPARSE=0 or a null key_small the
-// transform-only tail
-cudaError_t launch_sign_tail(int level, int32_t* y, uint8_t* h_slot, uint8_t* accepted, const int32_t* key_hat,
-                             int32_t* w, const int8_t* c, uint32_t n_slots, int sm_count, cudaStream_t st,
-                             uint32_t* work_ctr, const TailResolve* fused, const int8_t* key_small) {
-    if (n_slots == 0) return cudaSuccess;
-    ResolveArgs ra;
-    if (fused != nullptr) {
-        ra.zp = fused->zp; ra.h_out = fused->h_out; ra.ct_out = fused->ct_out; ra.attempts = fused->attempts; ra.kappa = fused->kappa;
-        ra.next_active = fused->next_active; ra.next_count = fused->next_count; ra.ct_slot = fused->ct_slot; ra.active = fused->active;
-        ra.done_list = fused->done_list;
-    }
-    static int sparse = -1;
-    if (sparse < 0) { const char* e = std::getenv("DIL_TAIL_SPARSE"); sparse = (e && std::atoi(e) == 0) ? 0 : 1; }
-    if (sparse && key_small != nullptr) {
+// key_small != nullptr selects the sparse-product tail where it exists (eta = 2); a null key_small the transform-only tail
+cudaError_t launch_sign_tail(int level, const SignBufs& b, const int32_t* key_hat, const int8_t* key_small, uint32_t cap_slots,
+                             int sm_count, cudaStream_t st) {
+    if (cap_slots == 0) return cudaSuccess;
+    if (key_small != nullptr) {
         switch (level) {
-            case 2: return launch_sign_tail_sparse<4, 4, 1 << 17, (Q_I - 1) / 88, 78, 80, 39, 2>(y, h_slot, accepted, key_hat, key_small, w, c, n_slots, sm_count, st, work_ctr, ra);
+            case 2: return launch_sign_tail_sparse<4, 4, 1 << 17, (Q_I - 1) / 88, 78, 80, 39, 2>(b, key_hat, key_small, cap_slots, sm_count, st);
             case 3: break;   // eta = 4: nibble sums would carry; the transform tail below handles level 3
-            case 5: return launch_sign_tail_sparse<8, 7, 1 << 19, (Q_I - 1) / 32, 120, 75, 60, 2>(y, h_slot, accepted, key_hat, key_small, w, c, n_slots, sm_count, st, work_ctr, ra);
+            case 5: return launch_sign_tail_sparse<8, 7, 1 << 19, (Q_I - 1) / 32, 120, 75, 60, 2>(b, key_hat, key_small, cap_slots, sm_count, st);
             default: return cudaErrorInvalidValue;
         }
     }
     switch (level) {
-        case 2: return launch_sign_tail_t<4, 4, 1 << 17, (Q_I - 1) / 88, 78, 80>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr, ra);
-        case 3: return launch_sign_tail_t<6, 5, 1 << 19, (Q_I - 1) / 32, 196, 55>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr, ra);
-        case 5: return launch_sign_tail_t<8, 7, 1 << 19, (Q_I - 1) / 32, 120, 75>(y, h_slot, accepted, key_hat, w, c, n_slots, sm_count, st, work_ctr, ra);
+        case 2: return launch_sign_tail_t<4, 4, 1 << 17, (Q_I - 1) / 88, 78, 80>(b, key_hat, cap_slots, sm_count, st);
+        case 3: return launch_sign_tail_t<6, 5, 1 << 19, (Q_I - 1) / 32, 196, 55>(b, key_hat, cap_slots, sm_count, st);
+        case 5: return launch_sign_tail_t<8, 7, 1 << 19, (Q_I - 1) / 32, 120, 75>(b, key_hat, cap_slots, sm_count, st);
     }
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_resolve(int level, uint8_t* zp, uint8_t* h_out, uint64_t* ct_out, uint32_t* attempts, uint16_t* kappa,
-                           uint32_t* next_active, uint32_t* next_count, const int32_t* zslot, const uint8_t* h_slot,
-                           const uint64_t* ct_slot, const uint8_t* accepted, const uint32_t* active, uint32_t n_items,
-                           uint32_t spec, uint32_t* done_list, cudaStream_t st) {
-    if (n_items == 0) return cudaSuccess;
-    unsigned grid = (n_items + 7) / 8;
+cudaError_t launch_resolve(int level, const SignBufs& b, uint32_t cap_items, cudaStream_t st) {
+    if (cap_items == 0) return cudaSuccess;
+    const unsigned grid = (cap_items + 7) / 8;
+    const ResolveArgs ra = resolve_args(b);
     switch (level) {
-        case 2: resolve_kernel<4, 17, 84><<<grid, 256, 0, st>>>(zp, h_out, ct_out, attempts, kappa, next_active, next_count, zslot, h_slot, ct_slot, accepted, active, n_items, spec, done_list); break;
-        case 3: resolve_kernel<5, 19, 61><<<grid, 256, 0, st>>>(zp, h_out, ct_out, attempts, kappa, next_active, next_count, zslot, h_slot, ct_slot, accepted, active, n_items, spec, done_list); break;
-        case 5: resolve_kernel<7, 19, 83><<<grid, 256, 0, st>>>(zp, h_out, ct_out, attempts, kappa, next_active, next_count, zslot, h_slot, ct_slot, accepted, active, n_items, spec, done_list); break;
+        case 2: resolve_kernel<4, 17, 84><<<grid, 256, 0, st>>>(ra, b.y, b.h_slot, b.accepted); break;
+        case 3: resolve_kernel<5, 19, 61><<<grid, 256, 0, st>>>(ra, b.y, b.h_slot, b.accepted); break;
+        case 5: resolve_kernel<7, 19, 83><<<grid, 256, 0, st>>>(ra, b.y, b.h_slot, b.accepted); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
-}  // namespace dil
-
-namespace dil {
-__global__ void iota_kernel(uint32_t* dst, uint32_t n) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) dst[t] = t;
-}
-// publish the next round's item count into mapped pinned host memory: a posted PCIe write, so the
-// host never queues a D2H copy behind the bulk signature transfers of the previous chunk
-__global__ void publish_count_kernel(volatile uint32_t* host_dst, const uint32_t* src) {
-    *host_dst = *src;
-    __threadfence_system();
-}
-cudaError_t launch_publish_count(uint32_t* host_dst_dev, const uint32_t* src, cudaStream_t st) {
-    publish_count_kernel<<<1, 1, 0, st>>>(host_dst_dev, src);
-    return cudaGetLastError();
-}
-cudaError_t launch_iota(uint32_t* dst, uint32_t n, cudaStream_t st) {
-    if (n == 0) return cudaSuccess;
-    iota_kernel<<<(n + 255) / 256, 256, 0, st>>>(dst, n);
-    return cudaGetLastError();
-}
 }  // namespace dil
 
 // =======================================================================================

@@ -297,6 +297,21 @@ class SignKey:
     def last_rounds(self):
         return int(self.engine._lib.dil_sign_last_rounds(self._h))
 
+    @property
+    def last_slots(self):
+        """Signing attempts (slots) the last batch executed, speculative ones included."""
+        return int(self.engine._lib.dil_sign_last_slots(self._h))
+
+    class _Tuning(ctypes.Structure):   # dil_sign_tuning
+        _fields_ = [("spec_target", ctypes.c_uint32), ("spec_max", ctypes.c_uint32), ("dev_chunk", ctypes.c_size_t),
+                    ("host_chunk", ctypes.c_size_t), ("host_copy_path", ctypes.c_int), ("unfused_mask", ctypes.c_int)]
+
+    def set_tuning(self, spec_target=0, spec_max=0, dev_chunk=0, host_chunk=0, host_copy_path=False, unfused_mask=False):
+        """Scheduler knobs of this key (dil_sign_key_set_tuning); zeros restore the defaults.  Results never change."""
+        t = self._Tuning(int(spec_target), int(spec_max), int(dev_chunk), int(host_chunk), int(bool(host_copy_path)),
+                         int(bool(unfused_mask)))
+        self.engine._check(self.engine._lib.dil_sign_key_set_tuning(self._h, ctypes.byref(t)), "dil_sign_key_set_tuning")
+
     PROFILE_CLASSES = ("init", "expand_mask", "signcore", "pack_w1", "challenge", "tail", "resolve")
 
     def set_profile(self, on=True):

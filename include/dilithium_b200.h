@@ -37,7 +37,10 @@
  *   - every function returns 0 on success or a negative dil_status; there is no CPU fallback:
  *     without a usable CUDA device dil_engine_create fails with DIL_ERR_NO_DEVICE.
  *   - an engine handle is bound to one device; calls on one handle from several threads are
- *     safe as long as they use different streams for overlapping buffers.
+ *     safe as long as they use different streams for overlapping buffers.  Key handles own
+ *     internal workspaces: calls on one key are serialised by the library (host side by a
+ *     per-key lock, device side by an event the next user of the workspace waits on), so
+ *     _dev calls on one key from several streams are legal and simply run back to back.
  */
 #ifndef DILITHIUM_B200_H
 #define DILITHIUM_B200_H
@@ -136,10 +139,22 @@ int dil_sign_key_destroy(dil_engine_t *e, dil_sign_key_t *k);
  * results are identical either way.  attempts may be NULL. */
 int dil_sign_batch_host(dil_engine_t *e, dil_sign_key_t *k, const uint8_t *msgs, const uint64_t *offsets, size_t n,
                         uint8_t *z, uint8_t *h, uint8_t *ctilde, uint32_t *attempts);
-/* device pointers (d_z 16-byte, d_ctilde 8-byte aligned); synchronises the stream once per rejection round */
+/* device pointers (d_z 16-byte, d_ctilde 8-byte aligned).  The rejection loop runs on the device: the call enqueues the
+ * expected number of rounds at once and synchronises the stream once at the end (again only if items are still active). */
 int dil_sign_batch_dev(dil_engine_t *e, dil_sign_key_t *k, const uint8_t *d_msgs, const uint64_t *d_offsets, size_t n,
                        uint8_t *d_z, uint8_t *d_h, uint8_t *d_ctilde, uint32_t *d_attempts, void *stream);
 uint32_t dil_sign_last_rounds(const dil_sign_key_t *k);   /* rejection rounds of the last batch */
+uint64_t dil_sign_last_slots(const dil_sign_key_t *k);    /* signing attempts (slots) the last batch executed, speculative ones included */
+/* Per-key tuning of the batch scheduler; zero fields keep the defaults.  Results never depend on these. */
+typedef struct {
+    uint32_t spec_target;    /* straggler speculation: rounds with fewer items are filled up to this many attempt slots (32768) */
+    uint32_t spec_max;       /* ... with at most this many consecutive attempts per item (32, the maximum)                    */
+    size_t dev_chunk;        /* dil_sign_batch_dev signs larger requests in pieces of this many messages (2^20)               */
+    size_t host_chunk;       /* the same for the streaming path of dil_sign_batch_host (2^18)                                 */
+    int host_copy_path;      /* non-zero: dil_sign_batch_host always uses chunked copy-engine transfers                       */
+    int unfused_mask;        /* non-zero: ExpandMask and the sign core run as two kernels instead of the fused mask_core      */
+} dil_sign_tuning;
+int dil_sign_key_set_tuning(dil_sign_key_t *k, const dil_sign_tuning *t);   /* t == NULL restores the defaults */
 /* optional device timing of the pipeline's kernel classes (CUDA events on the launching stream):
    index 0 init (mu, rho'), 1 ExpandMask, 2 fused sign core, 3 w1 pack, 4 challenge, 5 tail, 6 resolve;
    ms[8] = summed kernel time of the last batch, units[8] = slots (attempts) each class processed */

@@ -66,23 +66,22 @@ def test_sign_large_batch_properties(eng, oracle):
     assert np.array_equal(z, z2) and np.array_equal(h, h2) and np.array_equal(c, c2) and np.array_equal(att, att2)
 
 
-def test_sign_streaming_host_path(eng, monkeypatch):
+def test_sign_streaming_host_path(eng):
     """dil_sign_batch_host with pinned output buffers streams finished signatures out round by round
     (drain_kernel into mapped host memory); results must equal the pageable-buffer path (chunked
-    copy-engine transfers) bit for bit, also when the batch is split (DIL_SIGN_CHUNK) and for ragged sizes."""
+    copy-engine transfers) bit for bit, also when the batch is split (tuning host_chunk) and for ragged sizes."""
     import dilithium_b200 as d
     for level, n in ((2, 20000), (3, 3001), (5, 1025), (2, 1), (2, 0)):
         K = ol.kat(level)
         key = d.SignKey(eng, level, K["rho"][1], K["k"][1], K["tr"][1], K["s1"][1], K["s2"][1], K["t0"][1])
         msgs = [int(i).to_bytes(4, "little") * (1 + i % 9) for i in range(n)]
         ref = key.sign(msgs)
-        monkeypatch.delenv("DIL_SIGN_CHUNK", raising=False)
         got = [np.array(a) for a in key.sign(msgs, pinned=True)]
-        monkeypatch.setenv("DIL_SIGN_CHUNK", "4096")
+        key.set_tuning(host_chunk=4096)
         got2 = [np.array(a) for a in key.sign(msgs, pinned=True)]
-        monkeypatch.setenv("DIL_SIGN_DRAIN", "0")
+        key.set_tuning(host_chunk=4096, host_copy_path=True)
         got3 = [np.array(a) for a in key.sign(msgs, pinned=True)]
-        monkeypatch.delenv("DIL_SIGN_DRAIN")
+        key.set_tuning()
         for name, r, a, b, c in zip(("z", "h", "c", "att"), ref, got, got2, got3):
             assert np.array_equal(r, a), (level, n, name, "streaming")
             assert np.array_equal(r, b), (level, n, name, "streaming, split batch")
@@ -90,7 +89,7 @@ def test_sign_streaming_host_path(eng, monkeypatch):
         key.close()
 
 
-def test_sign_dev_split_batch(eng, monkeypatch):
+def test_sign_dev_split_batch(eng):
     """dil_sign_batch_dev signs very large batches in pieces (bounded workspace); with a small piece size the
     result must equal the single-piece result bit for bit."""
     import torch
@@ -101,16 +100,39 @@ def test_sign_dev_split_batch(eng, monkeypatch):
     msgs = torch.randint(0, 256, (n * 24,), dtype=torch.uint8, device="cuda")
     off = torch.arange(n + 1, dtype=torch.int64, device="cuda") * 24
     outs = []
-    for chunk in (None, "2048"):
-        if chunk:
-            monkeypatch.setenv("DIL_SIGN_DEV_CHUNK", chunk)
+    for chunk in (0, 2048):
+        key.set_tuning(dev_chunk=chunk)
         z = torch.zeros((n, key.z_bytes), dtype=torch.uint8, device="cuda"); h = torch.zeros((n, key.h_bytes), dtype=torch.uint8, device="cuda")
         c = torch.zeros((n, 32), dtype=torch.uint8, device="cuda"); att = torch.zeros(n, dtype=torch.int32, device="cuda")
         key.sign_dev(msgs, off, n, z, h, c, att)
         torch.cuda.synchronize()
         outs.append((z, h, c, att))
-    monkeypatch.delenv("DIL_SIGN_DEV_CHUNK")
+    key.set_tuning()
     for a, b in zip(*outs):
         assert torch.equal(a, b)
     assert int(outs[0][3].min()) >= 1
+    key.close()
+
+
+def test_sign_scheduler_tuning_does_not_change_results(eng):
+    """The round scheduler lives on the device (RoundCtl): whatever the speculation policy, the smallest accepted
+    kappa wins, so signatures and attempt counts must not depend on it."""
+    import dilithium_b200 as d
+    level, n = 2, 3000
+    K = ol.kat(level)
+    key = d.SignKey(eng, level, K["rho"][3], K["k"][3], K["tr"][3], K["s1"][3], K["s2"][3], K["t0"][3])
+    msgs = [int(i).to_bytes(4, "little") * (1 + i % 5) for i in range(n)]
+    ref = key.sign(msgs)
+    rounds = {}
+    for name, kw in (("no speculation", dict(spec_target=1)), ("two slots per item", dict(spec_target=1 << 20, spec_max=2)),
+                     ("small target", dict(spec_target=512, spec_max=7)), ("always 32 slots", dict(spec_target=1 << 22, spec_max=32))):
+        key.set_tuning(**kw)
+        got = key.sign(msgs)
+        rounds[name] = (key.last_rounds, key.last_slots)
+        for f, a, b in zip(("z", "h", "c", "att"), ref, got):
+            assert np.array_equal(a, b), (name, f)
+    # without speculation a batch needs as many rounds as its unluckiest message needs attempts
+    assert rounds["no speculation"][0] == int(ref[3].max())
+    assert rounds["no speculation"][1] == int(ref[3].sum())
+    assert rounds["always 32 slots"][0] <= 2
     key.close()

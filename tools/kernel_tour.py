@@ -27,6 +27,8 @@ K = ol.kat(2)
 sk = d.SignKey(eng, 2, K["rho"][0], K["k"][0], K["tr"][0], K["s1"][0], K["s2"][0], K["t0"][0])
 vk = d.VerifyKey(eng, 2, K["rho"][0], K["t1"][0])
 msgs = [bytes([i & 255]) * 40 for i in range(64 if small else 4096)]
+if len(sys.argv) > 2:   # spec_target: small values force the non-speculative round kernels on a small batch
+    sk.set_tuning(spec_target=int(sys.argv[2]))
 z, h, c, att = sk.sign(msgs)
 assert vk.verify(msgs, z, h, c).all()
 # host path with pinned outputs: finished signatures are drained round by round (drain_kernel)

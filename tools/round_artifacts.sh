@@ -15,7 +15,7 @@ for k in expand_mask_kernel matvec_shared_kernel challenge_kernel sign_tail_spar
 done
 ncu --set full --clock-control none --import-source on -k regex:drain_kernel -c 1 -f -o $out/${tag}_drain_kernel python tools/e2e_sign_bench.py 2 65536 1 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:ntt_tma_kernel -c 2 -f -o $out/${tag}_ntt python tools/quick_bench.py > /dev/null 2>&1
-DIL_SPEC_TARGET=16 compute-sanitizer --tool memcheck python tools/kernel_tour.py small > $out/${tag}_sanitizer_memcheck.log 2>&1; tail -2 $out/${tag}_sanitizer_memcheck.log
-DIL_SPEC_TARGET=16 compute-sanitizer --tool racecheck python tools/kernel_tour.py small > $out/${tag}_sanitizer_racecheck.log 2>&1; tail -2 $out/${tag}_sanitizer_racecheck.log
+compute-sanitizer --tool memcheck python tools/kernel_tour.py small 16 > $out/${tag}_sanitizer_memcheck.log 2>&1; tail -2 $out/${tag}_sanitizer_memcheck.log
+compute-sanitizer --tool racecheck python tools/kernel_tour.py small 16 > $out/${tag}_sanitizer_racecheck.log 2>&1; tail -2 $out/${tag}_sanitizer_racecheck.log
 compute-sanitizer --tool memcheck python tools/kernel_tour.py small > $out/${tag}_sanitizer_memcheck_spec.log 2>&1; tail -1 $out/${tag}_sanitizer_memcheck_spec.log
 ls -la $out | tail -30
