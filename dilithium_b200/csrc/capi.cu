@@ -92,6 +92,7 @@ int dil_engine_destroy(dil_engine_t* e) {
     if (!e) return DIL_OK;
     {
         DeviceGuard g(e->device);
+        dil_internal_free_multi_sign(e);
         for (auto& p : e->staging)
             if (p) cudaFree(p);
         if (e->arena_done) cudaEventDestroy(e->arena_done);

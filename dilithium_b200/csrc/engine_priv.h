@@ -19,7 +19,10 @@ struct dil_engine {
     cudaStream_t copy_stream = nullptr;   // D2H of finished chunks overlaps compute of the next chunk
     cudaEvent_t arena_done = nullptr;     // recorded after the last kernel that uses staging[3] (multi-key verification arena)
     std::string last_error;
+    void* multi_sign[3] = {nullptr, nullptr, nullptr};   // per-level workspace of dil_sign_multi_* (sign_api.cu owns the type)
 };
+
+void dil_internal_free_multi_sign(dil_engine* e);   // sign_api.cu
 
 
 namespace dil {

@@ -91,6 +91,14 @@ cudaError_t launch_challenge(int level, const SignBufs& b, uint32_t cap_slots, c
 cudaError_t launch_sign_tail(int level, const SignBufs& b, const int32_t* key_hat, const int8_t* key_small, uint32_t cap_slots,
                              int sm_count, cudaStream_t st);
 cudaError_t launch_resolve(int level, const SignBufs& b, uint32_t cap_items, cudaStream_t st);
+// ---- one key per signature (dil_sign_multi_*) ----
+cudaError_t launch_unpack_keys(int level, int32_t* key_items, const uint8_t* s1p, const uint8_t* s2p, const uint8_t* t0p, size_t n,
+                               cudaStream_t st);
+cudaError_t launch_scale_inv256(int32_t* x, size_t n_polys, cudaStream_t st);
+cudaError_t launch_matvec_multi(int level, int32_t* wh, const int32_t* a_items, const int32_t* yh, const SignBufs& b, uint32_t cap_slots,
+                                cudaStream_t st);
+cudaError_t launch_pack_w1(int level, uint32_t* w1p, const int32_t* w, size_t n_slots, cudaStream_t st);
+cudaError_t launch_sign_tail_multi(int level, const SignBufs& b, const int32_t* key_items, uint32_t cap_slots, int sm_count, cudaStream_t st);
 cudaError_t launch_plan(RoundCtl* ctl, uint32_t round, cudaStream_t st);
 // copies round `round`'s finished signatures (done list entries [done_snap[round-1], done_snap[round])) to the host
 cudaError_t launch_drain(uint8_t* hz, uint8_t* hh, uint8_t* hct, uint32_t* hatt, const SignBufs& b, uint32_t round, uint32_t zb,

@@ -64,16 +64,27 @@ const int32_t zetas_barrett[256] = {
 #define Z64(i) Z16(i), Z16(i + 16), Z16(i + 32), Z16(i + 48)
     Z64(0), Z64(64), Z64(128), Z64(192)};
 
+// The reference reduces with a signed 64-bit % (ref_ntt.cpp:41-43) and therefore accepts ANY int32 coefficient, e.g.
+// unreduced sums of residues; the engine's lazy arithmetic expects representatives in (-Q, Q).  The shim brings
+// arbitrary inputs into that range on the host so that a reference caller can never get a silently wrong result.
+static void reduce_in(int32_t* dst, const int32_t* src) {
+    for (int i = 0; i < 256; i++) dst[i] = src[i] % (int32_t)dil::Q;   // C++ %: result in (-Q, Q)
+}
 void ntt(int32_t a[256]) {
+    reduce_in(a, a);
     int rc = dil_ntt_host(engine(), a, 1);
     if (rc) die("ntt", rc);
 }
 void invntt(int32_t a[256]) {
+    reduce_in(a, a);
     int rc = dil_invntt_host(engine(), a, 1);
     if (rc) die("invntt", rc);
 }
 void pointwise_barrett(int32_t c[256], const int32_t a[256], const int32_t b[256]) {
-    int rc = dil_pointwise_host(engine(), c, a, b, 1);
+    int32_t ra[256], rb[256];
+    reduce_in(ra, a);
+    reduce_in(rb, b);
+    int rc = dil_pointwise_host(engine(), c, ra, rb, 1);
     if (rc) die("pointwise_barrett", rc);
 }
 // The radix-2x2 schedule IS how the engine computes every transform (ntt_core.cuh); results

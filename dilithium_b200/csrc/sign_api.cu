@@ -8,6 +8,7 @@
 // of time and looks at the state once per burst of rounds.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -55,6 +56,11 @@ struct dil_sign_key {
     uint32_t last_rounds = 0;
     uint64_t last_slots = 0;
     dil_sign_tuning tune{};      // zero = defaults
+    // one key per signature (dil_sign_multi_*): per-item key material and the unfused core's intermediates
+    int32_t *a_items = nullptr, *key_items = nullptr, *yh = nullptr, *wh = nullptr;
+    size_t multi_cap = 0, multi_slots = 0;
+    uint8_t* multi_in = nullptr;   // host variant: staged rho | K | tr | s1 | s2 | t0 records
+    size_t multi_in_cap = 0;
     // optional per-kernel-class device timing (CUDA events on the launching stream)
     bool profile = false;
     cudaEvent_t ev[16] = {};
@@ -212,9 +218,15 @@ std::vector<double> expected_trajectory(const dil_sign_key* k, size_t n) {
     return tr;
 }
 
+// one key per signature: per-item tr / K (32-byte records) instead of the key handle's seeds
+struct MultiKeys {
+    const uint8_t *tr, *key;
+};
+
 // the round loop; all pointers are device pointers
 int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uint64_t* d_off, size_t n, uint8_t* d_zp,
-                uint8_t* d_h, uint8_t* d_ct, uint32_t* d_att, cudaStream_t st, const DrainTarget* drain = nullptr) {
+                uint8_t* d_h, uint8_t* d_ct, uint32_t* d_att, cudaStream_t st, const DrainTarget* drain = nullptr,
+                const MultiKeys* mk = nullptr) {
     const LevelParams& P = k->P;
     int rc = ensure_ws(e, k, n);
     if (rc) return rc;
@@ -238,7 +250,8 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
     const uint32_t cap_slots = (uint32_t)slots_for(k, n);
     CK(dil::launch_sign_begin(b, (uint32_t)n, cap_slots, spec_target(k), spec_max(k), st));
     PROF_BEGIN(0);
-    CK(dil::launch_sign_init(k->mu_d, k->rhop, k->kappa, k->seeds, k->seeds + 32, 0, d_msgs, d_off, (uint32_t)n, st));
+    if (mk) CK(dil::launch_sign_init(k->mu_d, k->rhop, k->kappa, mk->tr, mk->key, 32, d_msgs, d_off, (uint32_t)n, st));
+    else CK(dil::launch_sign_init(k->mu_d, k->rhop, k->kappa, k->seeds, k->seeds + 32, 0, d_msgs, d_off, (uint32_t)n, st));
     PROF_END(0);
     launches += 2;
     if (prof) {
@@ -256,7 +269,9 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
     const uint32_t T = spec_target(k), M = spec_max(k);
     uint32_t enq = 0, seen = (uint32_t)n, seen_at = 0;   // last observed item count and the round it belongs to
     volatile uint32_t* hc = k->ctl_host;
-    int burst = prof ? 1 : (int)traj.size() + 1;
+    // per-item keys: the unfused core's stand-alone kernels take their sizes from the host, so every round is observed
+    const bool step = prof || mk != nullptr;
+    int burst = step ? 1 : (int)traj.size() + 1;
     for (;;) {
         for (int i = 0; i < burst; i++, enq++) {
             uint32_t ci = seen;   // hint: items of this round
@@ -268,7 +283,21 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
             }
             const uint64_t cs64 = ci >= T ? ci : ((uint64_t)ci * M < cap_slots ? (uint64_t)ci * M : cap_slots);
             const uint32_t cs = (uint32_t)(cs64 < ci ? ci : cs64);   // hint: slots of this round
-            if (!k->tune.unfused_mask) {
+            if (mk) {
+                // exact size of this round (the host saw the state after the previous one)
+                const uint32_t sp = seen >= T ? 1u : (uint32_t)std::min<uint64_t>(std::max<uint64_t>(std::min<uint64_t>(cap_slots, T) / seen, 1), M);
+                const size_t ns = (size_t)seen * sp;
+                PROF_BEGIN(1);
+                CK(dil::launch_expand_mask(P.level, b, (uint32_t)ns, st));
+                PROF_END(1);
+                PROF_BEGIN(2);
+                CK(dil::launch_ntt_fwd(k->yh, k->y, ns * P.l, e->sm_count, st));
+                CK(dil::launch_matvec_multi(P.level, k->wh, k->a_items, k->yh, b, (uint32_t)ns, st));
+                CK(dil::launch_ntt_inv(k->w, k->wh, ns * P.k, e->sm_count, st));
+                CK(dil::launch_pack_w1(P.level, reinterpret_cast<uint32_t*>(k->w1p), k->w, ns, st));
+                PROF_END(2);
+                launches += 3;
+            } else if (!k->tune.unfused_mask) {
                 // ExpandMask, the transforms and the mat-vec in one kernel (mask_core.cu); timed as class 2
                 PROF_BEGIN(1);
                 PROF_END(1);
@@ -291,7 +320,8 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
             PROF_END(4);
             // rounds with one slot per item: the tail finishes or re-queues its item itself and resolve returns at once
             PROF_BEGIN(5);
-            CK(dil::launch_sign_tail(P.level, b, k->key_hat, k->key_small, cs, e->sm_count, st));
+            if (mk) CK(dil::launch_sign_tail_multi(P.level, b, k->key_items, cs, e->sm_count, st));
+            else CK(dil::launch_sign_tail(P.level, b, k->key_hat, k->key_small, cs, e->sm_count, st));
             PROF_END(5);
             PROF_BEGIN(6);
             // only a first round of >= spec_target items is known to run without speculation; later rounds decide on the device
@@ -305,6 +335,12 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
                 CK(dil::launch_drain(drain->z, drain->h, drain->ct, drain->att, b, enq, (uint32_t)(P.l * P.z_bytes),
                                      (uint32_t)(P.omega + P.k), drain->stream));
                 launches++;
+            }
+            if (step && !prof) {
+                CK(dil::launch_publish_ctl(k->ctl_host_dev, k->ctl, st));
+                CK(cudaStreamSynchronize(st));
+                seen = hc[0];
+                seen_at = enq + 1;
             }
             if (prof) {
                 // per-class device time of this round; the slots it processed = growth of total_slots
@@ -322,7 +358,7 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
                 seen_at = enq + 1;
             }
         }
-        if (!prof) {
+        if (!step) {
             CK(dil::launch_publish_ctl(k->ctl_host_dev, k->ctl, st));
             CK(cudaStreamSynchronize(st));
             seen = hc[0];
@@ -330,7 +366,7 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
         }
         if (seen == 0) break;
         if (enq > 4000) return fail_msg(e, DIL_ERR_CUDA, "sign: rejection loop did not terminate");
-        burst = prof ? 1 : 2;
+        burst = step ? 1 : 2;
     }
     if (drain) CK(cudaEventRecord(drain->idle, drain->stream));
     e->launches += launches;
@@ -596,6 +632,175 @@ int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs,
     if (rc) return rc;
     if (er2 != cudaSuccess) return fail(e, er2, "sign D2H sync");
     if (er3 != cudaSuccess) return fail(e, er3, "sign sync");
+    return DIL_OK;
+}
+
+// ---- one key per signature -------------------------------------------------------------------------------------
+// The reference's sign driver feeds rho, tr, K, s1, s2, t0 in front of EVERY message (rtl_tb/tb_sign_top.v:171-284), so
+// a batch may carry a different key per signature (e.g. all 100 KAT vectors of a level in one call).  The engine keeps
+// one workspace per level for this mode; key material is unpacked, transformed and ExpandA'd per item on the device.
+}  // extern "C"
+
+namespace {
+
+dil_sign_key* multi_ctx(dil_engine* e, int level) {
+    const int idx = level == 2 ? 0 : (level == 3 ? 1 : 2);
+    if (!e->multi_sign[idx]) {
+        dil_sign_key* k = new (std::nothrow) dil_sign_key();
+        if (!k) return nullptr;
+        k->P = dil::level_params(level);
+        k->device = e->device;
+        e->multi_sign[idx] = k;
+    }
+    return static_cast<dil_sign_key*>(e->multi_sign[idx]);
+}
+
+void free_multi(dil_sign_key* k) {
+    const LevelParams& P = k->P;
+    wipe_free(k->key_items, k->multi_cap * (size_t)(P.l + 2 * P.k) * 1024);
+    wipe_free(k->multi_in, k->multi_in_cap);
+    if (k->a_items) cudaFree(k->a_items);
+    if (k->yh) cudaFree(k->yh);
+    if (k->wh) cudaFree(k->wh);
+    k->a_items = k->key_items = k->yh = k->wh = nullptr;
+    k->multi_in = nullptr;
+    k->multi_cap = k->multi_slots = k->multi_in_cap = 0;
+}
+
+int ensure_multi(dil_engine* e, dil_sign_key* k, size_t n) {
+    const LevelParams& P = k->P;
+    const size_t slots = slots_for(k, n);
+    if (n <= k->multi_cap && slots <= k->multi_slots) return DIL_OK;
+    const size_t in_cap = k->multi_in_cap;
+    uint8_t* in = k->multi_in;
+    k->multi_in = nullptr;           // the input staging is managed separately
+    k->multi_in_cap = 0;
+    free_multi(k);
+    k->multi_in = in;
+    k->multi_in_cap = in_cap;
+    cudaError_t err = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+    A(dmalloc(&k->a_items, n * (size_t)P.k * P.l * 256));
+    A(dmalloc(&k->key_items, n * (size_t)(P.l + 2 * P.k) * 256));
+    A(dmalloc(&k->yh, slots * (size_t)P.l * 256));
+    A(dmalloc(&k->wh, slots * (size_t)P.k * 256));
+    if (err != cudaSuccess) {
+        free_multi(k);
+        return fail_msg(e, DIL_ERR_ALLOC, std::string("multi-key sign workspace: ") + cudaGetErrorString(err));
+    }
+    k->multi_cap = n;
+    k->multi_slots = slots;
+    return DIL_OK;
+}
+
+constexpr size_t MULTI_CHUNK = 65536;   // per-item A_hat is 16 / 30 / 56 KiB: 1 - 3.5 GiB per chunk
+
+// all pointers device pointers; key arrays hold n records
+int sign_multi_run(dil_engine* e, dil_sign_key* k, const uint8_t* d_rho, const uint8_t* d_key, const uint8_t* d_tr, const uint8_t* d_s1p,
+                   const uint8_t* d_s2p, const uint8_t* d_t0p, const uint8_t* d_msgs, const uint64_t* d_off, size_t n, uint8_t* d_z,
+                   uint8_t* d_h, uint8_t* d_ct, uint32_t* d_att, cudaStream_t st) {
+    const LevelParams& P = k->P;
+    const size_t zb = (size_t)P.l * P.z_bytes, hb = (size_t)P.omega + P.k, nkey = (size_t)P.l + 2 * P.k;
+    for (size_t lo = 0; lo < n;) {
+        const size_t m = n - lo <= MULTI_CHUNK + MULTI_CHUNK / 4 ? n - lo : MULTI_CHUNK;
+        int rc = ensure_multi(e, k, m);
+        if (rc) return rc;
+        // per item: A_hat = ExpandA(rho); (s1 | s2 | t0) unpacked, transformed, scaled by 256^-1 for the tail
+        CK(dil::launch_expand_a(k->a_items, d_rho + lo * 32, m, P.k, P.l, e->sm_count, st));
+        CK(dil::launch_unpack_keys(P.level, k->key_items, d_s1p + lo * P.l * P.s_bytes, d_s2p + lo * P.k * P.s_bytes,
+                                   d_t0p + lo * P.k * 416, m, st));
+        CK(dil::launch_ntt_fwd(k->key_items, k->key_items, m * nkey, e->sm_count, st));
+        CK(dil::launch_scale_inv256(k->key_items, m * nkey, st));
+        e->launches += 6;
+        MultiKeys mk{d_tr + lo * 32, d_key + lo * 32};
+        rc = sign_rounds(e, k, d_msgs, d_off + lo, m, d_z + lo * zb, d_h + lo * hb, d_ct + lo * 32, d_att + lo, st, nullptr, &mk);
+        if (rc) return rc;
+        lo += m;
+    }
+    return DIL_OK;
+}
+
+}  // namespace
+
+void dil_internal_free_multi_sign(dil_engine* e) {
+    for (auto& p : e->multi_sign) {
+        if (!p) continue;
+        dil_sign_key* k = static_cast<dil_sign_key*>(p);
+        free_multi(k);
+        dil_sign_key_destroy(e, k);
+        p = nullptr;
+    }
+}
+
+extern "C" {
+
+int dil_sign_multi_dev(dil_engine_t* e, int level, const uint8_t* d_rho, const uint8_t* d_key, const uint8_t* d_tr, const uint8_t* d_s1p,
+                       const uint8_t* d_s2p, const uint8_t* d_t0p, const uint8_t* d_msgs, const uint64_t* d_offsets, size_t n,
+                       uint8_t* d_z, uint8_t* d_h, uint8_t* d_ctilde, uint32_t* d_attempts, void* stream) {
+    if (!e) return DIL_ERR_ARG;
+    if (level != 2 && level != 3 && level != 5) return DIL_ERR_ARG;
+    if (n == 0) return DIL_OK;
+    if (!d_rho || !d_key || !d_tr || !d_s1p || !d_s2p || !d_t0p || !d_msgs || !d_offsets || !d_z || !d_h || !d_ctilde || !d_attempts ||
+        n > 0x07FFFFFFu)
+        return DIL_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_ctilde) & 7u) || (reinterpret_cast<uintptr_t>(d_z) & 15u)) return DIL_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    dil_sign_key* k = multi_ctx(e, level);
+    if (!k) return DIL_ERR_ALLOC;
+    return sign_multi_run(e, k, d_rho, d_key, d_tr, d_s1p, d_s2p, d_t0p, d_msgs, d_offsets, n, d_z, d_h, d_ctilde, d_attempts,
+                          (cudaStream_t)stream);
+}
+
+int dil_sign_multi_host(dil_engine_t* e, int level, const uint8_t* rho, const uint8_t* key, const uint8_t* tr, const uint8_t* s1p,
+                        const uint8_t* s2p, const uint8_t* t0p, const uint8_t* msgs, const uint64_t* offsets, size_t n, uint8_t* z,
+                        uint8_t* h, uint8_t* ctilde, uint32_t* attempts) {
+    if (!e) return DIL_ERR_ARG;
+    if (level != 2 && level != 3 && level != 5) return DIL_ERR_ARG;
+    if (n == 0) return DIL_OK;
+    if (!rho || !key || !tr || !s1p || !s2p || !t0p || !msgs || !offsets || !z || !h || !ctilde || n > 0x07FFFFFFu) return DIL_ERR_ARG;
+    if (!offsets_ok(offsets, n)) return DIL_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    dil_sign_key* k = multi_ctx(e, level);
+    if (!k) return DIL_ERR_ALLOC;
+    const LevelParams& P = k->P;
+    cudaStream_t st = e->host_stream;
+    const size_t zb = (size_t)P.l * P.z_bytes, hb = (size_t)P.omega + P.k;
+    const size_t s1b = (size_t)P.l * P.s_bytes, s2b = (size_t)P.k * P.s_bytes, t0b = (size_t)P.k * 416;
+    const size_t mbytes = offsets[n] > 0 ? offsets[n] : 1;
+    // staging: inputs | outputs in one grow-only allocation
+    size_t total = 0;
+    auto seg = [&](size_t bytes) { size_t o = total; total += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_rho = seg(n * 32), o_key = seg(n * 32), o_tr = seg(n * 32), o_s1 = seg(n * s1b), o_s2 = seg(n * s2b), o_t0 = seg(n * t0b),
+                 o_msg = seg(mbytes), o_off = seg((n + 1) * 8), o_z = seg(n * zb), o_h = seg(n * hb), o_ct = seg(n * 32), o_att = seg(n * 4);
+    if (total > k->multi_in_cap) {
+        wipe_free(k->multi_in, k->multi_in_cap);
+        k->multi_in = nullptr;
+        k->multi_in_cap = 0;
+        CK(dmalloc(&k->multi_in, total));
+        k->multi_in_cap = total;
+    }
+    uint8_t* base = k->multi_in;
+    CK(cudaMemcpyAsync(base + o_rho, rho, n * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_key, key, n * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_tr, tr, n * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_s1, s1p, n * s1b, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_s2, s2p, n * s2b, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_t0, t0p, n * t0b, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_msg, msgs, offsets[n], cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_off, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    int rc = sign_multi_run(e, k, base + o_rho, base + o_key, base + o_tr, base + o_s1, base + o_s2, base + o_t0, base + o_msg,
+                            reinterpret_cast<const uint64_t*>(base + o_off), n, base + o_z, base + o_h, base + o_ct,
+                            reinterpret_cast<uint32_t*>(base + o_att), st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(z, base + o_z, n * zb, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h, base + o_h, n * hb, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctilde, base + o_ct, n * 32, cudaMemcpyDeviceToHost, st));
+    if (attempts) CK(cudaMemcpyAsync(attempts, base + o_att, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return DIL_OK;
 }
 

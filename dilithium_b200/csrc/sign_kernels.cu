@@ -411,7 +411,9 @@ __device__ __forceinline__ void tail_finish(bool bad, uint32_t a, const int32_t*
 // Rejected items are appended to the next round's active list.
 // ---------------------------------------------------------------------------------------
 
-template <int K, int L, int32_t GAMMA1, int32_t GAMMA2, int BETA, int OMEGA, int WARPS, int CTAS>
+// PER_ITEM = true (one key per signature, dil_sign_multi_*): key_hat holds one (s1_hat | s2_hat | t0_hat) record per
+// ITEM, canonical and already multiplied by 256^-1, and is read from global memory instead of shared memory.
+template <int K, int L, int32_t GAMMA1, int32_t GAMMA2, int BETA, int OMEGA, int WARPS, int CTAS, bool PER_ITEM = false>
 __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
     int32_t* __restrict__ y /* in: y, out: z (in place) */, uint8_t* __restrict__ h_slot, uint8_t* __restrict__ accepted,
     const int32_t* __restrict__ key_hat, int32_t* __restrict__ w /* in: w; scratch afterwards */, const int8_t* __restrict__ c,
@@ -423,8 +425,8 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
     constexpr int NKEY = L + 2 * K;
     constexpr int G1BITS = GAMMA1 == (1 << 17) ? 17 : 19;
     constexpr int ZB = L * 32 * (G1BITS + 1);          // packed z bytes per signature
-    uint32_t* key_sm = sm_words;                       // NKEY * 256
-    uint32_t* scr_all = sm_words + NKEY * N;           // WARPS * SCRATCH_WORDS
+    uint32_t* key_sm = sm_words;                       // NKEY * 256 (shared key only)
+    uint32_t* scr_all = sm_words + (PER_ITEM ? 0 : NKEY * N);   // WARPS * SCRATCH_WORDS
     uint32_t* hm_all = scr_all + WARPS * SCRATCH_WORDS;  // WARPS * K * 8 hint masks
     uint8_t* zstage_all = reinterpret_cast<uint8_t*>(hm_all + WARPS * K * 8);   // WARPS * ZB (fused resolve)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -436,12 +438,15 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
     }
     // key polynomials are kept pre-multiplied by 256^-1 so that every inverse transform below can skip
     // its scaling multiplications (ntt_inv_warp<true>)
-    for (int t = threadIdx.x; t < NKEY * (N / 4); t += blockDim.x) {
-        int4 q = __ldg(reinterpret_cast<const int4*>(key_hat) + t);
-        reinterpret_cast<uint4*>(key_sm)[t] = make_uint4(mul_full(canon_signed(q.x), INV256), mul_full(canon_signed(q.y), INV256),
-                                                         mul_full(canon_signed(q.z), INV256), mul_full(canon_signed(q.w), INV256));
+    if constexpr (!PER_ITEM) {
+        for (int t = threadIdx.x; t < NKEY * (N / 4); t += blockDim.x) {
+            int4 q = __ldg(reinterpret_cast<const int4*>(key_hat) + t);
+            reinterpret_cast<uint4*>(key_sm)[t] = make_uint4(mul_full(canon_signed(q.x), INV256), mul_full(canon_signed(q.y), INV256),
+                                                             mul_full(canon_signed(q.z), INV256), mul_full(canon_signed(q.w), INV256));
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    const uint32_t spec = rargs.ctl->spec;
     uint32_t* scr = scr_all + warp * SCRATCH_WORDS;
     uint32_t* hm = hm_all + warp * K * 8;
     FwdTw ftw;
@@ -465,8 +470,11 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
             ntt_fwd_warp(ch, scr, ftw, lane);
             __syncwarp();
         }
+        // this slot's key record: the CTA's shared-memory copy, or the item's record in global memory
+        const uint32_t* kb = key_sm;
+        if constexpr (PER_ITEM) kb = reinterpret_cast<const uint32_t*>(key_hat) + (size_t)ra.active[a / spec] * NKEY * N;
         auto mul_inv = [&](uint32_t (&x)[8], int p) {   // x = INTT(c_hat o key[p]) in layout A
-            const uint4* kp = reinterpret_cast<const uint4*>(key_sm + p * N) + lane;
+            const uint4* kp = reinterpret_cast<const uint4*>(kb + p * N) + lane;
             uint4 lo = kp[0], hi = kp[32];
             x[0] = mul_full(ch[0], lo.x); x[1] = mul_full(ch[1], lo.y); x[2] = mul_full(ch[2], lo.z); x[3] = mul_full(ch[3], lo.w);
             x[4] = mul_full(ch[4], hi.x); x[5] = mul_full(ch[5], hi.y); x[6] = mul_full(ch[6], hi.z); x[7] = mul_full(ch[7], hi.w);
@@ -518,7 +526,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) sign_tail_kernel(
             bad = __any_sync(0xffffffffu, bad);
         }
         uint32_t nh = 0;
-        if (!bad) bad = tail_ct0_hints<K, GAMMA2>(ch, key_sm + (L + K) * N, wi, scr, itw, hm, lane, nh) || nh > OMEGA;
+        if (!bad) bad = tail_ct0_hints<K, GAMMA2>(ch, kb + (L + K) * N, wi, scr, itw, hm, lane, nh) || nh > OMEGA;
         tail_finish<K, L, G1BITS, OMEGA, false>(bad, a, y, h_slot, accepted, hm, ra, zstage_all + (size_t)warp * ZB, lane);
     }
 }
@@ -882,12 +890,12 @@ static ResolveArgs resolve_args(const SignBufs& b) {
 }
 
 // transform-only tail (any eta): one 24-warp CTA per SM
-template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA>
+template <int K, int L, int32_t G1, int32_t G2, int BETA, int OMEGA, bool PER_ITEM = false>
 static cudaError_t launch_sign_tail_t(const SignBufs& b, const int32_t* key_hat, uint32_t cap_slots, int sm_count, cudaStream_t st) {
     constexpr int WARPS = 24, CTAS = 1;
     constexpr int ZB = L * 32 * ((G1 == (1 << 17) ? 17 : 19) + 1);
-    constexpr size_t smem = (size_t)((L + 2 * K) * N + WARPS * SCRATCH_WORDS + WARPS * K * 8) * 4 + (size_t)WARPS * ZB;
-    auto kern = sign_tail_kernel<K, L, G1, G2, BETA, OMEGA, WARPS, CTAS>;
+    constexpr size_t smem = (size_t)((PER_ITEM ? 0 : (L + 2 * K) * N) + WARPS * SCRATCH_WORDS + WARPS * K * 8) * 4 + (size_t)WARPS * ZB;
+    auto kern = sign_tail_kernel<K, L, G1, G2, BETA, OMEGA, WARPS, CTAS, PER_ITEM>;
     static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
     if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(smem), configured); e != cudaSuccess) return e;
     unsigned want = (cap_slots + WARPS - 1) / WARPS;
@@ -932,6 +940,17 @@ cudaError_t launch_sign_tail(int level, const SignBufs& b, const int32_t* key_ha
     return cudaErrorInvalidValue;
 }
 
+// one key per signature: key_items = n records of (s1_hat | s2_hat | t0_hat), canonical, pre-multiplied by 256^-1
+cudaError_t launch_sign_tail_multi(int level, const SignBufs& b, const int32_t* key_items, uint32_t cap_slots, int sm_count, cudaStream_t st) {
+    if (cap_slots == 0) return cudaSuccess;
+    switch (level) {
+        case 2: return launch_sign_tail_t<4, 4, 1 << 17, (Q_I - 1) / 88, 78, 80, true>(b, key_items, cap_slots, sm_count, st);
+        case 3: return launch_sign_tail_t<6, 5, 1 << 19, (Q_I - 1) / 32, 196, 55, true>(b, key_items, cap_slots, sm_count, st);
+        case 5: return launch_sign_tail_t<8, 7, 1 << 19, (Q_I - 1) / 32, 120, 75, true>(b, key_items, cap_slots, sm_count, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_resolve(int level, const SignBufs& b, uint32_t cap_items, cudaStream_t st) {
     if (cap_items == 0) return cudaSuccess;
     const unsigned grid = (cap_items + 7) / 8;
@@ -942,6 +961,155 @@ cudaError_t launch_resolve(int level, const SignBufs& b, uint32_t cap_items, cud
         case 5: resolve_kernel<7, 19, 83><<<grid, 256, 0, st>>>(ra, b.y, b.h_slot, b.accepted); break;
         default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+
+}  // namespace dil
+
+// =======================================================================================
+// Signing with ONE KEY PER SIGNATURE (dil_sign_multi_*): the reference's sign driver streams rho, tr, K, s1, s2, t0 in
+// front of every message (rtl_tb/tb_sign_top.v:171-284), i.e. every signature may use a different key.  Key material is
+// unpacked and transformed per item on the device; A_hat is expanded once per item into HBM and the mat-vec reads the
+// item's own matrix (the per-round kernels below); ExpandMask, challenge and resolve are the shared-key kernels.
+// =======================================================================================
+namespace dil {
+
+// out[item][first + p][8 g .. 8 g + 7] = bias - field(p, g) for the bit-packed polynomials of every item's key field
+// (decoder.v:89-143: s as eta - x in 3 / 4 bits, t0 as 2^12 - x in 13 bits); one thread per 8 coefficients
+__global__ void __launch_bounds__(256) unpack_key_field_kernel(int32_t* __restrict__ out, const uint8_t* __restrict__ in, size_t n_groups,
+                                                               int width, int bias, int polys, int first, int nkey) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const size_t item = g / ((size_t)polys * 32);
+    const uint32_t r = (uint32_t)(g % ((size_t)polys * 32)), p = r >> 5, q = r & 31;
+    const uint8_t* src = in + g * (size_t)width;       // fields are contiguous per item: item * polys * 32 * width + ...
+    uint64_t lo = 0, hi = 0;
+    for (int i = 0; i < width; i++) {
+        if (i < 8) lo |= (uint64_t)src[i] << (8 * i);
+        else hi |= (uint64_t)src[i] << (8 * (i - 8));
+    }
+    int32_t o[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const int pos = width * c;
+        uint64_t v = pos < 64 ? (lo >> pos) | (pos && pos + width > 64 ? hi << (64 - pos) : 0) : hi >> (pos - 64);
+        o[c] = bias - (int32_t)(v & ((1u << width) - 1));
+    }
+    int4* dst = reinterpret_cast<int4*>(out + ((item * nkey + first + p) * N)) + 2 * q;
+    dst[0] = make_int4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_int4(o[4], o[5], o[6], o[7]);
+}
+
+// x <- x * 256^-1 mod Q (canonical in, canonical out); the tail's inverse transforms skip their scaling
+__global__ void __launch_bounds__(256) scale_inv256_kernel(int32_t* __restrict__ x, size_t n_vec) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_vec) return;
+    int4 v = reinterpret_cast<int4*>(x)[t];
+    reinterpret_cast<int4*>(x)[t] = make_int4((int)mul_full((uint32_t)v.x, INV256), (int)mul_full((uint32_t)v.y, INV256),
+                                              (int)mul_full((uint32_t)v.z, INV256), (int)mul_full((uint32_t)v.w, INV256));
+}
+
+// w_hat[a][i] = sum_j A_hat[item(a)][i*l + j] o y_hat[a][j]: the MULT_A_Y loop nest (combined_top.v:1875-1913) with the
+// slot's own matrix; one thread per 4 coefficients of one output polynomial
+template <int K, int L>
+__global__ void __launch_bounds__(256) matvec_multi_kernel(int32_t* __restrict__ wh, const int32_t* __restrict__ a_items,
+                                                           const int32_t* __restrict__ yh, const uint32_t* __restrict__ active0,
+                                                           const uint32_t* __restrict__ active1, const RoundCtl* __restrict__ ctl) {
+    const uint32_t n_slots = ctl->n_slots, spec = ctl->spec;
+    const uint32_t* __restrict__ active = ctl->cur ? active1 : active0;
+    const size_t total = (size_t)n_slots * K * 64;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(t & 63), i = (uint32_t)((t >> 6) % K);
+        const size_t a = t / ((size_t)K * 64);
+        const int4* A = reinterpret_cast<const int4*>(a_items + ((size_t)active[a / spec] * K * L + (size_t)i * L) * N) + c;
+        const int4* Y = reinterpret_cast<const int4*>(yh + a * L * N) + c;
+        uint64_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            const int4 av = __ldg(A + j * 64), yv = Y[j * 64];
+            acc[0] += (uint64_t)(uint32_t)av.x * (uint32_t)yv.x; acc[1] += (uint64_t)(uint32_t)av.y * (uint32_t)yv.y;
+            acc[2] += (uint64_t)(uint32_t)av.z * (uint32_t)yv.z; acc[3] += (uint64_t)(uint32_t)av.w * (uint32_t)yv.w;
+        }
+        reinterpret_cast<int4*>(wh + (a * K + i) * N)[c] =
+            make_int4((int)reduce49(acc[0]), (int)reduce49(acc[1]), (int)reduce49(acc[2]), (int)reduce49(acc[3]));
+    }
+}
+
+// w1 = HighBits(w), bit-packed (encoder.v:96-133: 6 bits for gamma2 = (Q-1)/88, else 4); one thread per 16 coefficients
+template <int32_t GAMMA2>
+__global__ void __launch_bounds__(256) pack_w1_kernel(uint32_t* __restrict__ w1p, const int32_t* __restrict__ w, size_t n_groups) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_groups) return;
+    const int4* src = reinterpret_cast<const int4*>(w) + t * 4;
+    uint32_t h[16];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int4 v = src[q];
+        h[4 * q + 0] = highbits<GAMMA2>((uint32_t)v.x); h[4 * q + 1] = highbits<GAMMA2>((uint32_t)v.y);
+        h[4 * q + 2] = highbits<GAMMA2>((uint32_t)v.z); h[4 * q + 3] = highbits<GAMMA2>((uint32_t)v.w);
+    }
+    if constexpr (GAMMA2 == (Q_I - 1) / 32) {
+        uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            o0 |= h[c] << (4 * c);
+            o1 |= h[8 + c] << (4 * c);
+        }
+        w1p[t * 2] = o0;
+        w1p[t * 2 + 1] = o1;
+    } else {
+        uint64_t lo = 0;
+#pragma unroll
+        for (int c = 0; c < 10; c++) lo |= (uint64_t)h[c] << (6 * c);           // bits 0..59
+        lo |= (uint64_t)h[10] << 60;                                              // bits 60..65
+        const uint32_t hi = (h[10] >> 4) | (h[11] << 2) | (h[12] << 8) | (h[13] << 14) | (h[14] << 20) | (h[15] << 26);
+        w1p[t * 3] = (uint32_t)lo;
+        w1p[t * 3 + 1] = (uint32_t)(lo >> 32);
+        w1p[t * 3 + 2] = hi;
+    }
+}
+
+cudaError_t launch_unpack_keys(int level, int32_t* key_items, const uint8_t* s1p, const uint8_t* s2p, const uint8_t* t0p, size_t n,
+                               cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const LevelParams P = level_params(level);
+    const int nkey = P.l + 2 * P.k, sw = P.eta == 2 ? 3 : 4;
+    auto go = [&](const uint8_t* in, int width, int bias, int polys, int first) {
+        const size_t groups = n * (size_t)polys * 32;
+        unpack_key_field_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(key_items, in, groups, width, bias, polys, first, nkey);
+    };
+    go(s1p, sw, P.eta, P.l, 0);
+    go(s2p, sw, P.eta, P.k, P.l);
+    go(t0p, 13, 1 << 12, P.k, P.l + P.k);
+    return cudaGetLastError();
+}
+cudaError_t launch_scale_inv256(int32_t* x, size_t n_polys, cudaStream_t st) {
+    if (n_polys == 0) return cudaSuccess;
+    const size_t n_vec = n_polys * 64;
+    scale_inv256_kernel<<<(unsigned)((n_vec + 255) / 256), 256, 0, st>>>(x, n_vec);
+    return cudaGetLastError();
+}
+cudaError_t launch_matvec_multi(int level, int32_t* wh, const int32_t* a_items, const int32_t* yh, const SignBufs& b, uint32_t cap_slots,
+                                cudaStream_t st) {
+    if (cap_slots == 0) return cudaSuccess;
+    const LevelParams P = level_params(level);
+    const size_t total = (size_t)cap_slots * P.k * 64;
+    const unsigned grid = (unsigned)((total + 255) / 256 < 148u * 64u ? (total + 255) / 256 : 148u * 64u);
+    switch (level) {
+        case 2: matvec_multi_kernel<4, 4><<<grid, 256, 0, st>>>(wh, a_items, yh, b.active[0], b.active[1], b.ctl); break;
+        case 3: matvec_multi_kernel<6, 5><<<grid, 256, 0, st>>>(wh, a_items, yh, b.active[0], b.active[1], b.ctl); break;
+        case 5: matvec_multi_kernel<8, 7><<<grid, 256, 0, st>>>(wh, a_items, yh, b.active[0], b.active[1], b.ctl); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_pack_w1(int level, uint32_t* w1p, const int32_t* w, size_t n_slots, cudaStream_t st) {
+    if (n_slots == 0) return cudaSuccess;
+    const LevelParams P = level_params(level);
+    const size_t n_groups = n_slots * P.k * (N / 16);
+    const unsigned grid = (unsigned)((n_groups + 255) / 256);
+    if (level == 2) pack_w1_kernel<(Q_I - 1) / 88><<<grid, 256, 0, st>>>(w1p, w, n_groups);
+    else pack_w1_kernel<(Q_I - 1) / 32><<<grid, 256, 0, st>>>(w1p, w, n_groups);
     return cudaGetLastError();
 }
 

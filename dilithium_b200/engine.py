@@ -224,6 +224,26 @@ class Engine:
         self._check(rc, "dil_signcore_host")
         return w
 
+    def sign_multi(self, level, rho, key, tr, s1_packed, s2_packed, t0_packed, msgs):
+        """Sign n messages, each under its own secret key (n-record arrays, bit-packed as the KAT files): the I/O of
+        rtl_tb/tb_sign_top.v:171-284.  Returns (z, h, ctilde, attempts)."""
+        n = len(msgs)
+        k, l = LEVEL_DIMS[level]
+        zb = l * (576 if level == 2 else 640)
+        hb = {2: 84, 3: 61, 5: 83}[level]
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(m) for m in msgs])
+        blob = np.frombuffer(b"".join(msgs), dtype=np.uint8).copy() if off[-1] else np.zeros(1, np.uint8)
+        keys = [np.ascontiguousarray(x, dtype=np.uint8) for x in (rho, key, tr, s1_packed, s2_packed, t0_packed)]
+        z = np.empty((n, zb), np.uint8); h = np.empty((n, hb), np.uint8); c = np.empty((n, 32), np.uint8)
+        att = np.zeros(n, np.uint32)
+        P = ctypes.c_void_p
+        rc = self._lib.dil_sign_multi_host(self._h, int(level), *[a.ctypes.data_as(P) for a in keys], blob.ctypes.data_as(P),
+                                           off.ctypes.data_as(P), n, z.ctypes.data_as(P), h.ctypes.data_as(P), c.ctypes.data_as(P),
+                                           att.ctypes.data_as(P))
+        self._check(rc, "dil_sign_multi_host")
+        return z, h, c, att
+
     def verify_multi(self, level, rho, t1_packed, msgs, z, h, ctilde):
         """Verify n signatures, each under its own public key (rho[i], t1[i]).  Returns ok[n] (1 = accept)."""
         n = len(msgs)

@@ -155,6 +155,16 @@ typedef struct {
     int unfused_mask;        /* non-zero: ExpandMask and the sign core run as two kernels instead of the fused mask_core      */
 } dil_sign_tuning;
 int dil_sign_key_set_tuning(dil_sign_key_t *k, const dil_sign_tuning *t);   /* t == NULL restores the defaults */
+/* One key PER SIGNATURE, as the reference's sign driver streams it (rtl_tb/tb_sign_top.v:171-284: rho, tr, K, s1, s2, t0
+ * precede every message): rho, key (K), tr are n x 32 bytes, s1 / s2 / t0 n bit-packed records as in dil_sign_key_create.
+ * A_hat = ExpandA(rho[i]) and NTT(s1, s2, t0) are computed per item on the device.  Same outputs as dil_sign_batch_*. */
+int dil_sign_multi_host(dil_engine_t *e, int level, const uint8_t *rho, const uint8_t *key, const uint8_t *tr,
+                        const uint8_t *s1_packed, const uint8_t *s2_packed, const uint8_t *t0_packed, const uint8_t *msgs,
+                        const uint64_t *offsets, size_t n, uint8_t *z, uint8_t *h, uint8_t *ctilde, uint32_t *attempts);
+int dil_sign_multi_dev(dil_engine_t *e, int level, const uint8_t *d_rho, const uint8_t *d_key, const uint8_t *d_tr,
+                       const uint8_t *d_s1_packed, const uint8_t *d_s2_packed, const uint8_t *d_t0_packed, const uint8_t *d_msgs,
+                       const uint64_t *d_offsets, size_t n, uint8_t *d_z, uint8_t *d_h, uint8_t *d_ctilde, uint32_t *d_attempts,
+                       void *stream);
 /* optional device timing of the pipeline's kernel classes (CUDA events on the launching stream):
    index 0 init (mu, rho'), 1 ExpandMask, 2 fused sign core, 3 w1 pack, 4 challenge, 5 tail, 6 resolve;
    ms[8] = summed kernel time of the last batch, units[8] = slots (attempts) each class processed */

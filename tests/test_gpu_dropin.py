@@ -23,6 +23,44 @@ def test_reference_test_main_runs_on_engine():
     assert out.stdout.count(":OK") == 2, out.stdout
 
 
+def test_reference_hardware_emulator_test_runs_on_engine():
+    """The reference's second test main, hardware_code/ntt2x2_test.cpp (unmodified): the cycle-level emulator of the
+    RTL datapath is checked against ntt / invntt / pointwise_barrett (with c == a aliasing) / ntt2x2_ref / invntt2x2_ref
+    - all five served by the B200 engine through the shim.  The source hard-codes 1 000 000 iterations of seven gold
+    calls each (minutes of batch-of-one round trips), so the run is bounded: the program stops at the first mismatch
+    (prints ERROR, non-zero exit), hence "still running without a word after 25 s" = every comparison so far passed."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ntt2x2_test_on_engine")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ntt2x2_test_on_engine not built (reference tree absent at build time)")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=25)
+        assert out.returncode == 0 and "OK" in out.stdout and "ERROR" not in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    except subprocess.TimeoutExpired as t:
+        so = (t.stdout or b"").decode() if isinstance(t.stdout, bytes) else (t.stdout or "")
+        assert "ERROR" not in so and "rror" not in so.replace("Test for", ""), so[-2000:]
+
+
+def test_shim_accepts_unreduced_inputs(oracle):
+    """ref_ntt.cpp reduces with a signed 64-bit % and so accepts any int32; the shim must too (sums of residues)."""
+    from dilithium_b200 import _lib
+    shim = ctypes.CDLL(_lib.SHIM_PATH)
+    rng = np.random.default_rng(9)
+    a = rng.integers(-2**31, 2**31 - 1, size=256, dtype=np.int64).astype(np.int32)
+    b = rng.integers(-2**31, 2**31 - 1, size=256, dtype=np.int64).astype(np.int32)
+    am = (a.astype(np.int64) % 8380417).astype(np.int32)
+    bm = (b.astype(np.int64) % 8380417).astype(np.int32)
+    P = ctypes.POINTER(ctypes.c_int32)
+    x = a.copy()
+    shim._Z3nttPi(x.ctypes.data_as(P))
+    assert np.array_equal(x, oracle.ntt(am))
+    x = a.copy()
+    shim._Z6invnttPi(x.ctypes.data_as(P))
+    assert np.array_equal(x, oracle.invntt(am))
+    c = np.empty(256, np.int32)
+    shim._Z17pointwise_barrettPiPKiS1_(c.ctypes.data_as(P), a.ctypes.data_as(P), b.ctypes.data_as(P))
+    assert np.array_equal(c, oracle.pointwise(am, bm)[0])
+
+
 def test_shim_symbols_batch_of_one(oracle):
     """Call the reference-mangled symbols directly (as a C++ caller would after linking the shim)."""
     from dilithium_b200 import _lib

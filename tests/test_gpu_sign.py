@@ -136,3 +136,27 @@ def test_sign_scheduler_tuning_does_not_change_results(eng):
     assert rounds["no speculation"][1] == int(ref[3].sum())
     assert rounds["always 32 slots"][0] <= 2
     key.close()
+
+
+@pytest.mark.parametrize("level", [2, 3, 5])
+def test_sign_multi_all_kats_in_one_batch(eng, oracle, level):
+    """Key per signature, as rtl_tb/tb_sign_top.v:171-284 streams it: all 100 KAT vectors of a level (100 different
+    keys) signed as ONE batch must reproduce the KAT signatures bit for bit; a second batch mixes keys and random
+    messages (several messages per key, empty and long messages) and is checked against the oracle."""
+    K = ol.kat(level)
+    msgs = list(K["msgs"])
+    z, h, c, att = eng.sign_multi(level, K["rho"], K["k"], K["tr"], K["s1"], K["s2"], K["t0"], msgs)
+    assert np.array_equal(c, K["c"]) and np.array_equal(z, K["zs"]) and np.array_equal(h, K["h"])
+    exp = {2: (4.21, 17), 3: (4.23, 19), 5: (4.40, 24)}[level]      # BASELINE.md §2
+    assert abs(att.mean() - exp[0]) < 0.01 and att.max() == exp[1]
+    rng = np.random.default_rng(100 + level)
+    n = 257
+    kidx = rng.integers(0, 100, n)
+    msgs2 = [b"", bytes(3301)] + [bytes(rng.integers(0, 256, int(rng.integers(1, 200))).astype(np.uint8)) for _ in range(n - 2)]
+    z, h, c, att = eng.sign_multi(level, *[K[f][kidx] for f in ("rho", "k", "tr", "s1", "s2", "t0")], msgs2)
+    for m in range(0, n, 5):
+        i = kidx[m]
+        zo, ho, co, a = oracle.sign(level, K["rho"][i], K["k"][i], K["tr"][i], K["s1"][i], K["s2"][i], K["t0"][i], msgs2[m])
+        assert np.array_equal(c[m], co) and np.array_equal(z[m], zo) and np.array_equal(h[m], ho) and att[m] == a, (level, m)
+    ok = eng.verify_multi(level, K["rho"][kidx], K["t1"][kidx], msgs2, z, h, c)
+    assert ok.tolist() == [1] * n
