@@ -66,6 +66,7 @@ SIGNATURES = {
     "dil_verify_multi_host": (c_int, [c_void, c_int, c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void]),
     "dil_verify_multi_dev": (c_int, [c_void, c_int, c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void, c_void]),
     "dil_keygen_batch_host": (c_int, [c_void, c_int, c_void, c_size] + [c_void] * 7),
+    "dil_diag_keccak_dev": (c_int, [c_void, c_void, c_uint, c_uint, c_void]),
     "dil_invntt_tomont_dev": (c_int, [c_void, c_void, c_void, c_size, c_void]),
     "dil_poly_pointwise_dev": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void]),
     "dil_polyvec_matrix_pointwise_dev": (c_int, [c_void, c_void, c_void, c_void, c_int, c_int, c_size, c_void]),

@@ -207,6 +207,13 @@ int dil_signcore_dev(dil_engine_t* e, int32_t* w, const int32_t* a_hat, const in
     return DIL_OK;
 }
 
+int dil_diag_keccak_dev(dil_engine_t* e, uint64_t* d_out, unsigned ctas_per_sm, unsigned perms_per_thread, void* stream) {
+    DIL_CHECK_ENGINE(e);
+    if (!d_out || ctas_per_sm == 0 || ctas_per_sm > 16 || perms_per_thread == 0) return DIL_ERR_ARG;
+    DIL_LAUNCH(e, dil::launch_keccak_rate(d_out, (unsigned)e->sm_count * ctas_per_sm, perms_per_thread, (cudaStream_t)stream), 1);
+    return DIL_OK;
+}
+
 int dil_invntt_tomont_dev(dil_engine_t* e, int32_t* d, const int32_t* s, size_t n, void* st) { return dil_invntt_dev(e, d, s, n, st); }
 int dil_poly_pointwise_dev(dil_engine_t* e, int32_t* c, const int32_t* a, const int32_t* b, size_t n, void* st) {
     return dil_pointwise_dev(e, c, a, b, n, st);

@@ -86,7 +86,8 @@ cudaError_t launch_sign_init(uint64_t* mu, uint64_t* rhop, uint16_t* kappa, cons
 // cap_slots / cap_items bound the round's size (the kernels read the real size from b.ctl) and size the grids
 cudaError_t launch_expand_mask(int level, const SignBufs& b, uint32_t cap_slots, cudaStream_t st);
 // ExpandMask + sign core in one kernel (mask_core.cu): y, w and the packed HighBits(w) of every slot of the round
-cudaError_t launch_mask_core(int level, const SignBufs& b, const int32_t* a_hat, uint32_t cap_slots, int sm_count, cudaStream_t st);
+cudaError_t launch_mask_core(int level, const SignBufs& b, const int32_t* a_hat, uint32_t cap_slots, int sm_count, cudaStream_t st,
+                             int maxp = 0);
 cudaError_t launch_challenge(int level, const SignBufs& b, uint32_t cap_slots, cudaStream_t st);
 cudaError_t launch_sign_tail(int level, const SignBufs& b, const int32_t* key_hat, const int8_t* key_small, uint32_t cap_slots,
                              int sm_count, cudaStream_t st);
@@ -119,6 +120,9 @@ cudaError_t launch_verify_prep(int level, int32_t* v, uint32_t* hmask, uint32_t*
 cudaError_t launch_usehint_pack(int level, uint32_t* w1p, const int32_t* w, const uint32_t* hmask, uint32_t n, cudaStream_t st);
 cudaError_t launch_verify_hash(int level, uint8_t* ok, const uint64_t* mu, const uint64_t* w1p, const uint64_t* ctilde,
                                const uint32_t* bad, uint32_t n, cudaStream_t st);
+
+// ---- diagnostics ----
+cudaError_t launch_keccak_rate(uint64_t* out, unsigned ctas, uint32_t perms, cudaStream_t st);
 
 // ---- keygen pipeline ----
 cudaError_t launch_keygen_seed(uint8_t* rho, uint64_t* rhop, uint8_t* key, const uint8_t* xi, uint32_t n, cudaStream_t st);

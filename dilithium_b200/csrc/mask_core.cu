@@ -74,11 +74,12 @@ __device__ __forceinline__ void unpack_mask8(const unsigned char* __restrict__ s
 
 }  // namespace
 
-template <int K, int L, int GAMMA1_BITS, int WARPS, int NBUF, int MAXP>
+template <int K, int L, int GAMMA1_BITS, int WARPS, int NBUF>
 __global__ void __launch_bounds__(WARPS * 32, 1) mask_core_kernel(int32_t* __restrict__ w, uint8_t* __restrict__ w1p, int32_t* __restrict__ y,
                                                                 const int32_t* __restrict__ a_hat, const uint64_t* __restrict__ rhop,
                                                                 const uint16_t* __restrict__ kappa, const uint32_t* __restrict__ active0,
-                                                                const uint32_t* __restrict__ active1, RoundCtl* __restrict__ ctl) {
+                                                                const uint32_t* __restrict__ active1, RoundCtl* __restrict__ ctl,
+                                                                const int MAXP) {
     constexpr int BITS = GAMMA1_BITS + 1;                // 18 / 20 bits per coefficient
     constexpr int ZB = 32 * BITS;                         // squeezed bytes per polynomial: 576 / 640
     constexpr int ROW = ZB + 16;                          // row stride in the ring (skews banks, keeps 16-byte alignment)
@@ -246,28 +247,30 @@ __global__ void __launch_bounds__(WARPS * 32, 1) mask_core_kernel(int32_t* __res
 }
 
 template <int K, int L, int G1B, int NBUF>
-static cudaError_t launch_mask_core_t(const SignBufs& b, const int32_t* a_hat, uint32_t cap_slots, int sm_count, cudaStream_t st) {
-    constexpr int WARPS = 16, MAXP = 4;
+static cudaError_t launch_mask_core_t(const SignBufs& b, const int32_t* a_hat, uint32_t cap_slots, int sm_count, cudaStream_t st, int maxp) {
+    constexpr int WARPS = 16;
     constexpr int ROW = 32 * (G1B + 1) + 16;
     constexpr size_t smem = (size_t)(K * L * A_STRIDE + WARPS * SCRATCH_WORDS) * 4 + (size_t)NBUF * 32 * ROW;
     static_assert(smem + 1024 <= 227 * 1024, "mask core: shared memory budget");
-    auto kern = mask_core_kernel<K, L, G1B, WARPS, NBUF, MAXP>;
+    auto kern = mask_core_kernel<K, L, G1B, WARPS, NBUF>;
     static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
     if (cudaError_t e = ensure_dyn_smem(kern, smem, configured); e != cudaSuccess) return e;
     constexpr int G = 32 / L;
     const unsigned groups = (cap_slots + G - 1) / G;
     const unsigned want = (groups + 3) / 4;   // a CTA is worth launching for a handful of groups (MAXP of them are squeezed at once)
     const unsigned grid = want < (unsigned)sm_count ? (want ? want : 1) : (unsigned)sm_count;
-    kern<<<grid, WARPS * 32, smem, st>>>(b.w, reinterpret_cast<uint8_t*>(b.w1p), b.y, a_hat, b.rhop, b.kappa, b.active[0], b.active[1], b.ctl);
+    kern<<<grid, WARPS * 32, smem, st>>>(b.w, reinterpret_cast<uint8_t*>(b.w1p), b.y, a_hat, b.rhop, b.kappa, b.active[0], b.active[1], b.ctl,
+                                         maxp > 0 ? maxp : NBUF);
     return cudaGetLastError();
 }
 
-cudaError_t launch_mask_core(int level, const SignBufs& b, const int32_t* a_hat, uint32_t cap_slots, int sm_count, cudaStream_t st) {
+// maxp: how many warps of a CTA may squeeze masks at the same time (0 = as many as there are ring buffers)
+cudaError_t launch_mask_core(int level, const SignBufs& b, const int32_t* a_hat, uint32_t cap_slots, int sm_count, cudaStream_t st, int maxp) {
     if (cap_slots == 0) return cudaSuccess;
     switch (level) {
-        case 2: return launch_mask_core_t<4, 4, 17, 8>(b, a_hat, cap_slots, sm_count, st);
-        case 3: return launch_mask_core_t<6, 5, 19, 8>(b, a_hat, cap_slots, sm_count, st);
-        case 5: return launch_mask_core_t<8, 7, 19, 6>(b, a_hat, cap_slots, sm_count, st);
+        case 2: return launch_mask_core_t<4, 4, 17, 8>(b, a_hat, cap_slots, sm_count, st, maxp);
+        case 3: return launch_mask_core_t<6, 5, 19, 8>(b, a_hat, cap_slots, sm_count, st, maxp);
+        case 5: return launch_mask_core_t<8, 7, 19, 6>(b, a_hat, cap_slots, sm_count, st, maxp);
     }
     return cudaErrorInvalidValue;
 }

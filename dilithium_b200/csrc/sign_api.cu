@@ -297,12 +297,12 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
                 CK(dil::launch_pack_w1(P.level, reinterpret_cast<uint32_t*>(k->w1p), k->w, ns, st));
                 PROF_END(2);
                 launches += 3;
-            } else if (!k->tune.unfused_mask) {
+            } else if (k->tune.fused_mask) {
                 // ExpandMask, the transforms and the mat-vec in one kernel (mask_core.cu); timed as class 2
                 PROF_BEGIN(1);
                 PROF_END(1);
                 PROF_BEGIN(2);
-                CK(dil::launch_mask_core(P.level, b, k->a_hat, cs, e->sm_count, st));
+                CK(dil::launch_mask_core(P.level, b, k->a_hat, cs, e->sm_count, st, k->tune.mask_producers));
                 PROF_END(2);
                 launches--;
             } else {

@@ -1626,3 +1626,27 @@ cudaError_t launch_tr_batch(uint8_t* tr, const uint8_t* rho, const uint8_t* t1p,
 }
 
 }  // namespace dil
+
+// =======================================================================================
+// Diagnostics: the pure Keccak-f[1600] rate of this GPU (the ALU-pipe speed of light that bench.py measures in the
+// same run as the signing step and reports the Keccak-bound kernels against).  Same permutation code as every
+// hash kernel above (keccak.cuh), one state per thread, nothing but permutations.
+// =======================================================================================
+namespace dil {
+__global__ void __launch_bounds__(128) keccak_rate_kernel(uint64_t* __restrict__ out, uint32_t perms) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t A[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) A[i] = (uint64_t)(gid + 1) * 0x9E3779B97F4A7C15ULL + (uint64_t)i;
+    for (uint32_t p = 0; p < perms; p++) keccak_f1600(A);
+    uint64_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 25; i++) x ^= A[i];
+    out[gid] = x;
+}
+cudaError_t launch_keccak_rate(uint64_t* out, unsigned ctas, uint32_t perms, cudaStream_t st) {
+    if (ctas == 0) return cudaSuccess;
+    keccak_rate_kernel<<<ctas, 128, 0, st>>>(out, perms);
+    return cudaGetLastError();
+}
+}  // namespace dil

@@ -268,6 +268,23 @@ class Engine:
                                             P(d_ok.data_ptr()), self._stream())
         self._check(rc, "dil_verify_multi_dev")
 
+    def keccak_rate(self, ctas_per_sm=1, perms=2000, repeats=3):
+        """Measured pure Keccak-f[1600] rate of this GPU in permutations/s (dil_diag_keccak_dev, CUDA-event timed):
+        the ALU-pipe speed of light of the engine's hash kernels."""
+        import torch
+        threads = self.sm_count * ctas_per_sm * 128
+        out = torch.empty(threads, dtype=torch.int64, device=f"cuda:{self.device}")
+        best = 0.0
+        for _ in range(repeats + 1):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            self._check(self._lib.dil_diag_keccak_dev(self._h, ctypes.c_void_p(out.data_ptr()), ctas_per_sm, perms, self._stream()),
+                        "dil_diag_keccak_dev")
+            b.record()
+            b.synchronize()
+            best = max(best, threads * perms / (a.elapsed_time(b) * 1e-3))
+        return best
+
     def keygen(self, level, seeds):
         """Batched key generation from 32-byte seeds xi (host path).  Returns a dict of uint8 arrays with the
         KAT field names: rho, k, tr, s1, s2, t1, t0 (bit-packed as the reference's KAT files)."""
@@ -324,12 +341,14 @@ class SignKey:
 
     class _Tuning(ctypes.Structure):   # dil_sign_tuning
         _fields_ = [("spec_target", ctypes.c_uint32), ("spec_max", ctypes.c_uint32), ("dev_chunk", ctypes.c_size_t),
-                    ("host_chunk", ctypes.c_size_t), ("host_copy_path", ctypes.c_int), ("unfused_mask", ctypes.c_int)]
+                    ("host_chunk", ctypes.c_size_t), ("host_copy_path", ctypes.c_int), ("fused_mask", ctypes.c_int),
+                    ("mask_producers", ctypes.c_int)]
 
-    def set_tuning(self, spec_target=0, spec_max=0, dev_chunk=0, host_chunk=0, host_copy_path=False, unfused_mask=False):
+    def set_tuning(self, spec_target=0, spec_max=0, dev_chunk=0, host_chunk=0, host_copy_path=False, fused_mask=False,
+                   mask_producers=0):
         """Scheduler knobs of this key (dil_sign_key_set_tuning); zeros restore the defaults.  Results never change."""
         t = self._Tuning(int(spec_target), int(spec_max), int(dev_chunk), int(host_chunk), int(bool(host_copy_path)),
-                         int(bool(unfused_mask)))
+                         int(bool(fused_mask)), int(mask_producers))
         self.engine._check(self.engine._lib.dil_sign_key_set_tuning(self._h, ctypes.byref(t)), "dil_sign_key_set_tuning")
 
     PROFILE_CLASSES = ("init", "expand_mask", "signcore", "pack_w1", "challenge", "tail", "resolve")

@@ -152,7 +152,9 @@ typedef struct {
     size_t dev_chunk;        /* dil_sign_batch_dev signs larger requests in pieces of this many messages (2^20)               */
     size_t host_chunk;       /* the same for the streaming path of dil_sign_batch_host (2^18)                                 */
     int host_copy_path;      /* non-zero: dil_sign_batch_host always uses chunked copy-engine transfers                       */
-    int unfused_mask;        /* non-zero: ExpandMask and the sign core run as two kernels instead of the fused mask_core      */
+    int fused_mask;          /* non-zero: ExpandMask runs inside the sign core (mask_core kernel) instead of as its own kernel;
+                                measured slower on B200, kept selectable                                         */
+    int mask_producers;      /* fused mask_core: warps per CTA that may squeeze masks at once (0 = one per ring buffer)        */
 } dil_sign_tuning;
 int dil_sign_key_set_tuning(dil_sign_key_t *k, const dil_sign_tuning *t);   /* t == NULL restores the defaults */
 /* One key PER SIGNATURE, as the reference's sign driver streams it (rtl_tb/tb_sign_top.v:171-284: rho, tr, K, s1, s2, t0
@@ -196,6 +198,12 @@ int dil_verify_multi_dev(dil_engine_t *e, int level, const uint8_t *d_rho, const
  * s1 (l polys), s2 (k polys) as eta - s, t1 (10 bit), t0 as 2^12 - t0 (13 bit). */
 int dil_keygen_batch_host(dil_engine_t *e, int level, const uint8_t *xi, size_t n, uint8_t *rho, uint8_t *key, uint8_t *tr,
                           uint8_t *s1_packed, uint8_t *s2_packed, uint8_t *t1_packed, uint8_t *t0_packed);
+
+/* ---- diagnostics ----
+ * Pure Keccak-f[1600] rate of the device: sm_count * ctas_per_sm CTAs of 128 threads, every thread runs perms_per_thread
+ * permutations on its own state (the permutation code of every hash kernel of the engine) and writes one word to
+ * d_out[thread].  The caller times the launch; bench.py uses it as the measured ALU-pipe roofline of the run. */
+int dil_diag_keccak_dev(dil_engine_t *e, uint64_t *d_out, unsigned ctas_per_sm, unsigned perms_per_thread, void *stream);
 
 /* ---- north_star aliases (plain domain, identical to the above) ---- */
 int dil_invntt_tomont_dev(dil_engine_t *e, int32_t *dst, const int32_t *src, size_t n_polys, void *stream);
