@@ -8,8 +8,7 @@ One step = sign one batch of 65 536 independent 32-byte messages under one key, 
 challenge hash + SampleInBall -> c*s1, c*s2, c*t0, norm checks, MakeHint; deterministic round-3.1
 signing exactly as the reference's KAT vectors, rtl_src/combined_top.v mode 2).  The polynomial
 arithmetic inside is the engine's hot path; the stand-alone NTT kernel and the fused cfg2 sign core
-(NTT+matvec+INTT) are timed separately in the same run and reported as `roofline_ntt` /
-`sign_core`.
+(NTT+matvec+INTT) are timed separately in the same run and reported as `roofline_ntt` / `sign_core`.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]                 # this framework (CUDA engine)
     python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] # reference C++ arithmetic on host cores
@@ -17,18 +16,25 @@ arithmetic inside is the engine's hot path; the stand-alone NTT kernel and the f
 Multi-GPU: one process per GPU (torchrun), every rank signs its own 65 536-message shard (weak
 scaling); the only collective is ONE NCCL broadcast of the key material from rank 0.
 
-`value`   signs/s over all GPUs, messages already resident in HBM, CUDA-event timed, max over ranks.
-`e2e`     the same through dil_sign_batch_host: pinned host messages in, signatures back on the host
-          (finished signatures are drained to the host round by round while later rounds still sign).
-`roofline` the kernel class with the largest share of the step's device time (measured with CUDA
-          events around every launch in a separate profiled step): HBM fraction from algorithmic bytes as
-          the contract asks, plus `compute_roofline` (Keccak-f/s against the measured pure-Keccak peak)
-          because that class is bound by the integer ALU pipe, not by HBM.
+`value`    signs/s over all GPUs, messages already resident in HBM, CUDA-event timed, max over ranks.
+`e2e`      the same through dil_sign_batch_host: pinned host messages in, signatures back on the host
+           (finished signatures are drained to the host round by round while later rounds still sign);
+           `e2e.host_ceiling` relates it to the measured host-memory ceiling of the box (profiles/).
+`roofline` the kernel class with the largest share of the step's device time (CUDA events around every
+           launch in a separate profiled step): HBM fraction from algorithmic bytes as the contract asks,
+           plus `compute_roofline`: Keccak-f/s against the pure-Keccak rate MEASURED IN THIS RUN
+           (dil_diag_keccak_dev) because that class is bound by the integer ALU pipe, not by HBM.
+`configs`  the other BASELINE configurations under the same clock: cfg3 (Dilithium-3, 262 144 items: fused
+           ExpandA core with shared and per-item rho, full signing), cfg4 (Dilithium-5 verification, one GPU's
+           131 072-signature shard, a key per signature, 100 KAT tuples injected and asserted), cfg5 (batch sweep
+           2^10 .. 2^22 x levels 2/3/5, sharded over the ranks).  --no-configs skips them.
 """
 import argparse
 import ctypes
 import json
 import os
+import re
+import subprocess
 import sys
 import threading
 import time
@@ -43,6 +49,9 @@ MSG_BYTES = 32
 LEVEL_DIMS = {2: (4, 4), 3: (6, 5), 5: (8, 7)}
 LEVEL_EXTRA = {2: dict(w1=192, zb=576, hb=84), 3: dict(w1=128, zb=640, hb=61), 5: dict(w1=128, zb=640, hb=83)}
 UNIT = "signs/s"
+# measured with tools/d2h_ceiling.cu on the 8-GPU box (profiles/r2_d2h_ceiling_8gpu.txt): bytes/s ALL GPUs together
+# can write into host memory, barrier-synchronised, copy engine and SM stores alike
+HOST_CEILING_GBS = {1: 54.4, 2: 72.2, 4: 74.8, 8: 96.6}
 
 
 def metric_name(level):
@@ -59,6 +68,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=65536, help="signatures per GPU per step (weak scaling)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg3 / cfg4 / cfg5 sub-records")
+    ap.add_argument("--sweep-max-log2", type=int, default=22)
     return ap.parse_args()
 
 
@@ -76,37 +87,83 @@ def measured_peak():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-KECCAK_PEAK_GPS = 4.27   # G Keccak-f[1600]/s: pure-permutation micro-benchmark on one B200 (tools/keccak_pipe_bench.cu,
-                         # profiles/r1b_keccak_pipe_bench.txt): the ALU-pipe speed of light for the hash kernels
-
-
 def class_kernel_name(kernel_class, level):
     if kernel_class == "tail" and level == 3:   # eta = 4: the sparse products do not apply
         return "sign_tail_kernel (NTT(c), c*s2 / c*s1 / c*t0 through transforms, norm checks, MakeHint, resolve)"
     return CLASS_KERNEL[kernel_class]
 
 
-def keccak_roofline(kernel_class, level, slots, ms):
-    """For the Keccak-bound classes: achieved permutations/s against the measured pure-Keccak peak."""
+def keccak_perms_per_slot(kernel_class, level):
     k, l = LEVEL_DIMS[level]
     w1 = LEVEL_EXTRA[level]["w1"]
-    per_slot = {"expand_mask": l * 5,                                   # 576/640 squeezed bytes per polynomial = 5 blocks
-                "challenge": (64 + k * w1) // 136 + 1 + 1}.get(kernel_class)   # absorb mu||w1 + pad, then SampleInBall
+    return {"expand_mask": l * 5,                                   # 576/640 squeezed bytes per polynomial = 5 blocks
+            "challenge": (64 + k * w1) // 136 + 1 + 1}.get(kernel_class)   # absorb mu||w1 + pad, then SampleInBall
+
+
+def keccak_roofline(kernel_class, level, slots, ms, peak_gps=None, peak_source=None):
+    """For the Keccak-bound classes: achieved permutations/s against the pure-Keccak rate measured in this run."""
+    per_slot = keccak_perms_per_slot(kernel_class, level)
     if per_slot is None or ms <= 0:
         return None
     gps = per_slot * slots / (ms * 1e-3) / 1e9
-    return {"bound": "integer ALU (Keccak-f[1600])", "unit": "G Keccak-f/s", "achieved": gps, "peak": KECCAK_PEAK_GPS,
-            "frac": gps / KECCAK_PEAK_GPS, "permutations_per_slot": per_slot,
-            "peak_source": "tools/keccak_pipe_bench.cu on B200 (profiles/r1b_keccak_pipe_bench.txt)"}
+    out = {"bound": "integer ALU (Keccak-f[1600])", "unit": "G Keccak-f/s", "achieved": gps, "permutations_per_slot": per_slot}
+    if peak_gps:
+        out.update(peak=peak_gps, frac=gps / peak_gps, peak_source=peak_source)
+    return out
+
+
+def ncu_record(kernel_class):
+    """The committed ncu capture of `kernel_class` (profiles/dominant_kernel.json, written by tools/make_dominant.py from
+    the round's `ncu --set full` reports): dram bytes per launch and the pipe utilisations that name its limiter."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel.json"))).get(kernel_class)
+    except Exception:
+        return None
 
 
 def ncu_traffic(kernel_class):
-    """dram bytes per launch of `kernel_class` from the committed ncu capture, or None."""
+    r = ncu_record(kernel_class)
+    return r.get("dram_bytes_per_launch") if r else None
+
+
+def ncu_limiter(kernel_class):
+    """Which pipe the committed ncu capture shows busiest for this class (numbers, not prose)."""
+    r = ncu_record(kernel_class)
+    if not r:
+        return None
+    pipes = {n: r[f] for n, f in (("alu", "alu_pipe_pct"), ("fmaheavy", "fmaheavy_pipe_pct"), ("issue", "issue_pct")) if f in r}
+    if "dram_pct" in r:
+        pipes["dram"] = r["dram_pct"]
+    top = max(pipes, key=pipes.get)
+    return {"top_pipe": top, "pct_busy": pipes, "source": r.get("source")}
+
+
+def keccak_sass_mix():
+    """Instruction mix of one Keccak-f round in the SHIPPED library (cuobjdump -sass of keccak_rate_kernel's inner loop):
+    how many of its instructions issue on the integer ALU pipe (LOP3 / SHF / IADD3 ...)."""
+    lib = os.path.join(ROOT, "dilithium_b200", "libdilithium_b200.so")
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel.json")))
-        return prof.get(kernel_class, {}).get("dram_bytes_per_launch")
+        out = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3dil18keccak_rate_kernelEPmj", lib], capture_output=True, text=True,
+                             timeout=120).stdout
     except Exception:
         return None
+    ins = re.findall(r"/\*([0-9a-f]{4})\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)\s*([^;]*);", out)
+    if not ins:
+        return None
+    addr = [int(a, 16) for a, _, _ in ins]
+    loops = []
+    for a, op, args in ins:
+        if op.startswith("BRA"):
+            m = re.search(r"0x([0-9a-f]+)", args)
+            if m and int(m.group(1), 16) < int(a, 16):
+                loops.append((int(a, 16) - int(m.group(1), 16), int(m.group(1), 16), int(a, 16)))
+    if not loops:
+        return None
+    _, lo, hi = min(loops)
+    body = [op for a, (_, op, _) in zip(addr, ins) if lo <= a <= hi]
+    alu = sum(1 for op in body if op.split(".")[0] in ("LOP3", "SHF", "IADD3", "VIADD", "PRMT", "SEL", "ISETP", "IMNMX", "MOV", "LEA", "VIMNMX"))
+    fma = sum(1 for op in body if op.split(".")[0] in ("IMAD", "FFMA", "FMUL", "FADD"))
+    return {"instructions_per_round": len(body), "alu_pipe": alu, "fma_pipe": fma, "other": len(body) - alu - fma}
 
 
 def kat_key(level, index=0):
@@ -134,9 +191,6 @@ CLASS_KERNEL = {"expand_mask": "expand_mask_kernel<L,GAMMA1_BITS> (SHAKE-256 Exp
                 "challenge": "challenge_kernel (SHAKE-256 + SampleInBall)",
                 "tail": "sign_tail_sparse_kernel (sparse c*s2 / c*s1 products + norm checks; NTT(c), c*t0, MakeHint and resolve for survivors)", "resolve": "resolve_kernel",
                 "init": "sign_init_kernel"}
-CLASS_BOUND_NOTE = {"expand_mask": "integer ALU (Keccak): ncu alu pipe 95% busy; HBM fraction is not the limiter",
-                    "challenge": "integer ALU (Keccak)", "tail": "issue slots / ALU pipe 60 % + global-load latency (sparse products); fmaheavy 39 % (survivors' c*t0 transforms)",
-                    "signcore": "integer multiply pipe (fmaheavy): ncu 73% busy", "resolve": "HBM/latency"}
 
 
 # --------------------------------------------------------------------------------------
@@ -166,10 +220,33 @@ def cpu_sign(level, n_msgs, threads, steps=1, warmup=0):
     return n_msgs / dt, kind, threads, sample, dt * 1e3, float(att.mean())
 
 
+def cpu_ntt(threads, n_polys=65536):
+    """reference ntt() (compiled ref_ntt.cpp when present, else the oracle port) over n_polys polynomials on `threads` threads."""
+    import numpy as np
+    import oracle_lib as ol
+    rng = np.random.default_rng(SEED + 5)
+    a = rng.integers(0, Q, size=(n_polys, 256)).astype(np.int32)
+    ref = ol.load_ref()
+    t0 = time.perf_counter()
+    if ref is not None:
+        ref.run("ref_ntt_batch", a, threads, canon=False)
+    else:
+        ol.load().ntt(a, threads=threads)
+    return n_polys / (time.perf_counter() - t0), "reference" if ref is not None else "port"
+
+
+def host_threads():
+    """Threads the CPU arm uses: the cores this process may run on."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     n_msgs = 256 * cores if 256 * cores < 8192 else 8192
     steps = max(1, min(args.steps, 5))
     warm = max(0, min(args.warmup, 1))
@@ -179,7 +256,8 @@ def run_reference(args):
         "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32/int64 (signed % reduction)", "data": "synthetic",
         "config": {"workload": workload_name(args.level, args.batch), "level": args.level, "sample_messages_per_step": n_msgs,
-                   "mean_attempts": att, "note": "CPU arm: host cores only, no GPU; throughput does not depend on --gpus"},
+                   "mean_attempts": att, "note": "CPU arm: host cores only, no GPU; throughput does not depend on --gpus; "
+                                                 "steps / warmup are clamped to 5 / 1 so that the bounded sample ends within minutes"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -241,37 +319,228 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 # engine arm
 # --------------------------------------------------------------------------------------
+class Ctx:
+    """Per-rank state shared by the headline step and the configuration sub-records."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        import dilithium_b200 as d
+        self.torch, self.dist, self.d = torch, dist, d
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl engine needs a CUDA device: the engine has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.eng = d.Engine(self.local)
+        self.peak, self.peak_src = measured_peak()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def maxr(self, v):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def time_ms(self, fn, iters, warm=2):
+        """Device time per call (CUDA events on torch's current stream = the stream the engine launches on), max over ranks."""
+        torch = self.torch
+        for _ in range(warm):
+            fn()
+        self.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return self.maxr(a.elapsed_time(b)) / iters
+
+
+def sign_buffers(c, key, n, gen_seed):
+    torch = c.torch
+    gen = torch.Generator(device="cpu").manual_seed(gen_seed)
+    msgs_host = torch.randint(0, 256, (n * MSG_BYTES,), dtype=torch.uint8, generator=gen).pin_memory()
+    offs_host = (torch.arange(n + 1, dtype=torch.int64) * MSG_BYTES).pin_memory()
+    z = torch.empty((n, key.z_bytes), dtype=torch.uint8, device=c.dev)
+    h = torch.empty((n, key.h_bytes), dtype=torch.uint8, device=c.dev)
+    ct = torch.empty((n, 32), dtype=torch.uint8, device=c.dev)
+    att = torch.zeros(n, dtype=torch.int32, device=c.dev)
+    return msgs_host, offs_host, msgs_host.to(c.dev), offs_host.to(c.dev), z, h, ct, att
+
+
+def cfg3_record(c, keccak_peak):
+    """cfg3: Dilithium-3 (k=6,l=5), 262 144 items per GPU: fused ExpandA -> NTT -> A*y -> INTT core (mode S: one rho,
+    mode P: rho per item) and full signing of a 262 144-message batch."""
+    torch, d, eng = c.torch, c.d, c.eng
+    level, B = 3, 262144
+    k, l = LEVEL_DIMS[level]
+    kk = kat_key(level)
+    gen = torch.Generator(device=c.dev).manual_seed(SEED + 3)
+    y = torch.randint(0, Q, (B, l, 256), dtype=torch.int32, device=c.dev, generator=gen)
+    w = torch.empty((B, k, 256), dtype=torch.int32, device=c.dev)
+    rho = torch.from_numpy(kk["rho"]).to(c.dev)
+    rho_p = torch.randint(0, 256, (B, 32), dtype=torch.uint8, device=c.dev, generator=gen)
+    ms_s = c.time_ms(lambda: eng.matvec_expand(rho, y, k, l, ntt_input=True, intt_output=True, w=w), 10)
+    ms_p = c.time_ms(lambda: eng.matvec_expand(rho_p, y, k, l, per_item=True, ntt_input=True, intt_output=True, w=w), 3, warm=1)
+    del y, w
+    key = d.SignKey(eng, level, *[kk[f] for f in ("rho", "k", "tr", "s1", "s2", "t0")])
+    _, _, msgs, offs, z, h, ct, att = sign_buffers(c, key, B, SEED + 31 + c.rank)
+    ms_sign = c.time_ms(lambda: key.sign_dev(msgs, offs, B, z, h, ct, att), 3, warm=1)
+    mean_att = float(att.float().mean().item())
+    key.close()
+    bytes_item = (l + k) * 1024 + 32
+    out = {"workload": f"Dilithium-3 (k=6,l=5), {B} items per GPU", "n_gpus": c.world,
+           "fused_expand_core_shared_rho": {"items_per_s": c.world * B / (ms_s * 1e-3), "ms": ms_s,
+                                            "hbm_frac": B * bytes_item / (ms_s * 1e-3) / 1e9 / c.peak, "algorithmic_bytes_per_item": bytes_item,
+                                            "keccak_f_per_launch": "5 x k*l per CTA (A is expanded once per persistent CTA, never written to HBM)"},
+           "fused_expand_core_per_item_rho": {"items_per_s": c.world * B / (ms_p * 1e-3), "ms": ms_p,
+                                              "hbm_frac": B * bytes_item / (ms_p * 1e-3) / 1e9 / c.peak,
+                                              "keccak_f_per_s": B * 5 * k * l / (ms_p * 1e-3),
+                                              "keccak_frac_of_measured_peak": B * 5 * k * l / (ms_p * 1e-3) / keccak_peak if keccak_peak else None,
+                                              "bound": "integer ALU (Keccak: 5 x k*l = 150 permutations per item)"},
+           "full_sign": {"signs_per_s": c.world * B / (ms_sign * 1e-3), "ms": ms_sign, "mean_attempts": mean_att}}
+    return out
+
+
+def cfg4_record(c, keccak_peak):
+    """cfg4: Dilithium-5 verification, 1 M signatures over 8 GPUs = 131 072 per GPU, EVERY signature under its own public
+    key (per-item rho: A expanded on chip per item); the 100 level-5 KAT tuples are injected at fixed positions of every
+    GPU's shard and must be accepted (they yield the w that makes H(mu || w1') == c~)."""
+    import numpy as np
+    torch, d, eng = c.torch, c.d, c.eng
+    level, n = 5, 131072
+    k, l = LEVEL_DIMS[level]
+    K = np.load(os.path.join(ROOT, "tests", "golden", f"kat_L{level}.npz"))
+    M = np.load(os.path.join(ROOT, "tests", "golden", "kat_msgs.npz"))
+    kat_off = np.concatenate([[0], np.cumsum(M["mlen"])])
+    kat_msgs = [M["blob"][kat_off[i]:kat_off[i + 1]] for i in range(100)]
+    key_of = np.arange(n) % 100
+    pos = 1310 * np.arange(100) + 7                               # fixed KAT positions in every shard
+    rng = np.random.default_rng(SEED + 4 + c.rank)
+    mlen = np.full(n, MSG_BYTES, dtype=np.int64)
+    mlen[pos] = M["mlen"]
+    off = np.concatenate([[0], np.cumsum(mlen)]).astype(np.uint64)
+    blob = rng.integers(0, 256, int(off[-1]), dtype=np.uint8)
+    for j, p in enumerate(pos):
+        blob[int(off[p]):int(off[p + 1])] = kat_msgs[j]
+        key_of[p] = j
+    dv = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(c.dev)   # noqa: E731
+    d_rho, d_t1 = dv(K["rho"][key_of]), dv(K["t1"][key_of])
+    d_msgs, d_off = dv(blob), dv(off.view(np.int64))
+    zb, hb = l * 640, 75 + k
+    z = torch.empty((n, zb), dtype=torch.uint8, device=c.dev); h = torch.empty((n, hb), dtype=torch.uint8, device=c.dev)
+    ct = torch.empty((n, 32), dtype=torch.uint8, device=c.dev); att = torch.zeros(n, dtype=torch.int32, device=c.dev)
+    P = ctypes.c_void_p
+    skeys = [dv(K[f][key_of]) for f in ("rho", "k", "tr", "s1", "s2", "t0")]   # one secret key per signature (kept alive over the call)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rc = eng._lib.dil_sign_multi_dev(eng._h, level, *[P(t.data_ptr()) for t in skeys],
+                                     P(d_msgs.data_ptr()), P(d_off.data_ptr()), n, P(z.data_ptr()), P(h.data_ptr()), P(ct.data_ptr()),
+                                     P(att.data_ptr()), eng._stream())
+    eng._check(rc, "dil_sign_multi_dev")
+    torch.cuda.synchronize()
+    sign_multi_s = time.perf_counter() - t0
+    del skeys
+    # the injected tuples are the reference's own signatures: signing them again must reproduce the KAT bytes
+    kat_sig_ok = bool(np.array_equal(z[pos].cpu().numpy(), K["zs"]) and np.array_equal(h[pos].cpu().numpy(), K["h"]) and
+                      np.array_equal(ct[pos].cpu().numpy(), K["c"]))
+    z[torch.from_numpy(pos).to(c.dev)] = dv(K["zs"]); h[torch.from_numpy(pos).to(c.dev)] = dv(K["h"])
+    ct[torch.from_numpy(pos).to(c.dev)] = dv(K["c"])
+    ok = torch.zeros(n, dtype=torch.uint8, device=c.dev)
+    ms = c.time_ms(lambda: eng.verify_multi_dev(level, d_rho, d_t1, d_msgs, d_off, n, z, h, ct, ok), 3, warm=1)
+    okh = ok.cpu().numpy()
+    kat_ok = bool(okh[pos].all())
+    all_ok = bool(okh.all())
+    # tampered copy: exactly the tampered positions must be rejected
+    z2 = z.clone()
+    z2[5::1000, 77] ^= 8
+    eng.verify_multi_dev(level, d_rho, d_t1, d_msgs, d_off, n, z2, h, ct, ok)
+    exp = np.ones(n, np.uint8); exp[5::1000] = 0
+    tamper_ok = bool(np.array_equal(ok.cpu().numpy(), exp))
+    del z2
+    # one shared key for comparison (A_hat expanded once per key): this rank's signatures under KAT key 0
+    kk = kat_key(level)
+    sk = d.SignKey(eng, level, *[kk[f] for f in ("rho", "k", "tr", "s1", "s2", "t0")])
+    vk = d.VerifyKey(eng, level, kk["rho"], kk["t1"])
+    _, _, m1, o1, z1, h1, c1, a1 = sign_buffers(c, sk, n, SEED + 41 + c.rank)
+    sk.sign_dev(m1, o1, n, z1, h1, c1, a1)
+    ms_shared = c.time_ms(lambda: vk.verify_dev(m1, o1, n, z1, h1, c1, ok), 5, warm=1)
+    shared_ok = bool(int(ok.sum().item()) == n)
+    sk.close(); vk.close()
+    if not (kat_ok and all_ok and tamper_ok and shared_ok and kat_sig_ok):
+        raise RuntimeError(f"cfg4 check failed: kat_ok={kat_ok} all_ok={all_ok} tamper_ok={tamper_ok} shared_ok={shared_ok} kat_sig_ok={kat_sig_ok}")
+    perms = 5 * k * l + (32 + k * 320) // 136 + 1                 # ExpandA per item + tr = SHAKE-256(rho || t1)
+    bytes_item = (l + k + 1 + k) * 1024 + 32
+    return {"workload": f"Dilithium-5 (k=8,l=7) verification, {n} signatures per GPU ({c.world * n} over {c.world} GPU(s)), a public key per signature",
+            "n_gpus": c.world, "kat_tuples_injected": 100, "kat_positions": "1310*j + 7, j = 0..99, in every GPU's shard",
+            "kat_tuples_accepted": kat_ok, "all_accepted": all_ok, "tampered_rejected_exactly": tamper_ok,
+            "kat_signatures_reproduced_by_sign_multi": kat_sig_ok,
+            "per_item_key": {"verifies_per_s": c.world * n / (ms * 1e-3), "ms": ms, "keccak_f_per_s": n * perms / (ms * 1e-3),
+                             "keccak_frac_of_measured_peak": n * perms / (ms * 1e-3) / keccak_peak if keccak_peak else None,
+                             "hbm_frac": n * bytes_item / (ms * 1e-3) / 1e9 / c.peak, "algorithmic_bytes_per_item": bytes_item,
+                             "bound": f"integer ALU (Keccak: {perms} permutations per item)",
+                             "timing": "CUDA events around dil_verify_multi_dev (keys, messages, signatures resident in HBM), max over ranks"},
+            "shared_key": {"verifies_per_s": c.world * n / (ms_shared * 1e-3), "ms": ms_shared},
+            "setup_sign_multi_s": sign_multi_s}
+
+
+def cfg5_sweep(c, max_log2):
+    """cfg5: global batch B = 2^10 .. 2^22 (x4 steps) x levels 2/3/5, sharded evenly over the ranks: forward NTT of the
+    batch's l*B polynomials, the fused sign core, full signing and (shared-key) verification."""
+    torch, d, eng = c.torch, c.d, c.eng
+    rows = []
+    for level in (2, 3, 5):
+        k, l = LEVEL_DIMS[level]
+        kk = kat_key(level)
+        sk = d.SignKey(eng, level, *[kk[f] for f in ("rho", "k", "tr", "s1", "s2", "t0")])
+        vk = d.VerifyKey(eng, level, kk["rho"], kk["t1"])
+        a_hat = eng.expand_a(torch.from_numpy(kk["rho"]).to(c.dev), k, l)[0].contiguous()
+        for lg in range(10, max_log2 + 1, 2):
+            B = 1 << lg
+            b = max(B // c.world, 1)
+            it = 20 if b <= 16384 else (5 if b <= 262144 else 2)
+            y = torch.randint(0, Q, (b, l, 256), dtype=torch.int32, device=c.dev)
+            o = torch.empty_like(y)
+            w = torch.empty((b, k, 256), dtype=torch.int32, device=c.dev)
+            ms_ntt = c.time_ms(lambda: eng.ntt(y, out=o), it, warm=1)
+            ms_core = c.time_ms(lambda: eng.signcore(a_hat, y, k, l, w=w), it, warm=1)
+            del y, o, w
+            _, _, msgs, offs, z, h, ct, att = sign_buffers(c, sk, b, SEED + lg)
+            ms_sign = c.time_ms(lambda: sk.sign_dev(msgs, offs, b, z, h, ct, att), max(it // 2, 1), warm=1)
+            ok = torch.zeros(b, dtype=torch.uint8, device=c.dev)
+            ms_ver = c.time_ms(lambda: vk.verify_dev(msgs, offs, b, z, h, ct, ok), max(it // 2, 1), warm=1)
+            accepted = int(ok.sum().item()) == b
+            del msgs, offs, z, h, ct, att, ok
+            torch.cuda.empty_cache()
+            n = c.world * b
+            rows.append({"level": level, "batch": n, "per_gpu": b,
+                         "ntt_polys_per_s": n * l / (ms_ntt * 1e-3), "ntt_hbm_frac": b * l * 2048 / (ms_ntt * 1e-3) / 1e9 / c.peak,
+                         "signcore_items_per_s": n / (ms_core * 1e-3), "signcore_hbm_frac": b * (k + l) * 1024 / (ms_core * 1e-3) / 1e9 / c.peak,
+                         "signs_per_s": n / (ms_sign * 1e-3), "verifies_per_s": n / (ms_ver * 1e-3), "verify_all_accepted": accepted})
+        sk.close(); vk.close()
+    return {"workload": "batch sweep 2^10 .. 2^%d x levels 2/3/5, global batch sharded over %d GPU(s)" % (max_log2, c.world),
+            "note": "working sets below the 126 MB L2 (small batches) run from cache: their hbm_frac is not an HBM rate",
+            "rows": rows}
+
+
 def run_engine(args):
     import numpy as np
-    import torch
-    import torch.distributed as dist
-    import dilithium_b200 as d
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl engine needs a CUDA device: the engine has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    eng = d.Engine(local)
+    c = Ctx()
+    torch, dist, d, eng = c.torch, c.dist, c.d, c.eng
+    world, rank, local, dev = c.world, c.rank, c.local, c.dev
     level = args.level
     k, l = LEVEL_DIMS[level]
     B = args.batch
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def maxr(v):
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
 
     # one key for the whole job: rank 0 owns it, ONE broadcast ships it (rho | K | tr | s1 | s2 | t0)
     fields = ("rho", "k", "tr", "s1", "s2", "t0")
@@ -290,21 +559,15 @@ def run_engine(args):
     key = d.SignKey(eng, level, *[parts[f] for f in fields])
 
     # per-rank synthetic messages (the rank's shard of the global batch)
-    gen = torch.Generator(device="cpu").manual_seed(SEED + 1 + rank)
-    msgs_host = torch.randint(0, 256, (B * MSG_BYTES,), dtype=torch.uint8, generator=gen).pin_memory()
-    offs_host = (torch.arange(B + 1, dtype=torch.int64) * MSG_BYTES).pin_memory()
-    msgs, offs = msgs_host.to(dev), offs_host.to(dev)
-    z = torch.empty((B, key.z_bytes), dtype=torch.uint8, device=dev)
-    h = torch.empty((B, key.h_bytes), dtype=torch.uint8, device=dev)
-    c = torch.empty((B, 32), dtype=torch.uint8, device=dev)
-    att = torch.zeros(B, dtype=torch.int32, device=dev)
+    msgs_host, offs_host, msgs, offs, z, h, ct, att = sign_buffers(c, key, B, SEED + 1 + rank)
 
     def step():
-        key.sign_dev(msgs, offs, B, z, h, c, att)
+        key.sign_dev(msgs, offs, B, z, h, ct, att)
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
-    barrier()
+    c.barrier()
     l0 = eng.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
@@ -312,13 +575,13 @@ def run_engine(args):
         for _ in range(args.steps):
             step()
         ev1.record()
-        barrier()
+        c.barrier()
     launches = eng.launch_count - l0
-    ms_total = maxr(ev0.elapsed_time(ev1))
+    ms_total = c.maxr(ev0.elapsed_time(ev1))
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
     mean_attempts = float(att.float().mean().item())
-    rounds = key.last_rounds
+    rounds, slots = key.last_rounds, key.last_slots
 
     # per-kernel-class device time of one step (CUDA events around every launch), outside the timed region
     key.set_profile(True)
@@ -330,27 +593,27 @@ def run_engine(args):
     dominant = max((n for n in prof if n != "init"), key=lambda n: prof[n][0])
     cb = class_bytes(level)
 
-    # stand-alone hot-path kernels, separately timed (north_star: "NTT polys/sec vs HBM roofline")
-    def time_kernel(fn, iters=50):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(iters):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / iters
+    # the pure Keccak-f rate of THIS GPU in THIS run: the ALU-pipe roofline of the hash kernels
+    with ClockSampler(local) as kclk:
+        krates = {cps: eng.keccak_rate(ctas_per_sm=cps, perms=1500) for cps in (1, 2, 3)}
+    keccak_peak = max(krates.values())
+    kmix = keccak_sass_mix()
+    kclock = kclk.summary()["sm_mhz"]
+    keccak_model = None
+    if kmix and kclock:
+        # every SM sub-partition issues one ALU-pipe warp instruction per 2 cycles (16 lanes wide)
+        keccak_model = eng.sm_count * 4 * (kclock * 1e6) / 2 * 32 / (kmix["alu_pipe"] * 24)
+    keccak_src = ("dil_diag_keccak_dev in this run: %d SMs x {1,2,3} CTAs of 128 threads x 1500 permutations, CUDA events, best of 3; "
+                  "rates %s G/s" % (eng.sm_count, {kk_: round(v / 1e9, 3) for kk_, v in krates.items()}))
 
     yb = torch.randint(0, Q, (B, l, 256), dtype=torch.int32, device=dev)
     outb = torch.empty_like(yb)
     wb = torch.empty((B, k, 256), dtype=torch.int32, device=dev)
     a_hat = eng.expand_a(torch.from_numpy(parts["rho"]).to(dev), k, l)[0].contiguous()
     npoly = B * l
-    ntt_ms = time_kernel(lambda: eng.ntt(yb, out=outb))
-    intt_ms = time_kernel(lambda: eng.invntt(yb, out=outb))
-    core_ms = time_kernel(lambda: eng.signcore(a_hat, yb, k, l, w=wb))
+    ntt_ms = c.time_ms(lambda: eng.ntt(yb, out=outb), 50, warm=3)
+    intt_ms = c.time_ms(lambda: eng.invntt(yb, out=outb), 50, warm=3)
+    core_ms = c.time_ms(lambda: eng.signcore(a_hat, yb, k, l, w=wb), 50, warm=3)
     del yb, outb, wb
 
     # end to end through the host-pointer C ABI: pinned host messages in, signatures out to host memory
@@ -368,63 +631,90 @@ def run_engine(args):
             raise RuntimeError("dil_sign_batch_host failed")
 
     e2e_step()
-    barrier()
+    c.barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
         e2e_step()
-    barrier()
-    e2e_s = maxr(time.perf_counter() - t0)
+    c.barrier()
+    e2e_s = c.maxr(time.perf_counter() - t0)
     e2e_val = world * B * args.e2e_steps / e2e_s
-    e2e_ok = bool(torch.equal(z_h.to(dev), z) and torch.equal(h_h.to(dev), h) and torch.equal(c_h.to(dev), c))
+    e2e_ok = bool(torch.equal(z_h.to(dev), z) and torch.equal(h_h.to(dev), h) and torch.equal(c_h.to(dev), ct))
+    del z_h, h_h, c_h, a_h
+
+    configs = None
+    if not args.no_configs:
+        t_cfg = time.perf_counter()
+        configs = {"cfg3": cfg3_record(c, keccak_peak), "cfg4": cfg4_record(c, keccak_peak), "cfg5": cfg5_sweep(c, args.sweep_max_log2)}
+        configs["wall_s"] = time.perf_counter() - t_cfg
 
     if rank == 0:
-        peak, peak_src = measured_peak()
+        peak, peak_src = c.peak, c.peak_src
         dom_ms, dom_units = prof[dominant]
         dom_bytes = cb[dominant] * dom_units
         dom_achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         sig_bytes = key.z_bytes + key.h_bytes + 32
+        traffic = ncu_traffic(dominant)
+        ceiling = HOST_CEILING_GBS.get(world)
         line = {
             "metric": metric_name(level), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32/u64 integer (Shoup/Barrett modular arithmetic, 64-bit Keccak lanes)", "data": "synthetic",
             "config": {"workload": workload_name(level, B), "level": level, "k": k, "l": l, "batch_per_gpu": B,
                        "key": "reference KAT vector 0 (tests/golden)", "mean_attempts": mean_attempts, "rejection_rounds": rounds,
+                       "attempt_slots_per_step": slots, "host_syncs_per_step": "1 (the rejection loop runs on the device; rounds are enqueued ahead)",
                        "sharding": ("independent messages, one contiguous shard per rank; one NCCL broadcast of the key material"
                                     if world > 1 else "single GPU"),
                        "l2": "no flush: every round streams > 1 GiB of per-attempt state (y, w, c), far above the 126 MB L2",
                        "timing": "CUDA events on torch's current stream (the stream every kernel is launched on), max over ranks",
                        "kernels_per_round": "ExpandMask, sign core (+ packed HighBits), challenge, tail (+ resolve when one slot per item), "
-                                            "resolve only in speculative rounds"},
+                                            "resolve (returns at once unless the round speculates), plan"},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "step_profile_ms": {n: round(ms, 4) for n, (ms, _) in prof.items()},
-            "step_profile_note": f"device time per kernel class in one step (sum {prof_total:.3f} ms of {ms_step:.3f} ms wall); "
-                                 "the rest is launch latency and one 4-byte D2H + stream sync per rejection round",
+            "step_profile_note": f"device time per kernel class in one step (sum {prof_total:.3f} ms of {ms_step:.3f} ms wall)",
             "roofline": {"kernel": class_kernel_name(dominant, level), "class": dominant, "bound": "hbm", "achieved": dom_achieved, "peak": peak,
                          "unit": "GB/s", "frac": dom_achieved / peak,
-                         "traffic": (ncu_traffic(dominant) / 65536.0 * dom_units / max(rounds, 1)) if ncu_traffic(dominant) else None,
+                         "traffic": (traffic / 65536.0 * dom_units / max(rounds, 1)) if traffic else None,
                          "traffic_note": "ncu dram bytes of a 65536-slot launch scaled to this step's average launch size",
                          "algorithmic_bytes_per_slot": cb[dominant], "slots_per_step": dom_units, "launches_per_step": rounds,
                          "avg_launch_ms": dom_ms / max(rounds, 1), "peak_source": peak_src,
-                         "true_limiter": CLASS_BOUND_NOTE.get(dominant, ""),
-                         "compute_roofline": keccak_roofline(dominant, level, dom_units, dom_ms)},
+                         "ncu_limiter": ncu_limiter(dominant),
+                         "compute_roofline": keccak_roofline(dominant, level, dom_units, dom_ms, keccak_peak / 1e9, keccak_src)},
+            "keccak_peak": {"measured_g_per_s": keccak_peak / 1e9, "source": keccak_src, "sass_mix_per_round": kmix, "sm_mhz_during": kclock,
+                            "alu_pipe_model_g_per_s": keccak_model / 1e9 if keccak_model else None,
+                            "alu_pipe_model": "sm_count x 4 sub-partitions x clock / 2 cycles per ALU warp instruction x 32 threads / "
+                                              "(ALU-pipe instructions per round x 24 rounds)"},
+            "keccak_classes": {n: keccak_roofline(n, level, prof[n][1], prof[n][0], keccak_peak / 1e9, "same run") for n in ("expand_mask", "challenge")},
             "roofline_ntt": {"kernel": "ntt_tma_kernel<32,3,1,false> (stand-alone forward NTT, the north_star's named kernel)",
                              "bound": "hbm", "polys_per_s": npoly / (ntt_ms * 1e-3), "achieved": npoly * 2048 / (ntt_ms * 1e-3) / 1e9,
                              "peak": peak, "unit": "GB/s", "frac": npoly * 2048 / (ntt_ms * 1e-3) / 1e9 / peak, "polys_per_launch": npoly,
                              "invntt_polys_per_s": npoly / (intt_ms * 1e-3), "invntt_frac": npoly * 2048 / (intt_ms * 1e-3) / 1e9 / peak},
             "sign_core": {"workload": f"cfg2 core alone: w = INTT(A_hat * NTT(y)), {B} items, one fused kernel",
                           "items_per_s": B / (core_ms * 1e-3), "ms": core_ms,
-                          "hbm_frac": B * (k + l) * 1024 / (core_ms * 1e-3) / 1e9 / peak},
+                          "hbm_frac": B * (k + l) * 1024 / (core_ms * 1e-3) / 1e9 / peak, "ncu_limiter": ncu_limiter("signcore")},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * MSG_BYTES + (B + 1) * 8,
                     "d2h_bytes_per_step": B * (sig_bytes + 4), "steps": args.e2e_steps,
                     "api": "dil_sign_batch_host (C ABI): pinned host messages in, z/h/c~/attempts back in host memory",
-                    "timing": "host wall clock around the synchronous calls, max over ranks", "matches_device_path": e2e_ok},
+                    "timing": "host wall clock around the synchronous calls, max over ranks", "matches_device_path": e2e_ok,
+                    "host_ceiling": ({"aggregate_gb_per_s": ceiling, "signatures_per_s": ceiling * 1e9 / (sig_bytes + 4),
+                                      "e2e_frac_of_ceiling": e2e_val * (sig_bytes + 4) / (ceiling * 1e9),
+                                      "source": "profiles/r2_d2h_ceiling_8gpu.txt: barrier-synchronised D2H of all GPUs at once on the 8-GPU box, "
+                                                "copy engine and SM stores alike (tools/d2h_ceiling.cu)"} if ceiling else None)},
         }
+        if configs is not None:
+            line["configs"] = configs
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = host_threads()
             n_cpu = 256 * cores if 256 * cores < 8192 else 8192
             v, kind, threads, sample, _, _ = cpu_sign(level, n_cpu, cores, steps=2, warmup=1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
+            ntt_cpu, ntt_kind = cpu_ntt(cores)
+            line["cpu_baseline"]["ntt_polys_per_s"] = ntt_cpu
+            line["cpu_baseline"]["ntt_sample"] = f"65536 polynomials through {'the compiled reference ntt()' if ntt_kind == 'reference' else 'the oracle port'} on {cores} thread(s)"
+            if configs is not None:
+                for lv in (3, 5):
+                    vv, *_ = cpu_sign(lv, max(n_cpu // 4, 64), cores, steps=1, warmup=0)
+                    line["cpu_baseline"][f"dilithium{lv}_signs_per_s"] = vv
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -66,6 +66,14 @@ SIGNATURES = {
     "dil_verify_multi_host": (c_int, [c_void, c_int, c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void]),
     "dil_verify_multi_dev": (c_int, [c_void, c_int, c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void, c_void]),
     "dil_keygen_batch_host": (c_int, [c_void, c_int, c_void, c_size] + [c_void] * 7),
+    "dil_pool_create": (c_int, [ctypes.POINTER(c_void), c_void, c_int]),
+    "dil_pool_destroy": (c_int, [c_void]),
+    "dil_pool_size": (c_int, [c_void]),
+    "dil_pool_engine": (c_void, [c_void, c_int]),
+    "dil_pool_sign_key_create": (c_int, [c_void, ctypes.POINTER(c_void), c_int, c_void, c_void, c_void, c_void, c_void, c_void]),
+    "dil_pool_sign_key_destroy": (c_int, [c_void, c_void]),
+    "dil_pool_sign_batch_host": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void]),
+    "dil_diag_item_rows_threshold": (c_int, [c_size]),
     "dil_diag_keccak_dev": (c_int, [c_void, c_void, c_uint, c_uint, c_void]),
     "dil_invntt_tomont_dev": (c_int, [c_void, c_void, c_void, c_size, c_void]),
     "dil_poly_pointwise_dev": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void]),

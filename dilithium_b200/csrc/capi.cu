@@ -207,6 +207,11 @@ int dil_signcore_dev(dil_engine_t* e, int32_t* w, const int32_t* a_hat, const in
     return DIL_OK;
 }
 
+int dil_diag_item_rows_threshold(size_t min_batch) {
+    dil::set_item_rows_threshold(min_batch);
+    return DIL_OK;
+}
+
 int dil_diag_keccak_dev(dil_engine_t* e, uint64_t* d_out, unsigned ctas_per_sm, unsigned perms_per_thread, void* stream) {
     DIL_CHECK_ENGINE(e);
     if (!d_out || ctas_per_sm == 0 || ctas_per_sm > 16 || perms_per_thread == 0) return DIL_ERR_ARG;

@@ -122,6 +122,7 @@ cudaError_t launch_verify_hash(int level, uint8_t* ok, const uint64_t* mu, const
                                const uint32_t* bad, uint32_t n, cudaStream_t st);
 
 // ---- diagnostics ----
+void set_item_rows_threshold(size_t n);
 cudaError_t launch_keccak_rate(uint64_t* out, unsigned ctas, uint32_t perms, cudaStream_t st);
 
 // ---- keygen pipeline ----

@@ -16,11 +16,15 @@ constexpr int A_STRIDE = 260;  // words per A polynomial in shared memory (pad 4
 // a_sm: k*l polynomials in shared memory (stride A_STRIDE), pre-multiplied by 256^-1 when INTT_OUT.
 // EXTRA: the last input is multiplied by a per-item column extra_item[i] from global memory instead of a matrix column.
 // W1: also emit w1 = HighBits(w), bit-packed as encoder.v:96-133 (6 bits for gamma2 = (Q-1)/88, i.e. K = 4, else 4 bits).
-template <int K, int LA, bool INTT_OUT, bool EXTRA, bool W1>
+// PRESCALED: a_sm (and nothing else) already carries the 256^-1 factor of the inverse transform - worth it where one
+// matrix serves a whole batch (scaled once per CTA); the per-item-rho kernels leave their matrices unscaled (scaling 256
+// coefficients of each of the k*l generated polynomials would cost more than the 12 multiplications per inverse transform).
+template <int K, int LA, bool INTT_OUT, bool EXTRA, bool W1, bool PRESCALED = true>
 __device__ __forceinline__ void item_rows(int32_t* __restrict__ w_item, const uint32_t (&yh)[LA + (EXTRA ? 1 : 0)][8],
                                           const uint32_t* __restrict__ a_sm, uint32_t* __restrict__ scr, int lane,
                                           const int32_t* __restrict__ extra_item, uint8_t* __restrict__ w1_item, int i_begin,
-                                          int i_end) {
+                                          int i_end, int a_first_row = 0) {
+    // a_first_row: the matrix row held first in a_sm (kernels that stream A through shared memory a few rows at a time)
     constexpr int L = LA + (EXTRA ? 1 : 0);
 #pragma unroll 1
     for (int i = i_begin; i < i_end; i++) {
@@ -33,11 +37,11 @@ __device__ __forceinline__ void item_rows(int32_t* __restrict__ w_item, const ui
             if (EXTRA && j == LA) {
                 const int4* ep = reinterpret_cast<const int4*>(extra_item + i * N) + lane;
                 int4 elo = __ldg(ep), ehi = __ldg(ep + 32);
-                auto sc = [](int32_t x) -> uint32_t { return INTT_OUT ? mul_full(canon_signed(x), INV256) : canon_signed(x); };
+                auto sc = [](int32_t x) -> uint32_t { return INTT_OUT && PRESCALED ? mul_full(canon_signed(x), INV256) : canon_signed(x); };
                 lo = make_uint4(sc(elo.x), sc(elo.y), sc(elo.z), sc(elo.w));
                 hi = make_uint4(sc(ehi.x), sc(ehi.y), sc(ehi.z), sc(ehi.w));
             } else {
-                const uint4* ap = reinterpret_cast<const uint4*>(a_sm + (i * LA + j) * A_STRIDE) + lane;
+                const uint4* ap = reinterpret_cast<const uint4*>(a_sm + ((i - a_first_row) * LA + j) * A_STRIDE) + lane;
                 lo = ap[0];
                 hi = ap[32];
             }
@@ -56,7 +60,7 @@ __device__ __forceinline__ void item_rows(int32_t* __restrict__ w_item, const ui
                 asm volatile("" : "+l"(tab));
                 load_inv_tw(itw, tab, lane);
             }
-            ntt_inv_warp<true>(x, scr, itw, lane);   // a_sm carries the 256^-1 factor
+            ntt_inv_warp<PRESCALED>(x, scr, itw, lane);
             __syncwarp();
             int32_t* o = w_item + i * N + lane;
 #pragma unroll
@@ -91,6 +95,38 @@ __device__ __forceinline__ void item_rows(int32_t* __restrict__ w_item, const ui
     }
 }
 
+// The item's L input polynomials into registers, NTT domain, layout C (transformed here when NTT_IN).
+template <int L, bool NTT_IN>
+__device__ __forceinline__ void item_inputs(uint32_t (&yh)[L][8], const int32_t* __restrict__ v_item, uint32_t* __restrict__ scr, int lane) {
+    if constexpr (NTT_IN) {
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            const int32_t* p = v_item + j * N + lane;
+#pragma unroll
+            for (int r = 0; r < 8; r++) yh[j][r] = (uint32_t)p[32 * r];  // layout A: 128-B line per access
+        }
+        FwdTw ftw;
+        {   // 2 KiB table, L1 resident; reloaded per item (opaque pointer defeats hoisting) to keep registers low
+            const TwTable* tab = &TW_FWD;
+            asm volatile("" : "+l"(tab));
+            load_fwd_tw(ftw, tab, lane);
+        }
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            ntt_fwd_warp(yh[j], scr, ftw, lane);
+            __syncwarp();
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            const int4* p = reinterpret_cast<const int4*>(v_item + j * N) + lane;
+            int4 lo = p[0], hi = p[32];
+            yh[j][0] = canon_signed(lo.x); yh[j][1] = canon_signed(lo.y); yh[j][2] = canon_signed(lo.z); yh[j][3] = canon_signed(lo.w);
+            yh[j][4] = canon_signed(hi.x); yh[j][5] = canon_signed(hi.y); yh[j][6] = canon_signed(hi.z); yh[j][7] = canon_signed(hi.w);
+        }
+    }
+}
+
 // ---- per-item core, executed by one warp ----
 // v_item: l polys (global), w_item: k polys (global), a_sm: k*l polys in shared memory (stride A_STRIDE)
 // EXTRA = true (verification with per-item public keys): v_item holds L+1 polynomials, and the last one is
@@ -102,7 +138,7 @@ __device__ __forceinline__ void item_rows(int32_t* __restrict__ w_item, const ui
 // SPLIT = true (per-item kernel of level 5, two warps per item): both warps of the CTA call this together; warp
 // `part` transforms every second input and publishes it through yh_sm (layout C), and computes rows
 // [part*K/2, (part+1)*K/2) of the result - the single-warp latency of the per-item core is halved.
-template <int K, int LA, bool NTT_IN, bool INTT_OUT, bool EXTRA = false, bool W1 = false, bool SPLIT = false>
+template <int K, int LA, bool NTT_IN, bool INTT_OUT, bool EXTRA = false, bool W1 = false, bool SPLIT = false, bool PRESCALED = true>
 __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const int32_t* __restrict__ v_item,
                                           const uint32_t* __restrict__ a_sm, uint32_t* __restrict__ scr, int lane,
                                           const int32_t* __restrict__ extra_item = nullptr,
@@ -137,35 +173,11 @@ __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const in
             yh[j][0] = lo.x; yh[j][1] = lo.y; yh[j][2] = lo.z; yh[j][3] = lo.w;
             yh[j][4] = hi.x; yh[j][5] = hi.y; yh[j][6] = hi.z; yh[j][7] = hi.w;
         }
-    } else if constexpr (NTT_IN) {
-#pragma unroll
-        for (int j = 0; j < L; j++) {
-            const int32_t* p = v_item + j * N + lane;
-#pragma unroll
-            for (int r = 0; r < 8; r++) yh[j][r] = (uint32_t)p[32 * r];  // layout A: 128-B line per access
-        }
-        FwdTw ftw;
-        {   // 2 KiB table, L1 resident; reloaded per item (opaque pointer defeats hoisting) to keep registers low
-            const TwTable* tab = &TW_FWD;
-            asm volatile("" : "+l"(tab));
-            load_fwd_tw(ftw, tab, lane);
-        }
-#pragma unroll
-        for (int j = 0; j < L; j++) {
-            ntt_fwd_warp(yh[j], scr, ftw, lane);
-            __syncwarp();
-        }
     } else {
-#pragma unroll
-        for (int j = 0; j < L; j++) {
-            const int4* p = reinterpret_cast<const int4*>(v_item + j * N) + lane;
-            int4 lo = p[0], hi = p[32];
-            yh[j][0] = canon_signed(lo.x); yh[j][1] = canon_signed(lo.y); yh[j][2] = canon_signed(lo.z); yh[j][3] = canon_signed(lo.w);
-            yh[j][4] = canon_signed(hi.x); yh[j][5] = canon_signed(hi.y); yh[j][6] = canon_signed(hi.z); yh[j][7] = canon_signed(hi.w);
-        }
+        item_inputs<L, NTT_IN>(yh, v_item, scr, lane);
     }
     const int i_begin = SPLIT ? part * (K / 2) : 0, i_end = SPLIT ? (part + 1) * (K / 2) : K;
-    item_rows<K, LA, INTT_OUT, EXTRA, W1>(w_item, yh, a_sm, scr, lane, extra_item, w1_item, i_begin, i_end);
+    item_rows<K, LA, INTT_OUT, EXTRA, W1, PRESCALED>(w_item, yh, a_sm, scr, lane, extra_item, w1_item, i_begin, i_end);
 }
 
 #endif  // __CUDACC__

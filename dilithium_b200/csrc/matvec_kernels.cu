@@ -138,26 +138,91 @@ __global__ void __launch_bounds__(((G * K * L + 31) / 32) * 32) matvec_item_kern
         const int g = t / (K * L), ij = t % (K * L);
         if (item0 + g < batch) {
             uint32_t* out = a_sm + t * A_STRIDE;
-            expand_a_poly(rho + (item0 + g) * 32, ij / L, ij % L,
-                          [&](int idx, uint32_t val) { out[idx] = INTT_OUT ? mul_full(val, INV256) : val; });
+            expand_a_poly(rho + (item0 + g) * 32, ij / L, ij % L, [&](int idx, uint32_t val) { out[idx] = val; });   // unscaled
         }
     }
     __syncthreads();
     const int warp = t >> 5, lane = t & 31;
     if constexpr (SPLIT) {
         if (item0 < batch)   // uniform for the CTA: both warps enter (the core synchronises the CTA once)
-            item_core<K, L, NTT_IN, INTT_OUT, EXTRA, false, true>(w + item0 * K * N, v + item0 * (L + (EXTRA ? 1 : 0)) * N, a_sm,
+            item_core<K, L, NTT_IN, INTT_OUT, EXTRA, false, true, false>(w + item0 * K * N, v + item0 * (L + (EXTRA ? 1 : 0)) * N, a_sm,
                                                                  scr_all + warp * SCRATCH_WORDS, lane,
                                                                  EXTRA ? extra + item0 * K * N : nullptr, nullptr, yh_sm, warp);
     } else {
     for (int g = warp; g < G; g += NW) {
         const size_t item = item0 + g;
         if (item < batch)
-            item_core<K, L, NTT_IN, INTT_OUT, EXTRA>(w + item * K * N, v + item * (L + (EXTRA ? 1 : 0)) * N,
+            item_core<K, L, NTT_IN, INTT_OUT, EXTRA, false, false, false>(w + item * K * N, v + item * (L + (EXTRA ? 1 : 0)) * N,
                                                      a_sm + g * K * L * A_STRIDE, scr_all + warp * SCRATCH_WORDS, lane,
                                                      EXTRA ? extra + item * K * N : nullptr);
     }
     }
+}
+
+// ---- per-item-rho kernel, row-streamed: G = 8 items per CTA, A generated R rows at a time ----
+// The per-item matrix is the Keccak-bound part of key generation and per-key verification (>= 5 permutations for each
+// of the k*l polynomials of EVERY item, gen_a_ext.v:100-116 / rejection_a.v:67-112).  One item's whole matrix in
+// shared memory (matvec_item_kernel above) costs 16-56 KiB per item and leaves 6-7 warps per SM, most of them waiting
+// for their CTA's few Keccak threads.  Here a CTA owns 8 items and streams their matrices through shared memory R rows
+// at a time: G*l*R = 128 / 120 / 112 threads (levels 2 / 3 / 5) - four warps, one per SM sub-partition, every lane a
+// Keccak state - expand rows [i, i+R) of all 8 items, then the CTA's 8 warps (one per item, its transformed inputs in
+// registers) multiply-accumulate those rows, reduce, inverse-transform and store them, and the next R rows follow.
+// A never exists anywhere but in this R-row window; the Keccak phase, which is the bound, runs with full lanes on all
+// four ALU pipes for ~80 % of the CTA's life instead of ~50 %.
+template <int K, int L>
+__host__ __device__ constexpr int rows_per_step() { return K * L == 16 ? 4 : (K * L == 30 ? 3 : 2); }
+constexpr int ROWS_G = 8;   // items (= consumer warps) per CTA
+
+template <int K, int L, bool NTT_IN, bool INTT_OUT, bool EXTRA>
+__global__ void __launch_bounds__(ROWS_G * 32, 1) matvec_item_rows_kernel(int32_t* __restrict__ w, const uint8_t* __restrict__ rho,
+                                                                          const int32_t* __restrict__ v, uint32_t batch,
+                                                                          const int32_t* __restrict__ extra) {
+    constexpr int R = rows_per_step<K, L>();
+    constexpr int LI = L + (EXTRA ? 1 : 0);                      // input polynomials per item
+    static_assert(K % R == 0 && ROWS_G * L * R <= ROWS_G * 32, "row window must tile the matrix and fit the CTA's threads");
+    extern __shared__ __align__(16) uint32_t smem_u32v[];
+    uint32_t* rows_sm = smem_u32v;                               // [R][G][L] polynomials, stride A_STRIDE
+    uint32_t* scr_all = smem_u32v + R * ROWS_G * L * A_STRIDE;   // G * SCRATCH_WORDS
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    uint32_t* scr = scr_all + warp * SCRATCH_WORDS;
+    for (size_t item0 = (size_t)blockIdx.x * ROWS_G; item0 < batch; item0 += (size_t)gridDim.x * ROWS_G) {
+        const size_t item = item0 + warp;
+        const bool live = item < batch;                          // warp-uniform
+        uint32_t yh[LI][8];
+        if (live) item_inputs<LI, NTT_IN>(yh, v + item * LI * N, scr, lane);
+#pragma unroll 1
+        for (int i0 = 0; i0 < K; i0 += R) {
+            __syncthreads();                                     // the previous window has been consumed
+            if (t < R * ROWS_G * L) {
+                const int r = t / (ROWS_G * L), g = (t / L) % ROWS_G, j = t % L;
+                if (item0 + g < batch) {
+                    uint32_t* out = rows_sm + t * A_STRIDE;      // t == (r * G + g) * L + j
+                    expand_a_poly(rho + (item0 + g) * 32, i0 + r, j, [&](int idx, uint32_t val) { out[idx] = val; });   // unscaled
+                }
+            }
+            __syncthreads();
+            if (live) {
+#pragma unroll 1
+                for (int r = 0; r < R; r++)
+                    item_rows<K, L, INTT_OUT, EXTRA, false, false>(w + item * K * N, yh, rows_sm + (size_t)(r * ROWS_G + warp) * L * A_STRIDE, scr, lane,
+                                                           EXTRA ? extra + item * K * N : nullptr, nullptr, i0 + r, i0 + r + 1, i0 + r);
+            }
+        }
+    }
+}
+
+template <int K, int L, bool NTT_IN, bool INTT_OUT, bool EXTRA>
+static cudaError_t launch_item_rows_t(int32_t* w, const uint8_t* rho, const int32_t* v, const int32_t* extra, size_t batch, int sm_count,
+                                      cudaStream_t st) {
+    constexpr int R = rows_per_step<K, L>();
+    constexpr size_t smem = (size_t)(R * ROWS_G * L * A_STRIDE + ROWS_G * SCRATCH_WORDS) * 4;
+    static_assert(smem <= 227 * 1024, "row window does not fit in shared memory");
+    auto kern = matvec_item_rows_kernel<K, L, NTT_IN, INTT_OUT, EXTRA>;
+    static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
+    if (cudaError_t e = ensure_dyn_smem(kern, smem, configured); e != cudaSuccess) return e;
+    const size_t want = (batch + ROWS_G - 1) / ROWS_G, cap = (size_t)sm_count * 8;
+    kern<<<(unsigned)(want < cap ? want : cap), ROWS_G * 32, smem, st>>>(w, rho, v, (uint32_t)batch, extra);
+    return cudaGetLastError();
 }
 
 template <int K, int L>
@@ -209,9 +274,17 @@ static cudaError_t launch_item_t(int32_t* w, const uint8_t* rho, const int32_t* 
     return cudaGetLastError();
 }
 
+// Batches of at least this many items use the row-streamed per-item kernel.  Measured on B200 (profiles/r2b_per_item_ab.txt)
+// the one-CTA-per-item kernel is 5-10 % faster at every level, so the row-streamed variant is off unless
+// dil_diag_item_rows_threshold selects it (A/B measurements).
+static std::atomic<size_t> g_item_rows_min{~(size_t)0};
+void set_item_rows_threshold(size_t n) { g_item_rows_min.store(n); }
+
 template <int K, int L>
 static cudaError_t launch_item_flags(int32_t* w, const uint8_t* rho, const int32_t* v, size_t batch, bool ntt_in,
-                                     bool intt_out, cudaStream_t st) {
+                                     bool intt_out, int sm_count, cudaStream_t st) {
+    // the fully fused shape (key generation, cfg3 mode P) streams A row windows; small batches keep one CTA per item
+    if (ntt_in && intt_out && batch >= g_item_rows_min.load()) return launch_item_rows_t<K, L, true, true, false>(w, rho, v, nullptr, batch, sm_count, st);
     if (ntt_in && intt_out) return launch_item_t<K, L, true, true>(w, rho, v, batch, st);
     if (ntt_in) return launch_item_t<K, L, true, false>(w, rho, v, batch, st);
     if (intt_out) return launch_item_t<K, L, false, true>(w, rho, v, batch, st);
@@ -223,9 +296,9 @@ cudaError_t launch_matvec_expand(int32_t* w, const uint8_t* rho, const int32_t* 
     if (batch == 0) return cudaSuccess;
     const bool per_item = flags & DIL_RHO_PER_ITEM, ni = flags & DIL_NTT_INPUT, io = flags & DIL_INTT_OUTPUT;
     if (per_item) {
-        if (k == 4 && l == 4) return launch_item_flags<4, 4>(w, rho, v, batch, ni, io, st);
-        if (k == 6 && l == 5) return launch_item_flags<6, 5>(w, rho, v, batch, ni, io, st);
-        if (k == 8 && l == 7) return launch_item_flags<8, 7>(w, rho, v, batch, ni, io, st);
+        if (k == 4 && l == 4) return launch_item_flags<4, 4>(w, rho, v, batch, ni, io, sm_count, st);
+        if (k == 6 && l == 5) return launch_item_flags<6, 5>(w, rho, v, batch, ni, io, sm_count, st);
+        if (k == 8 && l == 7) return launch_item_flags<8, 7>(w, rho, v, batch, ni, io, sm_count, st);
     } else {
         if (k == 4 && l == 4) return launch_shared_flags<4, 4, true>(w, nullptr, rho, v, batch, ni, io, sm_count, st);
         if (k == 6 && l == 5) return launch_shared_flags<6, 5, true>(w, nullptr, rho, v, batch, ni, io, sm_count, st);
@@ -269,6 +342,16 @@ static cudaError_t launch_verify_item_t(int32_t* w, const uint8_t* rho, const in
 cudaError_t launch_verify_core_item(int32_t* w, const uint8_t* rho, const int32_t* v, const int32_t* extra, int level,
                                     size_t batch, cudaStream_t st) {
     if (batch == 0) return cudaSuccess;
+    if (batch >= g_item_rows_min.load()) {   // row-streamed kernel (8 items per CTA); tiny batches keep one CTA per item
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        switch (level) {
+            case 2: return launch_item_rows_t<4, 4, true, true, true>(w, rho, v, extra, batch, sms, st);
+            case 3: return launch_item_rows_t<6, 5, true, true, true>(w, rho, v, extra, batch, sms, st);
+            case 5: return launch_item_rows_t<8, 7, true, true, true>(w, rho, v, extra, batch, sms, st);
+        }
+        return cudaErrorInvalidValue;
+    }
     switch (level) {
         case 2: return launch_verify_item_t<4, 4>(w, rho, v, extra, batch, st);
         case 3: return launch_verify_item_t<6, 5>(w, rho, v, extra, batch, st);

@@ -447,3 +447,70 @@ class VerifyKey:
                                                    ctypes.c_void_p(d_h.data_ptr()), ctypes.c_void_p(d_c.data_ptr()),
                                                    ctypes.c_void_p(d_ok.data_ptr()), self.engine._stream())
         self.engine._check(rc, "dil_verify_batch_dev")
+
+
+class Pool:
+    """Several GPUs in one process (dil_pool_*): one engine per device, batches split into contiguous shards."""
+
+    def __init__(self, devices=None):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        if devices:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            rc = self._lib.dil_pool_create(ctypes.byref(h), arr, len(devices))
+        else:
+            rc = self._lib.dil_pool_create(ctypes.byref(h), None, 0)
+        if rc != 0:
+            raise DilithiumError(f"dil_pool_create failed: {self._lib.dil_status_string(rc).decode()}")
+        self._h = h
+        self._key = None
+
+    @property
+    def size(self):
+        return self._lib.dil_pool_size(self._h)
+
+    def load_key(self, level, rho, key, tr, s1_packed, s2_packed, t0_packed):
+        self.drop_key()
+        bufs = [np.ascontiguousarray(x, dtype=np.uint8) for x in (rho, key, tr, s1_packed, s2_packed, t0_packed)]
+        k = ctypes.c_void_p()
+        rc = self._lib.dil_pool_sign_key_create(self._h, ctypes.byref(k), int(level), *[b.ctypes.data_as(ctypes.c_void_p) for b in bufs])
+        if rc != 0:
+            raise DilithiumError(f"dil_pool_sign_key_create failed: {self._lib.dil_status_string(rc).decode()}")
+        self._key, self.level = k, int(level)
+
+    def drop_key(self):
+        if self._key:
+            self._lib.dil_pool_sign_key_destroy(self._h, self._key)
+            self._key = None
+
+    def sign_into(self, msgs_ptr, offsets_ptr, n, z_ptr, h_ptr, c_ptr, att_ptr):
+        """Raw-pointer form (host memory; pinned portable output buffers are streamed to)."""
+        P = ctypes.c_void_p
+        rc = self._lib.dil_pool_sign_batch_host(self._h, self._key, P(msgs_ptr), P(offsets_ptr), n, P(z_ptr), P(h_ptr), P(c_ptr), P(att_ptr))
+        if rc != 0:
+            raise DilithiumError(f"dil_pool_sign_batch_host failed: {self._lib.dil_status_string(rc).decode()}")
+
+    def sign(self, msgs):
+        n = len(msgs)
+        k, l = LEVEL_DIMS[self.level]
+        zb = l * (576 if self.level == 2 else 640)
+        hb = {2: 84, 3: 61, 5: 83}[self.level]
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(m) for m in msgs])
+        blob = np.frombuffer(b"".join(msgs), dtype=np.uint8).copy() if off[-1] else np.zeros(1, np.uint8)
+        z = np.empty((n, zb), np.uint8); h = np.empty((n, hb), np.uint8); c = np.empty((n, 32), np.uint8)
+        att = np.zeros(n, np.uint32)
+        self.sign_into(blob.ctypes.data, off.ctypes.data, n, z.ctypes.data, h.ctypes.data, c.ctypes.data, att.ctypes.data)
+        return z, h, c, att
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.drop_key()
+            self._lib.dil_pool_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -199,11 +199,33 @@ int dil_verify_multi_dev(dil_engine_t *e, int level, const uint8_t *d_rho, const
 int dil_keygen_batch_host(dil_engine_t *e, int level, const uint8_t *xi, size_t n, uint8_t *rho, uint8_t *key, uint8_t *tr,
                           uint8_t *s1_packed, uint8_t *s2_packed, uint8_t *t1_packed, uint8_t *t0_packed);
 
+/* ---- several GPUs in one process (items are independent, shards need no exchange) ----
+ * A pool owns one engine per device (devices == NULL or n_devices == 0: every visible device; a device may be listed
+ * twice).  dil_pool_sign_batch_host splits the batch into contiguous shards, one per engine, and signs them concurrently
+ * (one host thread per engine, each through dil_sign_batch_host: pinned output buffers - cudaHostAllocPortable /
+ * cudaHostRegisterPortable - are streamed to round by round).  Results are identical to signing the whole batch on one
+ * engine.  The only thing every GPU receives is the packed key (the path's single broadcast). */
+typedef struct dil_pool dil_pool_t;
+typedef struct dil_pool_sign_key dil_pool_sign_key_t;
+int dil_pool_create(dil_pool_t **out, const int *devices, int n_devices);
+int dil_pool_destroy(dil_pool_t *p);
+int dil_pool_size(const dil_pool_t *p);
+dil_engine_t *dil_pool_engine(dil_pool_t *p, int i);
+int dil_pool_sign_key_create(dil_pool_t *p, dil_pool_sign_key_t **out, int level, const uint8_t *rho, const uint8_t *key,
+                             const uint8_t *tr, const uint8_t *s1_packed, const uint8_t *s2_packed, const uint8_t *t0_packed);
+int dil_pool_sign_key_destroy(dil_pool_t *p, dil_pool_sign_key_t *k);
+int dil_pool_sign_batch_host(dil_pool_t *p, dil_pool_sign_key_t *k, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                             uint8_t *z, uint8_t *h, uint8_t *ctilde, uint32_t *attempts);
+
 /* ---- diagnostics ----
  * Pure Keccak-f[1600] rate of the device: sm_count * ctas_per_sm CTAs of 128 threads, every thread runs perms_per_thread
  * permutations on its own state (the permutation code of every hash kernel of the engine) and writes one word to
  * d_out[thread].  The caller times the launch; bench.py uses it as the measured ALU-pipe roofline of the run. */
 int dil_diag_keccak_dev(dil_engine_t *e, uint64_t *d_out, unsigned ctas_per_sm, unsigned perms_per_thread, void *stream);
+/* Per-item-rho batches of at least min_batch items use the row-streamed kernel (8 items per CTA, A generated a few rows
+ * at a time), smaller ones one CTA per item.  Default: never (the one-CTA-per-item kernel measured 5-10 % faster);
+ * process-wide, atomic; results are identical - this exists for A/B measurements. */
+int dil_diag_item_rows_threshold(size_t min_batch);
 
 /* ---- north_star aliases (plain domain, identical to the above) ---- */
 int dil_invntt_tomont_dev(dil_engine_t *e, int32_t *dst, const int32_t *src, size_t n_polys, void *stream);

@@ -31,11 +31,31 @@ def test_class_tables_cover_profile_classes():
 def test_keccak_roofline_counts():
     b = load_bench()
     # level 2: 4 polynomials x 5 blocks; challenge absorbs 64 + 768 bytes (7 permutations) + SampleInBall (1)
-    r = b.keccak_roofline("expand_mask", 2, 65536, 0.333)
-    assert r["permutations_per_slot"] == 20 and 0.5 < r["frac"] < 1.0
+    r = b.keccak_roofline("expand_mask", 2, 65536, 0.333, 4.27, "a measurement")
+    assert r["permutations_per_slot"] == 20 and 0.5 < r["frac"] < 1.0 and r["peak_source"] == "a measurement"
+    assert "frac" not in b.keccak_roofline("expand_mask", 2, 65536, 0.333)      # no peak measured -> no fraction claimed
     assert b.keccak_roofline("challenge", 2, 65536, 0.165)["permutations_per_slot"] == 8
     assert b.keccak_roofline("challenge", 5, 65536, 0.2)["permutations_per_slot"] == (64 + 8 * 128) // 136 + 2
     assert b.keccak_roofline("tail", 2, 65536, 0.2) is None
+
+
+def test_limiter_comes_from_the_committed_ncu_table():
+    b = load_bench()
+    lim = b.ncu_limiter("expand_mask")
+    assert lim["top_pipe"] == "alu" and lim["pct_busy"]["alu"] > 90 and "profiles/" in lim["source"]
+    assert b.ncu_limiter("signcore")["top_pipe"] == "fmaheavy"
+    assert b.ncu_limiter("no such class") is None
+
+
+def test_keccak_sass_mix_of_the_shipped_library():
+    """The ALU-pipe model of the Keccak peak counts the round body's instructions in the shipped .so (skipped without cuobjdump)."""
+    import shutil
+    import pytest
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not installed")
+    b = load_bench()
+    mix = b.keccak_sass_mix()
+    assert mix is not None and 170 <= mix["instructions_per_round"] <= 210 and mix["alu_pipe"] >= 160
 
 
 def test_committed_traffic_table():
