@@ -393,6 +393,7 @@ def cfg3_record(c, keccak_peak):
     ms_s = c.time_ms(lambda: eng.matvec_expand(rho, y, k, l, ntt_input=True, intt_output=True, w=w), 10)
     ms_p = c.time_ms(lambda: eng.matvec_expand(rho_p, y, k, l, per_item=True, ntt_input=True, intt_output=True, w=w), 3, warm=1)
     del y, w
+    torch.cuda.empty_cache()
     key = d.SignKey(eng, level, *[kk[f] for f in ("rho", "k", "tr", "s1", "s2", "t0")])
     _, _, msgs, offs, z, h, ct, att = sign_buffers(c, key, B, SEED + 31 + c.rank)
     ms_sign = c.time_ms(lambda: key.sign_dev(msgs, offs, B, z, h, ct, att), 3, warm=1)
@@ -515,6 +516,7 @@ def cfg5_sweep(c, max_log2):
             ms_ntt = c.time_ms(lambda: eng.ntt(y, out=o), it, warm=1)
             ms_core = c.time_ms(lambda: eng.signcore(a_hat, y, k, l, w=w), it, warm=1)
             del y, o, w
+            torch.cuda.empty_cache()
             _, _, msgs, offs, z, h, ct, att = sign_buffers(c, sk, b, SEED + lg)
             ms_sign = c.time_ms(lambda: sk.sign_dev(msgs, offs, b, z, h, ct, att), max(it // 2, 1), warm=1)
             ok = torch.zeros(b, dtype=torch.uint8, device=c.dev)

@@ -138,10 +138,12 @@ __device__ __forceinline__ void shake256_absorb_lanes(uint64_t (&A)[25], size_t 
     keccak_f1600(A);
 }
 
-// little-endian 64-bit load from an arbitrarily aligned byte string, zero beyond `len`
+// little-endian 64-bit load from an arbitrarily aligned byte string, zero beyond `len`; one 8-byte load when the
+// lane lies inside the string and happens to be 8-byte aligned (packed keys, fixed-length messages), else byte loads
 __device__ __forceinline__ uint64_t load_lane_bytes(const uint8_t* __restrict__ p, size_t off, size_t len) {
     uint64_t v = 0;
     if (off + 8 <= len) {
+        if ((reinterpret_cast<uintptr_t>(p + off) & 7u) == 0) return *reinterpret_cast<const uint64_t*>(p + off);
 #pragma unroll
         for (int b = 0; b < 8; b++) v |= (uint64_t)p[off + b] << (8 * b);
     } else {

@@ -857,6 +857,19 @@ int ensure_vws(dil_engine* e, dil_verify_key* k, size_t n) {
 int verify_run(dil_engine* e, dil_verify_key* k, const uint8_t* d_msgs, const uint64_t* d_off, size_t n, const uint8_t* d_z,
                const uint8_t* d_h, const uint8_t* d_ct, uint8_t* d_ok, cudaStream_t st) {
     const LevelParams& P = k->P;
+    // very large batches are verified in 2^20-signature pieces so that the unpacked intermediates (about 9 / 12 / 17 KB per
+    // signature at levels 2 / 3 / 5) stay bounded; the pieces run back to back on the caller's stream
+    constexpr size_t CHUNK = (size_t)1 << 20;
+    if (n > CHUNK + CHUNK / 4) {
+        const size_t zb = (size_t)P.l * P.z_bytes, hb = (size_t)P.omega + P.k;
+        for (size_t lo = 0; lo < n;) {
+            const size_t m = n - lo <= CHUNK + CHUNK / 4 ? n - lo : CHUNK;
+            int rc = verify_run(e, k, d_msgs, d_off + lo, m, d_z + lo * zb, d_h + lo * hb, d_ct + lo * 32, d_ok + lo, st);
+            if (rc) return rc;
+            lo += m;
+        }
+        return DIL_OK;
+    }
     int rc = ensure_vws(e, k, n);
     if (rc) return rc;
     const uint32_t nn = (uint32_t)n;

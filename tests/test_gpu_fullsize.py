@@ -144,3 +144,30 @@ def test_cfg4_full_shard_per_item_keys_with_kat_injection(eng, oracle):
     assert np.array_equal(ok2, exp)
     for m in (5, 6, 9, 1005, 2006, 3009):
         assert oracle.verify(level, rho[m], t1x[m], msgs2[m], z2[m], h[m], c[m]) != 0
+
+
+def test_very_large_batch_is_signed_and_verified_in_pieces(eng):
+    """Beyond 1.25 x 2^20 items dil_sign_batch_dev and dil_verify_batch_dev work in 2^20-item pieces (bounded workspace);
+    1.4 M Dilithium-2 signatures: all accepted, tampered ones on both sides of the piece boundary rejected exactly."""
+    import torch
+    import dilithium_b200 as d
+    level, n, mlen = 2, 1_400_000, 16
+    K = ol.kat(level)
+    sk = d.SignKey(eng, level, *[K[f][9] for f in ("rho", "k", "tr", "s1", "s2", "t0")])
+    vk = d.VerifyKey(eng, level, K["rho"][9], K["t1"][9])
+    gen = torch.Generator(device="cuda").manual_seed(14)
+    msgs = torch.randint(0, 256, (n * mlen,), dtype=torch.uint8, device="cuda", generator=gen)
+    off = torch.arange(n + 1, dtype=torch.int64, device="cuda") * mlen
+    z = torch.zeros((n, sk.z_bytes), dtype=torch.uint8, device="cuda"); h = torch.zeros((n, sk.h_bytes), dtype=torch.uint8, device="cuda")
+    c = torch.zeros((n, 32), dtype=torch.uint8, device="cuda"); att = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ok = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    sk.sign_dev(msgs, off, n, z, h, c, att)
+    vk.verify_dev(msgs, off, n, z, h, c, ok)
+    assert int(att.min()) >= 1 and int(ok.sum()) == n
+    bad = torch.tensor([0, (1 << 20) - 1, 1 << 20, (1 << 20) + 1, n - 1], device="cuda")
+    z[bad, 40] ^= 1
+    vk.verify_dev(msgs, off, n, z, h, c, ok)
+    exp = torch.ones(n, dtype=torch.uint8, device="cuda")
+    exp[bad] = 0
+    assert torch.equal(ok, exp)
+    sk.close(); vk.close()
