@@ -66,6 +66,7 @@ SIGNATURES = {
     "dil_verify_multi_host": (c_int, [c_void, c_int, c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void]),
     "dil_verify_multi_dev": (c_int, [c_void, c_int, c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void, c_void]),
     "dil_keygen_batch_host": (c_int, [c_void, c_int, c_void, c_size] + [c_void] * 7),
+    "dil_keygen_batch_dev": (c_int, [c_void, c_int, c_void, c_size] + [c_void] * 8),
     "dil_pool_create": (c_int, [ctypes.POINTER(c_void), c_void, c_int]),
     "dil_pool_destroy": (c_int, [c_void]),
     "dil_pool_size": (c_int, [c_void]),

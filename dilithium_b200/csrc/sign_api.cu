@@ -976,6 +976,7 @@ int dil_verify_batch_host(dil_engine_t* e, dil_verify_key_t* k, const uint8_t* m
     if (!e || !k) return DIL_ERR_ARG;
     if (n == 0) return DIL_OK;
     if (!msgs || !offsets || !z || !h || !ctilde || !ok || n > 0x7FFFFFFFu) return DIL_ERR_ARG;
+    if (!offsets_ok(offsets, n)) return DIL_ERR_ARG;
     std::lock_guard<std::mutex> g(k->mu);
     DeviceGuard dg(e->device);
     if (!dg.ok) return DIL_ERR_CUDA;
@@ -1002,15 +1003,37 @@ int dil_verify_batch_host(dil_engine_t* e, dil_verify_key_t* k, const uint8_t* m
         CK(dmalloc(&k->off_d, n + 1));
         k->io_cap = n;
     }
-    CK(cudaMemcpyAsync(k->msgs_d, msgs, offsets[n], cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(k->off_d, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(k->z_d, z, n * zb, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(k->h_d, h, n * hb, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(k->ct_d, ctilde, n * 32, cudaMemcpyHostToDevice, st));
-    int rc = verify_run(e, k, k->msgs_d, k->off_d, n, k->z_d, k->h_d, k->ct_d, k->ok_d, st);
+    // Streaming: signatures (2.4-4.6 KB each) cross PCIe in 64 K-signature pieces on the copy stream while the previous
+    // piece is being verified on the host stream; messages and offsets (small) go first.
+    cudaStream_t cs = e->copy_stream;
+    cudaEvent_t ready = nullptr;
+    CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    cudaError_t err = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+    A(cudaMemcpyAsync(k->msgs_d, msgs, offsets[n], cudaMemcpyHostToDevice, st));
+    A(cudaMemcpyAsync(k->off_d, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    // the staging buffers may still be read by the previous call's kernels on the host stream
+    A(cudaEventRecord(ready, st));
+    A(cudaStreamWaitEvent(cs, ready, 0));
+    constexpr size_t PIECE = 65536;
+    int rc = DIL_OK;
+    for (size_t lo = 0; lo < n && err == cudaSuccess && rc == DIL_OK;) {
+        const size_t m = n - lo <= PIECE + PIECE / 4 ? n - lo : PIECE;
+        A(cudaMemcpyAsync(k->z_d + lo * zb, z + lo * zb, m * zb, cudaMemcpyHostToDevice, cs));
+        A(cudaMemcpyAsync(k->h_d + lo * hb, h + lo * hb, m * hb, cudaMemcpyHostToDevice, cs));
+        A(cudaMemcpyAsync(k->ct_d + lo * 32, ctilde + lo * 32, m * 32, cudaMemcpyHostToDevice, cs));
+        A(cudaEventRecord(ready, cs));
+        A(cudaStreamWaitEvent(st, ready, 0));
+        if (err == cudaSuccess) rc = verify_run(e, k, k->msgs_d, k->off_d + lo, m, k->z_d + lo * zb, k->h_d + lo * hb, k->ct_d + lo * 32, k->ok_d + lo, st);
+        lo += m;
+    }
+    if (err == cudaSuccess && rc == DIL_OK) A(cudaMemcpyAsync(ok, k->ok_d, n, cudaMemcpyDeviceToHost, st));
+    cudaError_t e1 = cudaStreamSynchronize(cs), e2 = cudaStreamSynchronize(st);
+    cudaEventDestroy(ready);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(ok, k->ok_d, n, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if (err != cudaSuccess) return fail(e, err, "dil_verify_batch_host");
+    if (e1 != cudaSuccess) return fail(e, e1, "verify H2D sync");
+    if (e2 != cudaSuccess) return fail(e, e2, "verify sync");
     return DIL_OK;
 }
 
@@ -1018,63 +1041,6 @@ int dil_verify_batch_host(dil_engine_t* e, dil_verify_key_t* k, const uint8_t* m
 
 // =======================================================================================
 // Batched key generation (combined_top.v mode 0; outputs as rtl_tb/tb_keygen_top.v:180-275)
-// =======================================================================================
-extern "C" int dil_keygen_batch_host(dil_engine_t* e, int level, const uint8_t* xi, size_t n, uint8_t* rho, uint8_t* key,
-                                     uint8_t* tr, uint8_t* s1p, uint8_t* s2p, uint8_t* t1p, uint8_t* t0p) {
-    if (!e) return DIL_ERR_ARG;
-    if (level != 2 && level != 3 && level != 5) return DIL_ERR_ARG;
-    if (n == 0) return DIL_OK;
-    if (!xi || !rho || !key || !tr || !s1p || !s2p || !t1p || !t0p || n > 0x00FFFFFFu) return DIL_ERR_ARG;
-    std::lock_guard<std::mutex> g(e->mu);
-    DeviceGuard dg(e->device);
-    if (!dg.ok) return DIL_ERR_CUDA;
-    const LevelParams P = dil::level_params(level);
-    cudaStream_t st = e->host_stream;
-    const size_t K = P.k, L = P.l, sb = P.s_bytes;
-    // one transient arena for the whole batch
-    struct Seg { size_t off, bytes; };
-    size_t total = 0;
-    auto seg = [&](size_t bytes) { Seg s{total, bytes}; total += (bytes + 255) & ~(size_t)255; return s; };
-    Seg S_xi = seg(n * 32), S_rho = seg(n * 32), S_key = seg(n * 32), S_tr = seg(n * 32), S_rhop = seg(n * 64);
-    Seg S_s1 = seg(n * L * 1024), S_s2 = seg(n * K * 1024), S_t = seg(n * K * 1024);
-    Seg S_s1p = seg(n * L * sb), S_s2p = seg(n * K * sb), S_t1p = seg(n * K * 320), S_t0p = seg(n * K * 416);
-    uint8_t* base = nullptr;
-    cudaError_t aerr = cudaMalloc(reinterpret_cast<void**>(&base), total);
-    if (aerr != cudaSuccess) {
-        return fail_msg(e, DIL_ERR_ALLOC, std::string("keygen arena: ") + cudaGetErrorString(aerr));
-    }
-    auto P8 = [&](Seg s) { return base + s.off; };
-    auto P32 = [&](Seg s) { return reinterpret_cast<int32_t*>(base + s.off); };
-    int rc = DIL_OK;
-    cudaError_t err = cudaSuccess;
-    auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
-    A(cudaMemcpyAsync(P8(S_xi), xi, n * 32, cudaMemcpyHostToDevice, st));
-    A(dil::launch_keygen_seed(P8(S_rho), reinterpret_cast<uint64_t*>(P8(S_rhop)), P8(S_key), P8(S_xi), (uint32_t)n, st));
-    A(dil::launch_eta_sample(level, P32(S_s1), P32(S_s2), reinterpret_cast<const uint64_t*>(P8(S_rhop)), (uint32_t)n, st));
-    // t = INTT(ExpandA(rho) * NTT(s1)): per-item rho, A generated on chip
-    A(dil::launch_matvec_expand(P32(S_t), P8(S_rho), P32(S_s1), P.k, P.l, n, DIL_RHO_PER_ITEM | DIL_NTT_INPUT | DIL_INTT_OUTPUT,
-                                e->sm_count, st));
-    A(dil::launch_t_pack(P8(S_t1p), P8(S_t0p), P32(S_t), P32(S_s2), n * K, st));
-    A(dil::launch_s_pack(P.eta, P8(S_s1p), P32(S_s1), n * L, st));
-    A(dil::launch_s_pack(P.eta, P8(S_s2p), P32(S_s2), n * K, st));
-    A(dil::launch_tr_batch(P8(S_tr), P8(S_rho), P8(S_t1p), (uint32_t)(K * 320), (uint32_t)n, st));
-    A(cudaMemcpyAsync(rho, P8(S_rho), n * 32, cudaMemcpyDeviceToHost, st));
-    A(cudaMemcpyAsync(key, P8(S_key), n * 32, cudaMemcpyDeviceToHost, st));
-    A(cudaMemcpyAsync(tr, P8(S_tr), n * 32, cudaMemcpyDeviceToHost, st));
-    A(cudaMemcpyAsync(s1p, P8(S_s1p), n * L * sb, cudaMemcpyDeviceToHost, st));
-    A(cudaMemcpyAsync(s2p, P8(S_s2p), n * K * sb, cudaMemcpyDeviceToHost, st));
-    A(cudaMemcpyAsync(t1p, P8(S_t1p), n * K * 320, cudaMemcpyDeviceToHost, st));
-    A(cudaMemcpyAsync(t0p, P8(S_t0p), n * K * 416, cudaMemcpyDeviceToHost, st));
-    A(cudaStreamSynchronize(st));
-    if (err != cudaSuccess) rc = fail(e, err, "dil_keygen_batch_host");
-    else e->launches += 7;
-    cudaFree(base);
-    return rc;
-}
-
-// =======================================================================================
-// Verification with one public key PER signature (SURVEY.md §8d cfg4 "per-item rho"): A is expanded
-// on chip from rho[i] inside the fused kernel; t1[i] is unpacked, negated, scaled and NTT'd per item.
 // =======================================================================================
 namespace {
 struct Arena {   // carve 256-byte aligned segments out of one grow-only device allocation (engine staging slot 3)
@@ -1097,6 +1063,135 @@ int arena_reserve(dil_engine* e, size_t bytes, uint8_t** base) {
     return DIL_OK;
 }
 
+// one piece of a key-generation batch; all pointers device pointers; `work` holds the intermediates (keygen_work_bytes)
+size_t keygen_work_bytes(const LevelParams& P, size_t n) {
+    auto r = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    return r(n * 64) + r(n * P.l * 1024) + 2 * r(n * P.k * 1024);
+}
+cudaError_t keygen_piece(dil_engine* e, const LevelParams& P, uint8_t* work, const uint8_t* d_xi, size_t n, uint8_t* d_rho, uint8_t* d_key,
+                         uint8_t* d_tr, uint8_t* d_s1p, uint8_t* d_s2p, uint8_t* d_t1p, uint8_t* d_t0p, cudaStream_t st) {
+    auto r = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t K = P.k, L = P.l;
+    uint64_t* rhop = reinterpret_cast<uint64_t*>(work);
+    int32_t* s1 = reinterpret_cast<int32_t*>(work + r(n * 64));
+    int32_t* s2 = reinterpret_cast<int32_t*>(work + r(n * 64) + r(n * L * 1024));
+    int32_t* t = reinterpret_cast<int32_t*>(work + r(n * 64) + r(n * L * 1024) + r(n * K * 1024));
+    cudaError_t err = cudaSuccess;
+    auto A = [&](cudaError_t x) { if (err == cudaSuccess) err = x; };
+    A(dil::launch_keygen_seed(d_rho, rhop, d_key, d_xi, (uint32_t)n, st));
+    A(dil::launch_eta_sample(P.level, s1, s2, rhop, (uint32_t)n, st));
+    // t = INTT(ExpandA(rho) * NTT(s1)): per-item rho, A generated on chip
+    A(dil::launch_matvec_expand(t, d_rho, s1, P.k, P.l, n, DIL_RHO_PER_ITEM | DIL_NTT_INPUT | DIL_INTT_OUTPUT, e->sm_count, st));
+    A(dil::launch_t_pack(d_t1p, d_t0p, t, s2, n * K, st));
+    A(dil::launch_s_pack(P.eta, d_s1p, s1, n * L, st));
+    A(dil::launch_s_pack(P.eta, d_s2p, s2, n * K, st));
+    A(dil::launch_tr_batch(d_tr, d_rho, d_t1p, (uint32_t)(K * 320), (uint32_t)n, st));
+    if (err == cudaSuccess) e->launches += 7;
+    return err;
+}
+constexpr size_t KEYGEN_PIECE = 16384;   // keys per piece: 0.2-0.4 GB of intermediates (s1, s2, t as int32 polynomials)
+}  // namespace
+
+// device pointers in, device pointers out; enqueues on `stream` (the secret intermediates live in an engine-owned
+// workspace that the next user waits for)
+extern "C" int dil_keygen_batch_dev(dil_engine_t* e, int level, const uint8_t* d_xi, size_t n, uint8_t* d_rho, uint8_t* d_key,
+                                    uint8_t* d_tr, uint8_t* d_s1p, uint8_t* d_s2p, uint8_t* d_t1p, uint8_t* d_t0p, void* stream) {
+    if (!e) return DIL_ERR_ARG;
+    if (level != 2 && level != 3 && level != 5) return DIL_ERR_ARG;
+    if (n == 0) return DIL_OK;
+    if (!d_xi || !d_rho || !d_key || !d_tr || !d_s1p || !d_s2p || !d_t1p || !d_t0p || n > 0x00FFFFFFu) return DIL_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_rho) | reinterpret_cast<uintptr_t>(d_key) | reinterpret_cast<uintptr_t>(d_tr)) & 7u) return DIL_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    const LevelParams P = dil::level_params(level);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t K = P.k, L = P.l, sb = P.s_bytes;
+    const size_t piece = n < KEYGEN_PIECE ? n : KEYGEN_PIECE;
+    uint8_t* work = nullptr;
+    int rc = arena_reserve(e, keygen_work_bytes(P, piece), &work);
+    if (rc) return rc;
+    cudaError_t err = cudaSuccess;
+    if (!e->arena_done) err = cudaEventCreateWithFlags(&e->arena_done, cudaEventDisableTiming);
+    else err = cudaStreamWaitEvent(st, e->arena_done, 0);
+    for (size_t lo = 0; lo < n && err == cudaSuccess; lo += piece) {
+        const size_t m = n - lo < piece ? n - lo : piece;
+        err = keygen_piece(e, P, work, d_xi + lo * 32, m, d_rho + lo * 32, d_key + lo * 32, d_tr + lo * 32, d_s1p + lo * L * sb,
+                           d_s2p + lo * K * sb, d_t1p + lo * K * 320, d_t0p + lo * K * 416, st);
+    }
+    if (err == cudaSuccess) err = cudaEventRecord(e->arena_done, st);
+    if (err != cudaSuccess) return fail(e, err, "dil_keygen_batch_dev");
+    return DIL_OK;
+}
+
+// host pointers; pieces of 16 K keys: the packed keys of piece i cross PCIe on the copy stream while piece i + 1 is generated
+extern "C" int dil_keygen_batch_host(dil_engine_t* e, int level, const uint8_t* xi, size_t n, uint8_t* rho, uint8_t* key,
+                                     uint8_t* tr, uint8_t* s1p, uint8_t* s2p, uint8_t* t1p, uint8_t* t0p) {
+    if (!e) return DIL_ERR_ARG;
+    if (level != 2 && level != 3 && level != 5) return DIL_ERR_ARG;
+    if (n == 0) return DIL_OK;
+    if (!xi || !rho || !key || !tr || !s1p || !s2p || !t1p || !t0p || n > 0x00FFFFFFu) return DIL_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    const LevelParams P = dil::level_params(level);
+    cudaStream_t st = e->host_stream, cs = e->copy_stream;
+    const size_t K = P.k, L = P.l, sb = P.s_bytes;
+    const size_t piece = n < KEYGEN_PIECE ? n : KEYGEN_PIECE;
+    // one transient allocation: intermediates | two sets of packed outputs (double buffer) | seeds
+    auto r = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t out_bytes = r(piece * 32) * 3 + r(piece * L * sb) + r(piece * K * sb) + r(piece * K * 320) + r(piece * K * 416);
+    const size_t wbytes = keygen_work_bytes(P, piece);
+    const size_t total = wbytes + 2 * out_bytes + r(n * 32);
+    uint8_t* base = nullptr;
+    cudaError_t aerr = cudaMalloc(reinterpret_cast<void**>(&base), total);
+    if (aerr != cudaSuccess) return fail_msg(e, DIL_ERR_ALLOC, std::string("keygen arena: ") + cudaGetErrorString(aerr));
+    uint8_t* d_xi = base + wbytes + 2 * out_bytes;
+    cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    cudaError_t err = cudaSuccess;
+    auto A = [&](cudaError_t x) { if (err == cudaSuccess) err = x; };
+    for (int i = 0; i < 2; i++) {
+        A(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        A(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+    }
+    A(cudaMemcpyAsync(d_xi, xi, n * 32, cudaMemcpyHostToDevice, st));
+    int idx = 0;
+    for (size_t lo = 0; lo < n && err == cudaSuccess; lo += piece, idx ^= 1) {
+        const size_t m = n - lo < piece ? n - lo : piece;
+        uint8_t* o = base + wbytes + (size_t)idx * out_bytes;
+        uint8_t* o_rho = o; uint8_t* o_key = o_rho + r(piece * 32); uint8_t* o_tr = o_key + r(piece * 32);
+        uint8_t* o_s1 = o_tr + r(piece * 32); uint8_t* o_s2 = o_s1 + r(piece * L * sb); uint8_t* o_t1 = o_s2 + r(piece * K * sb);
+        uint8_t* o_t0 = o_t1 + r(piece * K * 320);
+        if (lo >= 2 * piece) A(cudaStreamWaitEvent(st, copied[idx], 0));   // this output set has left for the host
+        A(keygen_piece(e, P, base, d_xi + lo * 32, m, o_rho, o_key, o_tr, o_s1, o_s2, o_t1, o_t0, st));
+        A(cudaEventRecord(done[idx], st));
+        A(cudaStreamWaitEvent(cs, done[idx], 0));
+        A(cudaMemcpyAsync(rho + lo * 32, o_rho, m * 32, cudaMemcpyDeviceToHost, cs));
+        A(cudaMemcpyAsync(key + lo * 32, o_key, m * 32, cudaMemcpyDeviceToHost, cs));
+        A(cudaMemcpyAsync(tr + lo * 32, o_tr, m * 32, cudaMemcpyDeviceToHost, cs));
+        A(cudaMemcpyAsync(s1p + lo * L * sb, o_s1, m * L * sb, cudaMemcpyDeviceToHost, cs));
+        A(cudaMemcpyAsync(s2p + lo * K * sb, o_s2, m * K * sb, cudaMemcpyDeviceToHost, cs));
+        A(cudaMemcpyAsync(t1p + lo * K * 320, o_t1, m * K * 320, cudaMemcpyDeviceToHost, cs));
+        A(cudaMemcpyAsync(t0p + lo * K * 416, o_t0, m * K * 416, cudaMemcpyDeviceToHost, cs));
+        A(cudaEventRecord(copied[idx], cs));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(cs);
+    for (int i = 0; i < 2; i++) {
+        if (done[i]) cudaEventDestroy(done[i]);
+        if (copied[i]) cudaEventDestroy(copied[i]);
+    }
+    wipe_free(base, total);   // s1, s2, K, rho' were here
+    if (err != cudaSuccess) return fail(e, err, "dil_keygen_batch_host");
+    if (e1 != cudaSuccess) return fail(e, e1, "keygen sync");
+    if (e2 != cudaSuccess) return fail(e, e2, "keygen D2H sync");
+    return DIL_OK;
+}
+
+// =======================================================================================
+// Verification with one public key PER signature (SURVEY.md §8d cfg4 "per-item rho"): A is expanded
+// on chip from rho[i] inside the fused kernel; t1[i] is unpacked, negated, scaled and NTT'd per item.
+// =======================================================================================
+namespace {
 // all pointers device; `work` holds the intermediates laid out by the caller with multi_work_bytes()
 struct MultiWork { size_t tr, mu, bad, hm, v, w, t1n, w1p, total; };
 MultiWork multi_work_layout(const LevelParams& P, size_t n) {

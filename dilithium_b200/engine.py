@@ -302,6 +302,26 @@ class Engine:
         return out
 
 
+def _keygen_dev(self, level, d_seeds):
+    """Device-resident key generation (dil_keygen_batch_dev): d_seeds = CUDA uint8 tensor [n, 32]; returns a dict of CUDA
+    uint8 tensors with the KAT field names, produced on torch's current stream."""
+    import torch
+    n = d_seeds.numel() // 32
+    k, l = LEVEL_DIMS[level]
+    sb = 128 if level == 3 else 96
+    dev = d_seeds.device
+    out = {f: torch.empty((n, w), dtype=torch.uint8, device=dev) for f, w in
+           (("rho", 32), ("k", 32), ("tr", 32), ("s1", l * sb), ("s2", k * sb), ("t1", k * 320), ("t0", k * 416))}
+    P = ctypes.c_void_p
+    rc = self._lib.dil_keygen_batch_dev(self._h, int(level), P(d_seeds.data_ptr()), n,
+                                        *[P(out[f].data_ptr()) for f in ("rho", "k", "tr", "s1", "s2", "t1", "t0")], self._stream())
+    self._check(rc, "dil_keygen_batch_dev")
+    return out
+
+
+Engine.keygen_dev = _keygen_dev
+
+
 class SignKey:
     """Expanded signing key on the device (ExpandA + NTT of s1, s2, t0 done once; LOAD_RHO / NTT_S1 /
     NTT_S2 / NTT_T0 of combined_top.v:1560-1767).  Inputs are bit-packed exactly as the reference's

@@ -198,6 +198,9 @@ int dil_verify_multi_dev(dil_engine_t *e, int level, const uint8_t *d_rho, const
  * s1 (l polys), s2 (k polys) as eta - s, t1 (10 bit), t0 as 2^12 - t0 (13 bit). */
 int dil_keygen_batch_host(dil_engine_t *e, int level, const uint8_t *xi, size_t n, uint8_t *rho, uint8_t *key, uint8_t *tr,
                           uint8_t *s1_packed, uint8_t *s2_packed, uint8_t *t1_packed, uint8_t *t0_packed);
+/* device pointers (d_rho, d_key, d_tr 8-byte aligned); enqueues on `stream` and returns */
+int dil_keygen_batch_dev(dil_engine_t *e, int level, const uint8_t *d_xi, size_t n, uint8_t *d_rho, uint8_t *d_key, uint8_t *d_tr,
+                         uint8_t *d_s1_packed, uint8_t *d_s2_packed, uint8_t *d_t1_packed, uint8_t *d_t0_packed, void *stream);
 
 /* ---- several GPUs in one process (items are independent, shards need no exchange) ----
  * A pool owns one engine per device (devices == NULL or n_devices == 0: every visible device; a device may be listed

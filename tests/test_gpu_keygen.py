@@ -27,3 +27,32 @@ def test_keygen_matches_oracle_on_random_seeds(oracle):
         ref = oracle.keygen(2, seeds[i])
         for f in ("rho", "k", "s1", "s2", "t1", "t0", "tr"):
             assert np.array_equal(out[f][i], ref[f]), (i, f)
+
+
+@pytest.mark.parametrize("level", [2, 3, 5])
+def test_keygen_streaming_and_device_paths(oracle, level):
+    """More keys than one 16 K-key piece: the host path generates piece i + 1 while piece i's packed keys cross PCIe,
+    the device path (dil_keygen_batch_dev) writes straight into device buffers; both must equal the oracle on a sample,
+    each other everywhere, and every generated key must sign and verify."""
+    import torch
+    import dilithium_b200 as d
+    eng = d.Engine(0)
+    n = 16384 * 2 + 777
+    seeds = np.random.default_rng(level).integers(0, 256, size=(n, 32)).astype(np.uint8)
+    seeds[:100] = ol.kat(level)["z"]
+    out = eng.keygen(level, seeds)
+    dev = eng.keygen_dev(level, torch.from_numpy(seeds).cuda())
+    torch.cuda.synchronize()
+    K = ol.kat(level)
+    for f in ("rho", "k", "s1", "s2", "t1", "t0", "tr"):
+        assert np.array_equal(out[f], dev[f].cpu().numpy()), f
+        assert np.array_equal(out[f][:100], K[f]), f
+    for i in (100, 16383, 16384, 16385, 32768, n - 1):
+        ref = oracle.keygen(level, seeds[i])
+        for f in ("rho", "k", "s1", "s2", "t1", "t0", "tr"):
+            assert np.array_equal(out[f][i], ref[f]), (i, f)
+    # the generated keys work: one message per key, key per signature, then per-key verification
+    idx = np.arange(0, n, 41)
+    msgs = [int(i).to_bytes(4, "little") for i in idx]
+    z, h, c, att = eng.sign_multi(level, *[out[f][idx] for f in ("rho", "k", "tr", "s1", "s2", "t0")], msgs)
+    assert eng.verify_multi(level, out["rho"][idx], out["t1"][idx], msgs, z, h, c).all()
