@@ -37,3 +37,17 @@ def test_cpp_driver_replays_testbenches(tmp_path, level):
     out = subprocess.run([exe, str(tmp_path), str(level), str(n)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "MISMATCH" not in out.stdout and out.stdout.count("completed") == 3, out.stdout
+
+
+def test_cpp_pool_example_signs_on_every_gpu(tmp_path):
+    """examples/pool_sign.cpp: one C++ process, dil_pool_* over every visible GPU, pinned host buffers in and out; the
+    program itself cross-checks a shard against a single engine (exit code 0 iff identical)."""
+    import json
+    exe = os.path.join(ROOT, "examples", "pool_sign")
+    if not os.path.exists(exe):
+        pytest.skip("examples/pool_sign not built")
+    _write_kat_dir(str(tmp_path), 2, 1)
+    out = subprocess.run([exe, str(tmp_path), "2", "8192", "2"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rec = json.loads(out.stdout.strip().splitlines()[-1])
+    assert rec["matches_single_engine"] is True and rec["n_gpus"] >= 1 and 3.9 < rec["mean_attempts"] < 4.7
