@@ -49,6 +49,10 @@ template <unsigned K>
 struct ZI {
     static constexpr uint32_t w = zeta_inv(K), wp = shoup(zeta_inv(K));
 };
+template <unsigned K>
+struct ZIF {   // zeta_inv(K) * 256^-1: inverse twiddles that also carry the scaling (see ntt_inv_warp)
+    static constexpr uint32_t w = cmulq(zeta_inv(K), INV256), wp = shoup(cmulq(zeta_inv(K), INV256));
+};
 struct ZLast {  // 256^-1 and zeta_inv(1)*256^-1 for the merged last inverse layer
     static constexpr uint32_t f = INV256, fp = shoup(INV256);
     static constexpr uint32_t wf = cmulq(zeta_inv(1), INV256), wfp = shoup(cmulq(zeta_inv(1), INV256));
@@ -223,19 +227,44 @@ __device__ __forceinline__ void ntt_inv_warp(uint32_t (&x)[8], uint32_t* __restr
 #pragma unroll
         for (int r = 0; r < 8; r++) x[r] = p[36 * r];
     }
-    gs_k<64 * Q, 7>(x[0], x[1]); gs_k<64 * Q, 6>(x[2], x[3]); gs_k<64 * Q, 5>(x[4], x[5]); gs_k<64 * Q, 4>(x[6], x[7]);
-    gs_k<128 * Q, 3>(x[0], x[2]); gs_k<128 * Q, 3>(x[1], x[3]); gs_k<128 * Q, 2>(x[4], x[6]); gs_k<128 * Q, 2>(x[5], x[7]);
-    // last layer (span 128, twiddle index 1) merged with the 256^-1 scaling
+    if constexpr (PRESCALED) {
+        gs_k<64 * Q, 7>(x[0], x[1]); gs_k<64 * Q, 6>(x[2], x[3]); gs_k<64 * Q, 5>(x[4], x[5]); gs_k<64 * Q, 4>(x[6], x[7]);
+        gs_k<128 * Q, 3>(x[0], x[2]); gs_k<128 * Q, 3>(x[1], x[3]); gs_k<128 * Q, 2>(x[4], x[6]); gs_k<128 * Q, 2>(x[5], x[7]);
+        // last layer (span 128, twiddle index 1): the input already carries 256^-1
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-        uint32_t d = x[r] + 256 * Q - x[r + 4];
-        uint32_t s = x[r] + x[r + 4];
-        if constexpr (PRESCALED) {
+        for (int r = 0; r < 4; r++) {
+            uint32_t d = x[r] + 256 * Q - x[r + 4];
+            uint32_t s = x[r] + x[r + 4];
             x[r] = canon_small(s);
             x[r + 4] = csub(mul_shoup(d, ZI<1>::w, ZI<1>::wp));
-        } else {
-            x[r] = csub(mul_shoup(s, ZLast::f, ZLast::fp));
-            x[r + 4] = csub(mul_shoup(d, ZLast::wf, ZLast::wfp));
+        }
+    } else {
+        // The 256^-1 scaling rides on the twiddles: a difference output is multiplied by its twiddle anyway, so the
+        // twiddle of the FIRST difference a register takes in this phase is zeta * 256^-1 (compile-time constants, free),
+        // and everything downstream of it is scaled.  Only x[0], which is a sum in all three layers, needs one explicit
+        // multiplication - 1 instead of 4 (both inputs of every butterfly below have the same scaled / unscaled status).
+        auto gsf = [](uint32_t C, uint32_t& a, uint32_t& b, uint32_t w, uint32_t wp) {
+            uint32_t d = a + C - b;
+            a = a + b;
+            b = mul_shoup(d, w, wp);
+        };
+        gsf(64 * Q, x[0], x[1], ZIF<7>::w, ZIF<7>::wp); gsf(64 * Q, x[2], x[3], ZIF<6>::w, ZIF<6>::wp);
+        gsf(64 * Q, x[4], x[5], ZIF<5>::w, ZIF<5>::wp); gsf(64 * Q, x[6], x[7], ZIF<4>::w, ZIF<4>::wp);
+        // unscaled pairs (0,2), (4,6): scale on the difference; pairs (1,3), (5,7) are scaled already
+        gsf(128 * Q, x[0], x[2], ZIF<3>::w, ZIF<3>::wp); gs_k<4 * Q, 3>(x[1], x[3]);
+        gsf(128 * Q, x[4], x[6], ZIF<2>::w, ZIF<2>::wp); gs_k<4 * Q, 2>(x[5], x[7]);
+        {   // pair (0,4): both unscaled
+            uint32_t d = x[0] + 256 * Q - x[4];
+            uint32_t s = x[0] + x[4];
+            x[0] = csub(mul_shoup(s, ZLast::f, ZLast::fp));
+            x[4] = csub(mul_shoup(d, ZLast::wf, ZLast::wfp));
+        }
+#pragma unroll
+        for (int r = 1; r < 4; r++) {   // pairs (r, r+4): scaled, values < 8Q
+            uint32_t d = x[r] + 8 * Q - x[r + 4];
+            uint32_t s = x[r] + x[r + 4];
+            x[r] = canon_small(s);
+            x[r + 4] = csub(mul_shoup(d, ZI<1>::w, ZI<1>::wp));
         }
     }
 }

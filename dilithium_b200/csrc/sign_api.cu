@@ -1260,6 +1260,7 @@ extern "C" int dil_verify_multi_host(dil_engine_t* e, int level, const uint8_t* 
     if (level != 2 && level != 3 && level != 5) return DIL_ERR_ARG;
     if (n == 0) return DIL_OK;
     if (!rho || !t1p || !msgs || !offsets || !z || !h || !ctilde || !ok || n > 0x00FFFFFFu) return DIL_ERR_ARG;
+    if (!offsets_ok(offsets, n)) return DIL_ERR_ARG;
     std::lock_guard<std::mutex> g(e->mu);
     DeviceGuard dg(e->device);
     if (!dg.ok) return DIL_ERR_CUDA;

@@ -1132,7 +1132,8 @@ __global__ void __launch_bounds__(128) verify_mu_kernel(uint64_t* __restrict__ m
     if (t >= n) return;
     const uint8_t* tr = tr_base + (size_t)t * tr_stride;   // stride 0: one key for the batch, 32: one key per item
     const uint8_t* m = msgs + offsets[t];
-    const size_t mlen = (size_t)(offsets[t + 1] - offsets[t]);
+    // the host entry points validate the offsets; a non-monotonic pair in device memory reads as an empty message
+    const size_t mlen = offsets[t + 1] >= offsets[t] ? (size_t)(offsets[t + 1] - offsets[t]) : 0;
     uint64_t A[25];
     shake256_absorb_lanes(A, 32 + mlen, [&](size_t idx) -> uint64_t {
         if (idx < 4) return load_lane_bytes(tr, idx * 8, 32);
