@@ -495,6 +495,30 @@ def cfg4_record(c, keccak_peak):
             "setup_sign_multi_s": sign_multi_s}
 
 
+def kat_length_record(c, key, n):
+    """Messages of KAT-like lengths (the reference's vectors are 33 .. 3300 bytes, rtl_tb/tb_sign_top.v feeds mlen per message):
+    the same key and batch size as the headline, lengths cycling through the 100 KAT message lengths."""
+    import numpy as np
+    torch = c.torch
+    M = np.load(os.path.join(ROOT, "tests", "golden", "kat_msgs.npz"))
+    mlen = np.resize(M["mlen"].astype(np.int64), n)
+    off = np.concatenate([[0], np.cumsum(mlen)])
+    gen = torch.Generator(device="cpu").manual_seed(SEED + 77 + c.rank)
+    msgs = torch.randint(0, 256, (int(off[-1]),), dtype=torch.uint8, generator=gen).to(c.dev)
+    offs = torch.from_numpy(off).to(c.dev)
+    z = torch.empty((n, key.z_bytes), dtype=torch.uint8, device=c.dev); h = torch.empty((n, key.h_bytes), dtype=torch.uint8, device=c.dev)
+    ct = torch.empty((n, 32), dtype=torch.uint8, device=c.dev); att = torch.zeros(n, dtype=torch.int32, device=c.dev)
+    ms = c.time_ms(lambda: key.sign_dev(msgs, offs, n, z, h, ct, att), 5, warm=2)
+    key.set_profile(True)
+    key.sign_dev(msgs, offs, n, z, h, ct, att)
+    torch.cuda.synchronize()
+    init_ms = key.get_profile()["init"][0]
+    key.set_profile(False)
+    return {"workload": f"{n} messages per GPU, lengths cycling through the 100 KAT message lengths ({int(mlen.min())} .. {int(mlen.max())} bytes, "
+                        f"mean {float(mlen.mean()):.0f})", "signs_per_s": c.world * n / (ms * 1e-3), "ms": ms, "message_bytes_per_batch": int(off[-1]),
+            "mu_hash_ms": init_ms, "mu_hash_note": "mu = SHAKE-256(tr || M): one Keccak state per message, 1 permutation per 136 message bytes"}
+
+
 def cfg5_sweep(c, max_log2):
     """cfg5: global batch B = 2^10 .. 2^22 (x4 steps) x levels 2/3/5, sharded evenly over the ranks: forward NTT of the
     batch's l*B polynomials, the fused sign core, full signing and (shared-key) verification."""
@@ -646,7 +670,8 @@ def run_engine(args):
     configs = None
     if not args.no_configs:
         t_cfg = time.perf_counter()
-        configs = {"cfg3": cfg3_record(c, keccak_peak), "cfg4": cfg4_record(c, keccak_peak), "cfg5": cfg5_sweep(c, args.sweep_max_log2)}
+        configs = {"kat_length_messages": kat_length_record(c, key, B), "cfg3": cfg3_record(c, keccak_peak),
+                   "cfg4": cfg4_record(c, keccak_peak), "cfg5": cfg5_sweep(c, args.sweep_max_log2)}
         configs["wall_s"] = time.perf_counter() - t_cfg
 
     if rank == 0:

@@ -43,4 +43,18 @@ m5 = msgs[:16]
 z5, h5, c5, _ = sk5.sign(m5)
 ok5 = eng.verify_multi(5, np.repeat(K5["rho"][:1], 16, axis=0), np.repeat(K5["t1"][:1], 16, axis=0), m5, z5, h5, c5)
 assert ok5.all()
+# one key per signature (per-item A in HBM, per-item tail), the fused mask core, device-resident key generation, a pool
+zz, hh, cc, _ = eng.sign_multi(2, K["rho"][:24], K["k"][:24], K["tr"][:24], K["s1"][:24], K["s2"][:24], K["t0"][:24], msgs[:24])
+assert eng.verify_multi(2, K["rho"][:24], K["t1"][:24], msgs[:24], zz, hh, cc).all()
+sk.set_tuning(fused_mask=True, spec_target=(int(sys.argv[2]) if len(sys.argv) > 2 else 0))
+zf, hf, cf, af = sk.sign(msgs)
+assert np.array_equal(z, zf) and np.array_equal(h, hf) and np.array_equal(c, cf) and np.array_equal(att, af)
+kd = eng.keygen_dev(2, torch.arange(64 * 32, dtype=torch.uint8, device="cuda").reshape(64, 32))
+torch.cuda.synchronize()
+assert np.array_equal(kd["t1"].cpu().numpy(), keys["t1"])
+pool = d.Pool([0, 0])
+pool.load_key(2, K["rho"][0], K["k"][0], K["tr"][0], K["s1"][0], K["s2"][0], K["t0"][0])
+pz, ph, pc, pa = pool.sign(msgs)
+assert np.array_equal(z, pz) and np.array_equal(att, pa)
+pool.close()
 print("tour ok", eng.launch_count)

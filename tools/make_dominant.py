@@ -3,7 +3,7 @@
 summaries that tools/ncu_summary.py wrote:  python tools/make_dominant.py [tag]   (default tag r1b)"""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1c"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2d"
 CLASSES = {"expand_mask": "expand_mask_kernel", "signcore": "matvec_shared_kernel", "challenge": "challenge_kernel",
            "tail": "sign_tail_sparse_kernel"}
 out = {}
@@ -17,6 +17,7 @@ for cls, kern in CLASSES.items():
                 "alu_pipe_pct": l["sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed"],
                 "fmaheavy_pipe_pct": l["sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"],
                 "issue_pct": l["sm__issue_active.avg.pct_of_peak_sustained_elapsed"],
+                "dram_pct": l.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"), "round_tag": tag,
                 "source": f"profiles/{tag}_sign_{kern}.json (ncu --set full, first launch of a 65536-message Dilithium-2 batch)"}
 json.dump(out, open(os.path.join(ROOT, "profiles", "dominant_kernel.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))
