@@ -554,9 +554,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sign_tail_sparse_kernel(
     const ResolveCtx ra = resolve_ctx(rargs);
     extern __shared__ __align__(16) uint32_t sm_words[];
     constexpr int NP = L + K;                              // small key polynomials: s1 | s2
-    constexpr int GROUP = 15 / (2 * ETA);                  // terms whose biased nibbles can be added without a carry
-    constexpr int TABB = 2 * 8 * 256;                      // table bytes per polynomial: sign x alignment x 512 nibbles
-    static_assert(GROUP >= 1 && 2 * ETA * TAU < 256, "nibble / byte sums must not carry");
+    // eta = 2: elements are biased NIBBLES (0..4), three terms fit a nibble sum, one 4-byte load covers a lane's 8 coefficients.
+    // eta = 4: biased elements (0..8) need BYTES (one 8-byte load per term), 31 terms fit a byte sum, then 16-bit sums.
+    constexpr bool BYTES = ETA > 3;
+    constexpr int GROUP = BYTES ? 255 / (2 * ETA) : 15 / (2 * ETA);   // terms that can be added without a carry
+    constexpr int TABB = BYTES ? 2 * 8 * 512 : 2 * 8 * 256;           // table bytes per polynomial: sign x alignment x 512 elements
+    static_assert(GROUP >= 1 && (BYTES ? 2 * ETA * TAU < 65536 : 2 * ETA * TAU < 256), "partial sums must not carry");
     constexpr int G1BITS = GAMMA1 == (1 << 17) ? 17 : 19;
     uint32_t* t0_sm = sm_words;                                   // K * 256: t0_hat * 256^-1
     uint32_t* scr_all = t0_sm + K * N;                            // WARPS * SCRATCH_WORDS
@@ -575,17 +578,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sign_tail_sparse_kernel(
         reinterpret_cast<uint4*>(t0_sm)[t] = make_uint4(mul_full(canon_signed(q.x), INV256), mul_full(canon_signed(q.y), INV256),
                                                         mul_full(canon_signed(q.z), INV256), mul_full(canon_signed(q.w), INV256));
     }
-    // tables: T[p][sign][a][m] = eta +- e_p[m + a]  (0 beyond the end) as nibbles, eight consecutive m per thread
-    for (int idx = threadIdx.x; idx < NP * 2 * 8 * 64; idx += blockDim.x) {
-        const int m = (idx & 63) * 8, al = (idx >> 6) & 7, sg = (idx >> 9) & 1, p = idx >> 10;
+    // tables: T[p][sign][a][m] = eta +- e_p[m + a]  (0 beyond the end), one 32-bit word (8 nibbles / 4 bytes) per thread step
+    constexpr int EPW = BYTES ? 4 : 8;                     // elements per table word
+    constexpr int WPA = 512 / EPW;                         // words per (polynomial, sign, alignment) row
+    for (int idx = threadIdx.x; idx < NP * 2 * 8 * WPA; idx += blockDim.x) {
+        const int m = (idx % WPA) * EPW, al = (idx / WPA) & 7, sg = (idx / (WPA * 8)) & 1, p = idx / (WPA * 16);
         uint32_t word = 0;
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
+        for (int q = 0; q < EPW; q++) {
             const int j = m + q + al;
             int e = 0;
             if (j < 256) e = -(int)key_small[p * N + j];
             else if (j < 512) e = (int)key_small[p * N + j - 256];
-            word |= (uint32_t)(ETA + (sg ? -e : e)) << (4 * q);
+            word |= (uint32_t)(ETA + (sg ? -e : e)) << ((32 / EPW) * q);
         }
         reinterpret_cast<uint32_t*>(tabs)[idx] = word;
     }
@@ -596,26 +601,54 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sign_tail_sparse_kernel(
 
     // x[0..7] = (c * small_p)[8*lane .. 8*lane+7] from the term list of the current slot
     auto sparse_mul = [&](int p, int32_t (&x)[8]) {
-        const uint8_t* tp = tabs + (size_t)p * TABB + 4 * lane;
-        uint32_t b0 = 0, b1 = 0, nacc = 0, tw = 0;
+        if constexpr (!BYTES) {
+            const uint8_t* tp = tabs + (size_t)p * TABB + 4 * lane;
+            uint32_t b0 = 0, b1 = 0, nacc = 0, tw = 0;
 #pragma unroll
-        for (int t = 0; t < TAU; t++) {
-            uint32_t u;
-            if ((t & 1) == 0) {   // term offsets are read two at a time
-                tw = (t + 1 < TAU) ? reinterpret_cast<const uint32_t*>(terms)[t >> 1] : (uint32_t)terms[t];
-                u = tw & 0xFFFFu;
-            } else {
-                u = tw >> 16;
+            for (int t = 0; t < TAU; t++) {
+                uint32_t u;
+                if ((t & 1) == 0) {   // term offsets are read two at a time
+                    tw = (t + 1 < TAU) ? reinterpret_cast<const uint32_t*>(terms)[t >> 1] : (uint32_t)terms[t];
+                    u = tw & 0xFFFFu;
+                } else {
+                    u = tw >> 16;
+                }
+                nacc += *reinterpret_cast<const uint32_t*>(tp + u);
+                if (t % GROUP == GROUP - 1 || t == TAU - 1) {
+                    b0 += nacc & 0x0F0F0F0Fu;          // coefficients 0, 2, 4, 6
+                    b1 += (nacc >> 4) & 0x0F0F0F0Fu;   // coefficients 1, 3, 5, 7
+                    nacc = 0;
+                }
             }
-            nacc += *reinterpret_cast<const uint32_t*>(tp + u);
-            if (t % GROUP == GROUP - 1 || t == TAU - 1) {
-                b0 += nacc & 0x0F0F0F0Fu;          // coefficients 0, 2, 4, 6
-                b1 += (nacc >> 4) & 0x0F0F0F0Fu;   // coefficients 1, 3, 5, 7
-                nacc = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = (int32_t)((((i & 1) ? b1 : b0) >> (8 * (i >> 1))) & 0xFFu) - TAU * ETA;
+        } else {
+            const uint8_t* tp = tabs + (size_t)p * TABB + 8 * lane;
+            uint32_t b0 = 0, b1 = 0, tw = 0;                 // byte sums of coefficients 0..3 / 4..7
+            uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;         // 16-bit sums: (c0, c2), (c1, c3), (c4, c6), (c5, c7)
+#pragma unroll
+            for (int t = 0; t < TAU; t++) {
+                uint32_t u;
+                if ((t & 1) == 0) {
+                    tw = (t + 1 < TAU) ? reinterpret_cast<const uint32_t*>(terms)[t >> 1] : (uint32_t)terms[t];
+                    u = tw & 0xFFFFu;
+                } else {
+                    u = tw >> 16;
+                }
+                const uint2 v = *reinterpret_cast<const uint2*>(tp + u);
+                b0 += v.x;
+                b1 += v.y;
+                if (t % GROUP == GROUP - 1 || t == TAU - 1) {
+                    h0 += b0 & 0x00FF00FFu; h1 += (b0 >> 8) & 0x00FF00FFu;
+                    h2 += b1 & 0x00FF00FFu; h3 += (b1 >> 8) & 0x00FF00FFu;
+                    b0 = b1 = 0;
+                }
             }
+            x[0] = (int32_t)(h0 & 0xFFFFu) - TAU * ETA; x[1] = (int32_t)(h1 & 0xFFFFu) - TAU * ETA;
+            x[2] = (int32_t)(h0 >> 16) - TAU * ETA;     x[3] = (int32_t)(h1 >> 16) - TAU * ETA;
+            x[4] = (int32_t)(h2 & 0xFFFFu) - TAU * ETA; x[5] = (int32_t)(h3 & 0xFFFFu) - TAU * ETA;
+            x[6] = (int32_t)(h2 >> 16) - TAU * ETA;     x[7] = (int32_t)(h3 >> 16) - TAU * ETA;
         }
-#pragma unroll
-        for (int i = 0; i < 8; i++) x[i] = (int32_t)((((i & 1) ? b1 : b0) >> (8 * (i >> 1))) & 0xFFu) - TAU * ETA;
     };
 
     uint32_t claim = 0;
@@ -632,7 +665,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sign_tail_sparse_kernel(
                 const uint32_t m = __ballot_sync(0xffffffffu, byte != 0);
                 if (byte != 0) {
                     const int pos = 8 * lane + i, al = (-pos) & 7;
-                    terms[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((byte == 0xFFu ? 2048 : 0) + al * 256 + (256 - pos - al) / 2);
+                    terms[cnt + __popc(m & ((1u << lane) - 1u))] =
+                        BYTES ? (uint16_t)((byte == 0xFFu ? 4096 : 0) + al * 512 + (256 - pos - al))
+                              : (uint16_t)((byte == 0xFFu ? 2048 : 0) + al * 256 + (256 - pos - al) / 2);
                 }
                 cnt += __popc(m);
             }
@@ -909,7 +944,7 @@ static cudaError_t launch_sign_tail_sparse(const SignBufs& b, const int32_t* key
                                            int sm_count, cudaStream_t st) {
     constexpr int WARPS = 24;
     constexpr size_t smem = (size_t)(K * N + WARPS * SCRATCH_WORDS + WARPS * K * 8) * 4 + (size_t)WARPS * 64 * 2 +
-                            (size_t)(L + K) * 2 * 8 * 256;
+                            (size_t)(L + K) * 2 * 8 * (ETA > 3 ? 512 : 256);
     static_assert(smem <= 227 * 1024, "sparse tail tables do not fit in shared memory");
     auto kern = sign_tail_sparse_kernel<K, L, G1, G2, BETA, OMEGA, TAU, ETA, WARPS>;
     static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
@@ -927,7 +962,7 @@ cudaError_t launch_sign_tail(int level, const SignBufs& b, const int32_t* key_ha
     if (key_small != nullptr) {
         switch (level) {
             case 2: return launch_sign_tail_sparse<4, 4, 1 << 17, (Q_I - 1) / 88, 78, 80, 39, 2>(b, key_hat, key_small, cap_slots, sm_count, st);
-            case 3: break;   // eta = 4: nibble sums would carry; the transform tail below handles level 3
+            case 3: return launch_sign_tail_sparse<6, 5, 1 << 19, (Q_I - 1) / 32, 196, 55, 49, 4>(b, key_hat, key_small, cap_slots, sm_count, st);
             case 5: return launch_sign_tail_sparse<8, 7, 1 << 19, (Q_I - 1) / 32, 120, 75, 60, 2>(b, key_hat, key_small, cap_slots, sm_count, st);
             default: return cudaErrorInvalidValue;
         }

@@ -70,3 +70,41 @@ def test_sparse_product_matches_negacyclic(tau, eta):
                     assert bacc.max() <= 255        # no carry between bytes
             out[8 * lane:8 * lane + 8] = bacc - tau * eta
         assert np.array_equal(out, negacyclic(c, s))
+
+
+def test_sparse_product_bytes_eta4():
+    """Level 3 (eta = 4, tau = 49): biased elements 0..8 do not fit nibble sums, so the tables hold BYTES (one 8-byte load per
+    term and lane), 31 terms are added per byte sum and then spread into 16-bit sums - restated with the kernel's exact word
+    arithmetic (packed 32-bit adds, masks 0x00FF00FF) and offsets (sign * 4096 + al * 512 + shift bytes)."""
+    tau, eta = 49, 4
+    rng = np.random.default_rng(3)
+    group = 255 // (2 * eta)
+    assert group == 31
+    for _ in range(20):
+        s = rng.integers(-eta, eta + 1, size=N)
+        c = np.zeros(N, dtype=np.int64)
+        c[rng.choice(N, size=tau, replace=False)] = rng.choice([-1, 1], size=tau)
+        T = build_tables(s, eta)                       # same element values, stored one per byte
+        tab = np.zeros(2 * 8 * 512, dtype=np.uint8)    # byte image of one polynomial's table as the kernel lays it out
+        for sg in range(2):
+            for al in range(8):
+                tab[sg * 4096 + al * 512: sg * 4096 + (al + 1) * 512] = T[sg, al]
+        out = np.zeros(N, dtype=np.int64)
+        for lane in range(32):
+            b0 = b1 = 0
+            h = [0, 0, 0, 0]
+            for t, (sg, al, shift) in enumerate(term_offsets(c)):
+                u = sg * 4096 + al * 512 + shift + 8 * lane
+                assert u % 8 == 0 and u + 8 <= (sg * 8 + al + 1) * 512
+                vx = int.from_bytes(tab[u:u + 4].tobytes(), "little")
+                vy = int.from_bytes(tab[u + 4:u + 8].tobytes(), "little")
+                b0 = (b0 + vx) & 0xFFFFFFFF
+                b1 = (b1 + vy) & 0xFFFFFFFF
+                if t % group == group - 1 or t == tau - 1:
+                    assert all(((b >> (8 * i)) & 0xFF) <= 255 for b in (b0, b1) for i in range(4))
+                    h[0] += b0 & 0x00FF00FF; h[1] += (b0 >> 8) & 0x00FF00FF
+                    h[2] += b1 & 0x00FF00FF; h[3] += (b1 >> 8) & 0x00FF00FF
+                    b0 = b1 = 0
+            x = [h[0] & 0xFFFF, h[1] & 0xFFFF, h[0] >> 16, h[1] >> 16, h[2] & 0xFFFF, h[3] & 0xFFFF, h[2] >> 16, h[3] >> 16]
+            out[8 * lane:8 * lane + 8] = np.array(x) - tau * eta
+        assert np.array_equal(out, negacyclic(c, s))
