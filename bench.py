@@ -731,10 +731,22 @@ def run_engine(args):
         if configs is not None:
             line["configs"] = configs
         if world == 1 and not args.no_cpu_baseline:
+            # the CPU leg also CHECKS the timed step's output: a strided sample of the signatures the engine just produced goes
+            # through the oracle's verify (the oracle is the checker here, never the thing measured)
+            import oracle_lib as ol
+            orc = ol.load()
+            kk0 = kat_key(level)
+            mh = msgs_host.numpy().reshape(B, MSG_BYTES)
+            zc, hc_, cc = z.cpu().numpy(), h.cpu().numpy(), ct.cpu().numpy()
+            sample_idx = list(range(0, B, max(B // 24, 1)))
+            checked_ok = all(orc.verify(level, kk0["rho"], kk0["t1"], mh[i].tobytes(), zc[i], hc_[i], cc[i]) == 0 for i in sample_idx)
+            if not checked_ok:
+                raise RuntimeError("bench: the oracle rejected a signature of the timed step")
             cores = host_threads()
             n_cpu = 256 * cores if 256 * cores < 8192 else 8192
             v, kind, threads, sample, _, _ = cpu_sign(level, n_cpu, cores, steps=2, warmup=1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
+            line["cpu_baseline"]["oracle_verified_signatures_of_the_timed_step"] = len(sample_idx)
             ntt_cpu, ntt_kind = cpu_ntt(cores)
             line["cpu_baseline"]["ntt_polys_per_s"] = ntt_cpu
             line["cpu_baseline"]["ntt_sample"] = f"65536 polynomials through {'the compiled reference ntt()' if ntt_kind == 'reference' else 'the oracle port'} on {cores} thread(s)"
