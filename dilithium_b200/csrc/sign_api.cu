@@ -45,6 +45,9 @@ struct dil_sign_key {
     uint8_t *h_slot = nullptr, *accepted = nullptr;
     uint64_t* ct_slot = nullptr;
     size_t slots = 0;            // slot capacity of y/w/c/w1p/h_slot/ct_slot/accepted
+    // the host path's own streams: two key handles (even of the same key) can have a batch in flight each, so that one
+    // batch's last signatures drain while the next batch already signs (bench.py's e2e loop, examples/pool_sign.cpp)
+    cudaStream_t st_own = nullptr, cs_own = nullptr;
     uint32_t* ctl_host = nullptr;      // mapped pinned copy of the first 16 words of the round state
     uint32_t* ctl_host_dev = nullptr;  // its device alias
     cudaEvent_t round_ev = nullptr;    // orders the copy stream's drains after the rounds they copy
@@ -467,6 +470,8 @@ int dil_sign_key_destroy(dil_engine_t* e, dil_sign_key_t* k) {
     for (auto& ev : k->ev)
         if (ev) cudaEventDestroy(ev);
     if (k->round_ev) cudaEventDestroy(k->round_ev);
+    if (k->st_own) cudaStreamDestroy(k->st_own);
+    if (k->cs_own) cudaStreamDestroy(k->cs_own);
     if (k->ctl_host) cudaFreeHost(k->ctl_host);
     (void)e;
     delete k;
@@ -529,7 +534,11 @@ int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs,
     DeviceGuard dg(e->device);
     if (!dg.ok) return DIL_ERR_CUDA;
     const LevelParams& P = k->P;
-    cudaStream_t st = e->host_stream;
+    if (!k->st_own) {
+        CK(cudaStreamCreateWithFlags(&k->st_own, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&k->cs_own, cudaStreamNonBlocking));
+    }
+    cudaStream_t st = k->st_own;
     const size_t mbytes = offsets[n] > 0 ? offsets[n] : 1;
     const size_t zb = (size_t)P.l * P.z_bytes, hb = (size_t)P.omega + P.k;
     if (mbytes > k->msgs_cap) {
@@ -556,7 +565,7 @@ int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs,
     }
     CK(cudaMemcpyAsync(k->msgs_d, msgs, offsets[n], cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(k->off_d, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    cudaStream_t cs = e->copy_stream;
+    cudaStream_t cs = k->cs_own;
     // Streaming path: when every output buffer is pinned host memory the device can address (cudaHostAlloc /
     // cudaHostRegister; torch's pinned tensors are), finished signatures leave round by round (DrainTarget)
     // and the transfer hides behind the remaining rounds.  Pageable buffers take the chunked copy path below.
