@@ -67,6 +67,8 @@ def parse():
     ap.add_argument("--level", type=int, default=2, choices=[2, 3, 5])
     ap.add_argument("--batch", type=int, default=65536, help="signatures per GPU per step (weak scaling)")
     ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--in-flight", type=int, default=4,
+                    help="sign batches in flight per GPU in the timed loops (one key handle, stream and host thread each); 1 = strictly one at a time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg3 / cfg4 / cfg5 sub-records")
     ap.add_argument("--sweep-max-log2", type=int, default=22)
@@ -590,16 +592,66 @@ def run_engine(args):
     def step():
         key.sign_dev(msgs, offs, B, z, h, ct, att)
 
+    # Batches in flight: a streaming caller keeps several 65 536-message batches going at once - one key handle (same key), one
+    # stream, one host thread and one set of output buffers per batch in flight; step i runs in context i mod T.  The late, small
+    # rejection rounds of one batch leave SMs idle (Keccak wave quantisation, latency-bound rounds); the other batches' kernels fill
+    # them, and the engine speculates less when it sees the load (sign_api.cu spec_for).  Every step is still one full batch, and
+    # all K steps start and finish inside the timed region.  The strictly serial figure is measured first and reported next to it.
+    T = max(1, min(args.in_flight, args.steps))
+    ctxs = [(key, z, h, ct, att, torch.cuda.Stream())]
+    for _ in range(1, T):
+        kx = d.SignKey(eng, level, *[parts[f] for f in fields])
+        ctxs.append((kx, torch.empty_like(z), torch.empty_like(h), torch.empty_like(ct), torch.zeros_like(att), torch.cuda.Stream()))
+
+    def run_pipelined(n_steps, start_ev=None):
+        errs = []
+
+        def worker(wi):
+            try:
+                torch.cuda.set_device(local)
+                kx, zx, hx, cx, ax, st = ctxs[wi]
+                with torch.cuda.stream(st):
+                    if start_ev is not None:
+                        st.wait_event(start_ev)
+                    for _ in range(wi, n_steps, T):
+                        kx.sign_dev(msgs, offs, B, zx, hx, cx, ax)
+            except Exception as ex:   # noqa: BLE001
+                errs.append(ex)
+        th = [threading.Thread(target=worker, args=(wi,)) for wi in range(T)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+        for cx_ in ctxs:
+            torch.cuda.current_stream().wait_stream(cx_[5])
+
     warm = max(args.warmup, 3)
     for _ in range(warm):
         step()
     c.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    c.barrier()
+    serial_ms = c.maxr(ev0.elapsed_time(ev1))
+    serial = {"value": world * B * args.steps / (serial_ms * 1e-3), "unit": UNIT, "ms_per_step": serial_ms / args.steps,
+              "rejection_rounds": key.last_rounds, "attempt_slots_per_step": key.last_slots}
+    if T > 1:
+        run_pipelined(max(warm, T))
+        c.barrier()
     l0 = eng.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         ev0.record()
-        for _ in range(args.steps):
-            step()
+        if T > 1:
+            run_pipelined(args.steps, ev0)
+        else:
+            for _ in range(args.steps):
+                step()
         ev1.record()
         c.barrier()
     launches = eng.launch_count - l0
@@ -608,13 +660,17 @@ def run_engine(args):
     value = world * B * args.steps / (ms_total * 1e-3)
     mean_attempts = float(att.float().mean().item())
     rounds, slots = key.last_rounds, key.last_slots
+    pipelined_same = all(bool(torch.equal(zx, z) and torch.equal(hx, h) and torch.equal(cx, ct)) for _, zx, hx, cx, _, _ in ctxs[1:])
+    if not pipelined_same:
+        raise RuntimeError("bench: batches in flight produced different signatures for the same messages")
 
-    # per-kernel-class device time of one step (CUDA events around every launch), outside the timed region
+    # per-kernel-class device time of one step on its own (CUDA events around every launch), outside the timed region
     key.set_profile(True)
     step()
     torch.cuda.synchronize()
     prof = {n: v for n, v in key.get_profile().items() if n != "pack_w1"}   # w1 packing is fused into the sign core
     key.set_profile(False)
+    prof_rounds = max(key.last_rounds, 1)
     prof_total = sum(ms for ms, _ in prof.values())
     dominant = max((n for n in prof if n != "init"), key=lambda n: prof[n][0])
     cb = class_bytes(level)
@@ -642,22 +698,20 @@ def run_engine(args):
     core_ms = c.time_ms(lambda: eng.signcore(a_hat, yb, k, l, w=wb), 50, warm=3)
     del yb, outb, wb
 
-    # end to end through the host-pointer C ABI: pinned host messages in, signatures out to host memory.  Two batches are in
-    # flight (two key handles of the same key, two sets of pinned buffers, one host thread each): batch i + 1 already signs
-    # while batch i's last signatures drain, as a streaming caller would use the API.  Every step still includes the H2D copy of
-    # its messages and the D2H of all its signatures; the strictly serial figure (one call at a time) is reported next to it.
+    # end to end through the host-pointer C ABI: pinned host messages in, signatures out to host memory.  T batches are in
+    # flight as above (T key handles of the same key, T sets of pinned buffers, one host thread each): the next batch already
+    # signs while the previous one's last signatures drain, as a streaming caller would use the API.  Every step still includes
+    # the H2D copy of its messages and the D2H of all its signatures; the strictly serial figure is reported next to it.
     P = ctypes.c_void_p
     lib = eng._lib
-    key2 = d.SignKey(eng, level, *[parts[f] for f in fields])
     bufs = []
-    for _ in range(2):
+    for _ in range(T):
         bufs.append((torch.empty((B, key.z_bytes), dtype=torch.uint8).pin_memory(), torch.empty((B, key.h_bytes), dtype=torch.uint8).pin_memory(),
                      torch.empty((B, 32), dtype=torch.uint8).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()))
 
     def e2e_call(which):
-        kh = (key, key2)[which]
         z_h, h_h, c_h, a_h = bufs[which]
-        rc = lib.dil_sign_batch_host(eng._h, kh._h, P(msgs_host.data_ptr()), P(offs_host.data_ptr()), B, P(z_h.data_ptr()),
+        rc = lib.dil_sign_batch_host(eng._h, ctxs[which][0]._h, P(msgs_host.data_ptr()), P(offs_host.data_ptr()), B, P(z_h.data_ptr()),
                                      P(h_h.data_ptr()), P(c_h.data_ptr()), P(a_h.data_ptr()))
         if rc != 0:
             raise RuntimeError("dil_sign_batch_host failed")
@@ -672,11 +726,11 @@ def run_engine(args):
         def worker(which):
             try:
                 torch.cuda.set_device(local)
-                for _ in range(which, n_steps, 2):
+                for _ in range(which, n_steps, in_flight):
                     e2e_call(which)
             except Exception as ex:   # noqa: BLE001
                 errs.append(ex)
-        th = [threading.Thread(target=worker, args=(w,)) for w in range(2)]
+        th = [threading.Thread(target=worker, args=(w,)) for w in range(in_flight)]
         for t in th:
             t.start()
         for t in th:
@@ -684,19 +738,20 @@ def run_engine(args):
         if errs:
             raise errs[0]
 
-    e2e_steps = max(args.e2e_steps, 2)
+    e2e_steps = max(args.e2e_steps, T)
     e2e_res = {}
-    for in_flight in (1, 2):
-        e2e_run(2, in_flight)
+    for in_flight in sorted({1, T}):
+        e2e_run(max(2, in_flight), in_flight)
         c.barrier()
         t0 = time.perf_counter()
         e2e_run(e2e_steps, in_flight)
         c.barrier()
         e2e_res[in_flight] = world * B * e2e_steps / c.maxr(time.perf_counter() - t0)
-    e2e_val = e2e_res[2]
+    e2e_val = e2e_res[T]
     e2e_ok = all(bool(torch.equal(zh.to(dev), z) and torch.equal(hh.to(dev), h) and torch.equal(ch.to(dev), ct)) for zh, hh, ch, _ in bufs)
-    key2.close()
     del bufs
+    for kx, *_ in ctxs[1:]:
+        kx.close()
 
     configs = None
     if not args.no_configs:
@@ -718,24 +773,31 @@ def run_engine(args):
             "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32/u64 integer (Shoup/Barrett modular arithmetic, 64-bit Keccak lanes)", "data": "synthetic",
             "config": {"workload": workload_name(level, B), "level": level, "k": k, "l": l, "batch_per_gpu": B,
-                       "key": "reference KAT vector 0 (tests/golden)", "mean_attempts": mean_attempts, "rejection_rounds": rounds,
+                       "key": "reference KAT vector 0 (tests/golden)", "mean_attempts": mean_attempts,
+                       "batches_in_flight": T,
+                       "batches_in_flight_note": ("every step is one full batch; step i runs on key handle / stream / host thread i mod T, all K steps "
+                                                  "start and finish inside the timed region; `one_batch_at_a_time` is the strictly serial figure"),
+                       "rejection_rounds": rounds,
                        "attempt_slots_per_step": slots, "host_syncs_per_step": "1 (the rejection loop runs on the device; rounds are enqueued ahead)",
                        "sharding": ("independent messages, one contiguous shard per rank; one NCCL broadcast of the key material"
                                     if world > 1 else "single GPU"),
                        "l2": "no flush: every round streams > 1 GiB of per-attempt state (y, w, c), far above the 126 MB L2",
-                       "timing": "CUDA events on torch's current stream (the stream every kernel is launched on), max over ranks",
+                       "timing": ("CUDA events on torch's current stream; the batch streams wait for the start event and the current stream waits "
+                                  "for every batch stream before the stop event; max over ranks"),
                        "kernels_per_round": "ExpandMask, sign core (+ packed HighBits), challenge, tail (+ resolve when one slot per item), "
                                             "resolve (returns at once unless the round speculates), plan"},
+            "one_batch_at_a_time": serial,
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "step_profile_ms": {n: round(ms, 4) for n, (ms, _) in prof.items()},
-            "step_profile_note": f"device time per kernel class in one step (sum {prof_total:.3f} ms of {ms_step:.3f} ms wall)",
+            "step_profile_note": (f"device time per kernel class of one step run alone (sum {prof_total:.3f} ms; one batch at a time takes "
+                                  f"{serial['ms_per_step']:.3f} ms per step, {ms_step:.3f} ms with {T} in flight)"),
             "roofline": {"kernel": class_kernel_name(dominant, level), "class": dominant, "bound": "hbm", "achieved": dom_achieved, "peak": peak,
                          "unit": "GB/s", "frac": dom_achieved / peak,
-                         "traffic": (traffic / 65536.0 * dom_units / max(rounds, 1)) if traffic else None,
+                         "traffic": (traffic / 65536.0 * dom_units / prof_rounds) if traffic else None,
                          "traffic_note": "ncu dram bytes of a 65536-slot launch scaled to this step's average launch size",
-                         "algorithmic_bytes_per_slot": cb[dominant], "slots_per_step": dom_units, "launches_per_step": rounds,
-                         "avg_launch_ms": dom_ms / max(rounds, 1), "peak_source": peak_src,
+                         "algorithmic_bytes_per_slot": cb[dominant], "slots_per_step": dom_units, "launches_per_step": prof_rounds,
+                         "avg_launch_ms": dom_ms / prof_rounds, "peak_source": peak_src,
                          "ncu_limiter": ncu_limiter(dominant),
                          "compute_roofline": keccak_roofline(dominant, level, dom_units, dom_ms, keccak_peak / 1e9, keccak_src)},
             "keccak_peak": {"measured_g_per_s": keccak_peak / 1e9, "source": keccak_src, "sass_mix_per_round": kmix, "sm_mhz_during": kclock,
@@ -753,8 +815,8 @@ def run_engine(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * MSG_BYTES + (B + 1) * 8,
                     "d2h_bytes_per_step": B * (sig_bytes + 4), "steps": e2e_steps,
                     "api": "dil_sign_batch_host (C ABI): pinned host messages in, z/h/c~/attempts back in host memory",
-                    "batches_in_flight": 2, "one_call_at_a_time": e2e_res[1],
-                    "timing": "host wall clock around the synchronous calls (two host threads, one key handle and buffer set each), max over ranks",
+                    "batches_in_flight": T, "one_call_at_a_time": e2e_res[1],
+                    "timing": "host wall clock around the synchronous calls (one host thread, key handle and pinned buffer set per batch in flight), max over ranks",
                     "matches_device_path": e2e_ok,
                     "host_ceiling": ({"aggregate_gb_per_s": ceiling, "signatures_per_s": ceiling * 1e9 / (sig_bytes + 4),
                                       "e2e_frac_of_ceiling": e2e_val * (sig_bytes + 4) / (ceiling * 1e9),

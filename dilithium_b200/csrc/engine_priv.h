@@ -11,6 +11,7 @@ struct dil_engine {
     int device = -1;
     int sm_count = 0;
     std::atomic<uint64_t> launches{0};
+    std::atomic<int> sign_in_flight{0};   // sign batches inside their round loop right now (load-adaptive speculation, sign_api.cu)
     std::mutex mu;           // guards staging (host-pointer calls serialise on it)
     std::mutex err_mu;       // guards last_error (set from any entry point, whichever lock it holds)
     void* staging[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -128,14 +128,36 @@ bool offsets_ok(const uint64_t* off, size_t n) {
 // slots; the smallest accepted kappa wins, which is exactly the sequential result of combined_top.v:2217-2228
 // (restart with the next kappa).  The policy itself runs on the device (spec_policy, sign_kernels.cu).
 constexpr uint32_t SPEC_TARGET_DEFAULT = 32768, SPEC_MAX_DEFAULT = 32;
-uint32_t spec_target(const dil_sign_key* k) { return k->tune.spec_target ? k->tune.spec_target : SPEC_TARGET_DEFAULT; }
-uint32_t spec_max(const dil_sign_key* k) {
-    return k->tune.spec_max && k->tune.spec_max <= 32 ? k->tune.spec_max : SPEC_MAX_DEFAULT;   // one warp lane per slot in resolve
+struct Spec {
+    uint32_t target, max;
+};
+// Without explicit tuning the policy follows the load of the engine: when other sign batches are in flight on the same GPU
+// (two or more key handles signing from different host threads, the streaming use of the API), their kernels fill the
+// SMs that the small late rounds of this batch leave idle, so speculating costs more than it hides - fewer slots per
+// item then, and later.  Measured on one B200, 65 536-message Dilithium-2 batches (profiles/r2e_concurrent_spec.txt):
+// 1 in flight 12.1 M signs/s with 32768 / 32; 2 in flight 13.9 M with 16384 / 16; 4 in flight 14.6 M with 8192 / 8.
+Spec spec_for(const dil_sign_key* k, int in_flight) {
+    Spec s{SPEC_TARGET_DEFAULT, SPEC_MAX_DEFAULT};
+    if (in_flight == 2) s = Spec{16384, 16};
+    else if (in_flight >= 3) s = Spec{8192, 8};
+    if (k->tune.spec_target) s.target = k->tune.spec_target;
+    if (k->tune.spec_max && k->tune.spec_max <= 32) s.max = k->tune.spec_max;   // one warp lane per slot in resolve
+    return s;
 }
-size_t slots_for(const dil_sign_key* k, size_t n) {
-    const size_t T = spec_target(k), M = spec_max(k);
+size_t slots_for(Spec s, size_t n) {
+    const size_t T = s.target, M = s.max;
     return n > T ? n : (n * M < T ? n * M : T);
 }
+// the workspace is sized for the policy that needs the most slots (a lone batch)
+size_t slots_alloc(const dil_sign_key* k, size_t n) { return slots_for(spec_for(k, 1), n); }
+
+// sign batches currently inside sign_rounds on this engine (any key handle, any host thread)
+struct InFlight {
+    std::atomic<int>& c;
+    int seen;
+    explicit InFlight(std::atomic<int>& ctr) : c(ctr), seen(++ctr) {}
+    ~InFlight() { --c; }
+};
 
 void free_ws(dil_sign_key* k) {
     const LevelParams& P = k->P;
@@ -155,7 +177,7 @@ void free_ws(dil_sign_key* k) {
 }
 
 int ensure_ws(dil_engine* e, dil_sign_key* k, size_t n) {
-    const size_t slots = slots_for(k, n);
+    const size_t slots = slots_alloc(k, n);
     if (n <= k->cap && slots <= k->slots) return DIL_OK;
     free_ws(k);
     const LevelParams& P = k->P;
@@ -204,9 +226,9 @@ struct DrainTarget {
 // Expected number of active items at the start of every round of a batch of n items (the device decides what really
 // happens; this only sizes the first burst of launches and their grids): an attempt is rejected with probability
 // 1 - 1/repetitions, the scheme's expected repetitions being 4.25 / 5.1 / 3.85 at levels 2 / 3 / 5.
-std::vector<double> expected_trajectory(const dil_sign_key* k, size_t n) {
+std::vector<double> expected_trajectory(const dil_sign_key* k, Spec sp, size_t n) {
     const double q = k->P.level == 2 ? 0.765 : (k->P.level == 3 ? 0.804 : 0.74);
-    const size_t T = spec_target(k), M = spec_max(k), cap = slots_for(k, n);
+    const size_t T = sp.target, M = sp.max, cap = slots_for(sp, n);
     std::vector<double> tr;
     double rem = (double)n;
     while (rem >= 0.3 && tr.size() < 200) {
@@ -250,8 +272,10 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
     b.ct_slot = k->ct_slot; b.h_slot = k->h_slot; b.accepted = k->accepted;
     b.zp = d_zp; b.h_out = d_h; b.ct_out = reinterpret_cast<uint64_t*>(d_ct); b.attempts = d_att;
     b.track_done = drain != nullptr;
-    const uint32_t cap_slots = (uint32_t)slots_for(k, n);
-    CK(dil::launch_sign_begin(b, (uint32_t)n, cap_slots, spec_target(k), spec_max(k), st));
+    InFlight load(e->sign_in_flight);
+    const Spec sp = spec_for(k, load.seen);
+    const uint32_t cap_slots = (uint32_t)slots_for(sp, n);
+    CK(dil::launch_sign_begin(b, (uint32_t)n, cap_slots, sp.target, sp.max, st));
     PROF_BEGIN(0);
     if (mk) CK(dil::launch_sign_init(k->mu_d, k->rhop, k->kappa, mk->tr, mk->key, 32, d_msgs, d_off, (uint32_t)n, st));
     else CK(dil::launch_sign_init(k->mu_d, k->rhop, k->kappa, k->seeds, k->seeds + 32, 0, d_msgs, d_off, (uint32_t)n, st));
@@ -268,8 +292,8 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
     // a handful of empty launches.  The host reads the round state (posted write into mapped memory) once per burst.
     // Grid sizes are hints (every kernel strides or claims work dynamically, so any grid is correct): the expected
     // number of active items plus a margin, never more than the last count the host has seen.
-    const std::vector<double> traj = expected_trajectory(k, n);
-    const uint32_t T = spec_target(k), M = spec_max(k);
+    const std::vector<double> traj = expected_trajectory(k, sp, n);
+    const uint32_t T = sp.target, M = sp.max;
     uint32_t enq = 0, seen = (uint32_t)n, seen_at = 0;   // last observed item count and the round it belongs to
     volatile uint32_t* hc = k->ctl_host;
     // per-item keys: the unfused core's stand-alone kernels take their sizes from the host, so every round is observed
@@ -678,7 +702,7 @@ void free_multi(dil_sign_key* k) {
 
 int ensure_multi(dil_engine* e, dil_sign_key* k, size_t n) {
     const LevelParams& P = k->P;
-    const size_t slots = slots_for(k, n);
+    const size_t slots = slots_alloc(k, n);
     if (n <= k->multi_cap && slots <= k->multi_slots) return DIL_OK;
     const size_t in_cap = k->multi_in_cap;
     uint8_t* in = k->multi_in;

@@ -133,7 +133,12 @@ int dil_sign_sizes(int level, size_t *z_bytes, size_t *h_bytes);
 int dil_sign_key_create(dil_engine_t *e, dil_sign_key_t **out, int level, const uint8_t *rho, const uint8_t *key,
                         const uint8_t *tr, const uint8_t *s1_packed, const uint8_t *s2_packed, const uint8_t *t0_packed);
 int dil_sign_key_destroy(dil_engine_t *e, dil_sign_key_t *k);
-/* host pointers.  When z, h, ctilde (and attempts, if given) are all pinned host memory the device can address
+/* Streaming use: a key handle signs one batch at a time (calls on one handle serialise).  To keep several batches in
+ * flight on one GPU - the next batch signs while the small last rejection rounds of the previous one leave SMs idle -
+ * create two to four handles of the same key and call from one host thread per handle (dil_sign_batch_host uses streams
+ * owned by the handle; dil_sign_batch_dev the stream it is given).  Measured on one B200, Dilithium-2, 65 536-message
+ * batches: 12.1 M signs/s with one batch at a time, 13.9 M with two and 14.6 M with four in flight.
+ * host pointers.  When z, h, ctilde (and attempts, if given) are all pinned host memory the device can address
  * (cudaHostAlloc / cudaHostRegister; z and ctilde 16-byte aligned), finished signatures are streamed into them
  * round by round while the batch is still signing; pageable buffers take chunked copy-engine transfers.  The
  * results are identical either way.  attempts may be NULL. */
@@ -147,8 +152,10 @@ uint32_t dil_sign_last_rounds(const dil_sign_key_t *k);   /* rejection rounds of
 uint64_t dil_sign_last_slots(const dil_sign_key_t *k);    /* signing attempts (slots) the last batch executed, speculative ones included */
 /* Per-key tuning of the batch scheduler; zero fields keep the defaults.  Results never depend on these. */
 typedef struct {
-    uint32_t spec_target;    /* straggler speculation: rounds with fewer items are filled up to this many attempt slots (32768) */
-    uint32_t spec_max;       /* ... with at most this many consecutive attempts per item (32, the maximum)                    */
+    uint32_t spec_target;    /* straggler speculation: rounds with fewer items are filled up to this many attempt slots         */
+    uint32_t spec_max;       /* ... with at most this many consecutive attempts per item (at most 32).  Defaults follow the
+                                engine's load: 32768 / 32 for a lone batch, 16384 / 16 with two and 8192 / 8 with three or
+                                more sign batches in flight on the engine (other batches fill the idle SMs instead)            */
     size_t dev_chunk;        /* dil_sign_batch_dev signs larger requests in pieces of this many messages (2^20)               */
     size_t host_chunk;       /* the same for the streaming path of dil_sign_batch_host (2^18)                                 */
     int host_copy_path;      /* non-zero: dil_sign_batch_host always uses chunked copy-engine transfers                       */
