@@ -51,6 +51,7 @@ struct dil_sign_key {
     uint32_t* ctl_host = nullptr;      // mapped pinned copy of the first 16 words of the round state
     uint32_t* ctl_host_dev = nullptr;  // its device alias
     cudaEvent_t round_ev = nullptr;    // orders the copy stream's drains after the rounds they copy
+    cudaEvent_t block_ev = nullptr;    // blocking-sync event: the host thread sleeps instead of spinning when other batches are in flight
     // host-variant staging
     uint8_t *msgs_d = nullptr, *zp_d = nullptr, *h_d = nullptr, *ct_d = nullptr;
     uint64_t* off_d = nullptr;
@@ -151,6 +152,16 @@ size_t slots_for(Spec s, size_t n) {
 // the workspace is sized for the policy that needs the most slots (a lone batch)
 size_t slots_alloc(const dil_sign_key* k, size_t n) { return slots_for(spec_for(k, 1), n); }
 
+// Waiting for a stream: a lone batch spins (lowest latency); with other batches in flight on the engine the host thread
+// sleeps on a blocking-sync event instead, so that T threads per GPU do not burn T cores while their batches sign.
+cudaError_t wait_stream(dil_sign_key* k, cudaStream_t s, bool loaded) {
+    if (loaded && k->block_ev) {
+        cudaError_t er = cudaEventRecord(k->block_ev, s);
+        return er != cudaSuccess ? er : cudaEventSynchronize(k->block_ev);
+    }
+    return cudaStreamSynchronize(s);
+}
+
 // sign batches currently inside sign_rounds on this engine (any key handle, any host thread)
 struct InFlight {
     std::atomic<int>& c;
@@ -203,6 +214,7 @@ int ensure_ws(dil_engine* e, dil_sign_key* k, size_t n) {
         if (err == cudaSuccess) A(cudaHostGetDevicePointer(reinterpret_cast<void**>(&k->ctl_host_dev), k->ctl_host, 0));
     }
     if (err == cudaSuccess && !k->round_ev) A(cudaEventCreateWithFlags(&k->round_ev, cudaEventDisableTiming));
+    if (err == cudaSuccess && !k->block_ev) A(cudaEventCreateWithFlags(&k->block_ev, cudaEventDisableTiming | cudaEventBlockingSync));
     if (err != cudaSuccess) {
         free_ws(k);
         return fail_msg(e, DIL_ERR_ALLOC, std::string("sign workspace: ") + cudaGetErrorString(err));
@@ -387,7 +399,7 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
         }
         if (!step) {
             CK(dil::launch_publish_ctl(k->ctl_host_dev, k->ctl, st));
-            CK(cudaStreamSynchronize(st));
+            CK(wait_stream(k, st, load.seen > 1));
             seen = hc[0];
             seen_at = enq;
         }
@@ -494,6 +506,7 @@ int dil_sign_key_destroy(dil_engine_t* e, dil_sign_key_t* k) {
     for (auto& ev : k->ev)
         if (ev) cudaEventDestroy(ev);
     if (k->round_ev) cudaEventDestroy(k->round_ev);
+    if (k->block_ev) cudaEventDestroy(k->block_ev);
     if (k->st_own) cudaStreamDestroy(k->st_own);
     if (k->cs_own) cudaStreamDestroy(k->cs_own);
     if (k->ctl_host) cudaFreeHost(k->ctl_host);
@@ -623,8 +636,9 @@ int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs,
                                  k->att_d + lo, st, &t);
                 lo += m;
             }
-            cudaError_t e2 = cudaStreamSynchronize(st);
-            cudaError_t e1 = cudaStreamSynchronize(cs);
+            const bool loaded = e->sign_in_flight.load() > 0;
+            cudaError_t e2 = wait_stream(k, st, loaded);
+            cudaError_t e1 = wait_stream(k, cs, loaded);
             cudaEventDestroy(dt.idle);
             if (rc) return rc;
             if (e1 != cudaSuccess) return fail(e, e1, "sign drain sync");

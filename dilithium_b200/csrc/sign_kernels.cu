@@ -114,31 +114,28 @@ __global__ void __launch_bounds__(128) expand_mask_kernel(int32_t* __restrict__ 
     constexpr int CHUNK = BITS;                       // bytes per 8 coefficients
     constexpr int32_t G1 = 1 << GAMMA1_BITS;
     for (int p = 0; p < 32 && wbase + p < n_polys; p++) {
-        const unsigned char* src = stage + (size_t)p * ROW + lane * CHUNK;
-        uint64_t lo, mid;
-        uint32_t hi;
-        if constexpr (BITS == 18) {  // 18 bytes, 2-byte aligned
-            const uint16_t* h = reinterpret_cast<const uint16_t*>(src);
-            lo = (uint64_t)h[0] | ((uint64_t)h[1] << 16) | ((uint64_t)h[2] << 32) | ((uint64_t)h[3] << 48);
-            mid = (uint64_t)h[4] | ((uint64_t)h[5] << 16) | ((uint64_t)h[6] << 32) | ((uint64_t)h[7] << 48);
-            hi = h[8];
-        } else {                     // 20 bytes, 4-byte aligned
-            const uint32_t* h = reinterpret_cast<const uint32_t*>(src);
-            lo = (uint64_t)h[0] | ((uint64_t)h[1] << 32);
-            mid = (uint64_t)h[2] | ((uint64_t)h[3] << 32);
-            hi = h[4];
+        // the lane's 18 / 20 bytes as five aligned 32-bit words (18-byte chunks of odd lanes start two bytes into a word:
+        // one funnel shift per word lines them up), then one funnel shift, one mask and one subtraction per coefficient
+        const unsigned off = lane * CHUNK;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(stage + (size_t)p * ROW + (off & ~3u));
+        uint32_t wd[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) wd[i] = src[i];
+        if constexpr (BITS == 18) {
+            const unsigned s = (off & 2u) * 8;
+#pragma unroll
+            for (int i = 0; i < 4; i++) wd[i] = __funnelshift_r(wd[i], wd[i + 1], s);
+            wd[4] >>= s;
         }
         int32_t v[8];
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            const int pos = c * BITS;
-            uint64_t bits;
-            if (pos + BITS <= 64) bits = lo >> pos;
-            else if (pos < 64) bits = (lo >> pos) | (mid << (64 - pos));
-            else if (pos + BITS <= 128) bits = mid >> (pos - 64);
-            else if (pos < 128) bits = (mid >> (pos - 64)) | ((uint64_t)hi << (128 - pos));
-            else bits = hi >> (pos - 128);
-            v[c] = G1 - (int32_t)((uint32_t)bits & ((1u << BITS) - 1));
+            const int pos = c * BITS, wi = pos >> 5, sh = pos & 31;
+            uint32_t x;
+            if (sh + BITS <= 32) x = wd[wi] >> sh;
+            else x = __funnelshift_r(wd[wi], wd[wi + 1], sh);
+            if (sh + BITS != 32) x &= (1u << BITS) - 1;
+            v[c] = G1 - (int32_t)x;
         }
         int4* dst = reinterpret_cast<int4*>(y + (size_t)(wbase + p) * N) + 2 * lane;
         dst[0] = make_int4(v[0], v[1], v[2], v[3]);

@@ -4,7 +4,10 @@
 // reference's KAT files) from pinned host memory into pinned host memory, checks that the pool's signatures equal the
 // ones a single engine produces for a sample shard, and prints one JSON line with the end-to-end rate.
 //
-//   usage: pool_sign <KAT dir> [level=2] [n_per_gpu=65536] [steps=5] [gpus=all]
+// `in_flight` batches are signed at the same time (one pool key, one set of output buffers and one host thread per batch in
+// flight): the next batch signs while the last rejection rounds of the previous one leave SMs idle and its last signatures drain.
+//
+//   usage: pool_sign <KAT dir> [level=2] [n_per_gpu=65536] [steps=5] [gpus=all] [in_flight=2]
 #include <cuda_runtime.h>
 
 #include <chrono>
@@ -14,6 +17,7 @@
 #include <cstring>
 #include <fstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "dilithium_b200.h"
@@ -41,12 +45,13 @@ static Bytes read_hex_line(const std::string& path, size_t index) {
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::fprintf(stderr, "%s: %s\n", #call, cudaGetErrorString(e_)); return 3; } } while (0)
 
 int main(int argc, char** argv) {
-    if (argc < 2) { std::fprintf(stderr, "usage: pool_sign <KAT dir> [level] [n_per_gpu] [steps] [gpus]\n"); return 2; }
+    if (argc < 2) { std::fprintf(stderr, "usage: pool_sign <KAT dir> [level] [n_per_gpu] [steps] [gpus] [in_flight]\n"); return 2; }
     const std::string dir = argv[1];
     const int level = argc > 2 ? std::atoi(argv[2]) : 2;
     const size_t per_gpu = argc > 3 ? (size_t)std::atol(argv[3]) : 65536;
     const int steps = argc > 4 ? std::atoi(argv[4]) : 5;
     int gpus = argc > 5 ? std::atoi(argv[5]) : 0;
+    const int T = argc > 6 && std::atoi(argv[6]) > 0 ? std::atoi(argv[6]) : 2;
     const std::string sfx = "_" + std::to_string(level) + ".txt";
     const size_t key_index = 0;
     Bytes rho = read_hex_line(dir + "/rho" + sfx, key_index), key = read_hex_line(dir + "/k" + sfx, key_index),
@@ -57,27 +62,47 @@ int main(int argc, char** argv) {
     dil_pool_t* pool = nullptr;
     CK(dil_pool_create(&pool, devs.empty() ? nullptr : devs.data(), (int)devs.size()));
     const size_t G = (size_t)dil_pool_size(pool), n = per_gpu * G, mlen = 32;
-    dil_pool_sign_key_t* pk = nullptr;
-    CK(dil_pool_sign_key_create(pool, &pk, level, rho.data(), key.data(), tr.data(), s1.data(), s2.data(), t0.data()));
+    std::vector<dil_pool_sign_key_t*> pks(T, nullptr);
+    for (int t = 0; t < T; t++)
+        CK(dil_pool_sign_key_create(pool, &pks[t], level, rho.data(), key.data(), tr.data(), s1.data(), s2.data(), t0.data()));
     size_t zb = 0, hb = 0;
     CK(dil_sign_sizes(level, &zb, &hb));
-    // pinned, portable buffers: every engine streams its shard into its slice
-    uint8_t *msgs, *z, *h, *ct;
+    // pinned, portable buffers: every engine streams its shard into its slice; one output set per batch in flight
+    uint8_t* msgs;
     uint64_t* off;
-    uint32_t* att;
+    std::vector<uint8_t*> zs(T), hs(T), cts(T);
+    std::vector<uint32_t*> atts(T);
     CU(cudaHostAlloc((void**)&msgs, n * mlen, cudaHostAllocPortable | cudaHostAllocMapped));
     CU(cudaHostAlloc((void**)&off, (n + 1) * 8, cudaHostAllocPortable | cudaHostAllocMapped));
-    CU(cudaHostAlloc((void**)&z, n * zb, cudaHostAllocPortable | cudaHostAllocMapped));
-    CU(cudaHostAlloc((void**)&h, n * hb, cudaHostAllocPortable | cudaHostAllocMapped));
-    CU(cudaHostAlloc((void**)&ct, n * 32, cudaHostAllocPortable | cudaHostAllocMapped));
-    CU(cudaHostAlloc((void**)&att, n * 4, cudaHostAllocPortable | cudaHostAllocMapped));
+    for (int t = 0; t < T; t++) {
+        CU(cudaHostAlloc((void**)&zs[t], n * zb, cudaHostAllocPortable | cudaHostAllocMapped));
+        CU(cudaHostAlloc((void**)&hs[t], n * hb, cudaHostAllocPortable | cudaHostAllocMapped));
+        CU(cudaHostAlloc((void**)&cts[t], n * 32, cudaHostAllocPortable | cudaHostAllocMapped));
+        CU(cudaHostAlloc((void**)&atts[t], n * 4, cudaHostAllocPortable | cudaHostAllocMapped));
+    }
+    uint8_t *z = zs[0], *h = hs[0], *ct = cts[0];
+    uint32_t* att = atts[0];
     uint64_t x = 0x44494C32ull;
     for (size_t i = 0; i < n * mlen; i++) { x = x * 6364136223846793005ull + 1442695040888963407ull; msgs[i] = (uint8_t)(x >> 56); }
     for (size_t i = 0; i <= n; i++) off[i] = i * mlen;
-    CK(dil_pool_sign_batch_host(pool, pk, msgs, off, n, z, h, ct, att));   // warm-up (workspaces, kernel attributes)
+    for (int t = 0; t < T; t++)   // warm-up (workspaces, kernel attributes)
+        CK(dil_pool_sign_batch_host(pool, pks[t], msgs, off, n, zs[t], hs[t], cts[t], atts[t]));
+    std::vector<int> rcs(T, DIL_OK);
     auto t0c = std::chrono::steady_clock::now();
-    for (int s = 0; s < steps; s++) CK(dil_pool_sign_batch_host(pool, pk, msgs, off, n, z, h, ct, att));
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++)
+            th.emplace_back([&, t] {
+                for (int s = t; s < steps && rcs[t] == DIL_OK; s += T)
+                    rcs[t] = dil_pool_sign_batch_host(pool, pks[t], msgs, off, n, zs[t], hs[t], cts[t], atts[t]);
+            });
+        for (auto& w : th) w.join();
+    }
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0c).count();
+    for (int t = 0; t < T; t++) CK(rcs[t]);
+    bool sets_equal = true;
+    for (int t = 1; t < T && t < steps; t++)
+        sets_equal = sets_equal && !std::memcmp(zs[t], z, n * zb) && !std::memcmp(hs[t], h, n * hb) && !std::memcmp(cts[t], ct, n * 32);
     // cross-check: the last shard, signed alone on engine 0 (pageable outputs -> copy path), must be identical
     const size_t lo = (G - 1) * per_gpu, m = per_gpu < 4096 ? per_gpu : 4096;
     dil_sign_key_t* k0 = nullptr;
@@ -88,16 +113,16 @@ int main(int argc, char** argv) {
     std::vector<uint64_t> o1(m + 1);
     for (size_t i = 0; i <= m; i++) o1[i] = i * mlen;
     CK(dil_sign_batch_host(e0, k0, msgs + lo * mlen, o1.data(), m, z1.data(), h1.data(), c1.data(), a1.data()));
-    const bool same = !std::memcmp(z1.data(), z + lo * zb, m * zb) && !std::memcmp(h1.data(), h + lo * hb, m * hb) &&
+    const bool same = sets_equal && !std::memcmp(z1.data(), z + lo * zb, m * zb) && !std::memcmp(h1.data(), h + lo * hb, m * hb) &&
                       !std::memcmp(c1.data(), ct + lo * 32, m * 32) && !std::memcmp(a1.data(), att + lo, m * 4);
     double att_mean = 0;
     for (size_t i = 0; i < n; i++) att_mean += att[i];
-    std::printf("{\"tool\": \"pool_sign\", \"level\": %d, \"n_gpus\": %zu, \"batch\": %zu, \"steps\": %d, \"signs_per_s\": %.1f, "
+    std::printf("{\"tool\": \"pool_sign\", \"level\": %d, \"n_gpus\": %zu, \"batch\": %zu, \"steps\": %d, \"in_flight\": %d, \"signs_per_s\": %.1f, "
                 "\"ms_per_batch\": %.3f, \"gb_per_s_to_host\": %.2f, \"mean_attempts\": %.4f, \"matches_single_engine\": %s}\n",
-                level, G, n, steps, n * steps / sec, sec / steps * 1e3, n * steps * (double)(zb + hb + 36) / sec / 1e9, att_mean / n,
+                level, G, n, steps, T, n * steps / sec, sec / steps * 1e3, n * steps * (double)(zb + hb + 36) / sec / 1e9, att_mean / n,
                 same ? "true" : "false");
     dil_sign_key_destroy(e0, k0);
-    dil_pool_sign_key_destroy(pool, pk);
+    for (auto* pk : pks) dil_pool_sign_key_destroy(pool, pk);
     dil_pool_destroy(pool);
     return same ? 0 : 1;
 }

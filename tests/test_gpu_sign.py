@@ -160,3 +160,70 @@ def test_sign_multi_all_kats_in_one_batch(eng, oracle, level):
         assert np.array_equal(c[m], co) and np.array_equal(z[m], zo) and np.array_equal(h[m], ho) and att[m] == a, (level, m)
     ok = eng.verify_multi(level, K["rho"][kidx], K["t1"][kidx], msgs2, z, h, c)
     assert ok.tolist() == [1] * n
+
+
+def test_sign_batches_in_flight(eng, oracle):
+    """Streaming use of the API: several key handles of the same key sign different batches at the same time from their
+    own host threads (host path: the handle's own streams and the round-by-round drain into pinned buffers; device path:
+    one torch stream per thread).  The engine speculates less when it sees the load (sign_api.cu spec_for); every
+    batch must equal what a lone call produces, bit for bit, and a sample must match the oracle."""
+    import threading
+    import torch
+    import dilithium_b200 as d
+    level, n, T = 2, 6000, 4
+    K = ol.kat(level)
+    parts = [K[f][5] for f in ("rho", "k", "tr", "s1", "s2", "t0")]
+    keys = [d.SignKey(eng, level, *parts) for _ in range(T)]
+    batches = [[(t * n + i).to_bytes(4, "little") * (1 + (i + t) % 7) for i in range(n)] for t in range(T)]
+    lone = [[np.array(a) for a in keys[0].sign(b, pinned=True)] for b in batches]
+    lone_rounds = keys[0].last_rounds
+    for m in range(0, n, 601):
+        zo, ho, co, a = oracle.sign(level, *parts, batches[1][m])
+        assert np.array_equal(lone[1][0][m], zo) and np.array_equal(lone[1][1][m], ho) and np.array_equal(lone[1][2][m], co) and lone[1][3][m] == a
+    # host path, T threads x 3 calls each
+    got, errs = [None] * T, []
+
+    def host_worker(t):
+        try:
+            torch.cuda.set_device(0)
+            for _ in range(3):
+                got[t] = [np.array(a) for a in keys[t].sign(batches[t], pinned=True)]
+        except Exception as ex:   # noqa: BLE001
+            errs.append(ex)
+    th = [threading.Thread(target=host_worker, args=(t,)) for t in range(T)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs
+    for t in range(T):
+        for name, a, b in zip(("z", "h", "c", "att"), lone[t], got[t]):
+            assert np.array_equal(a, b), (t, name, "host path in flight")
+    # device path on T streams
+    dev_in, dev_out, streams = [], [], [torch.cuda.Stream() for _ in range(T)]
+    for t in range(T):
+        blob = np.frombuffer(b"".join(batches[t]), dtype=np.uint8).copy()
+        off = np.zeros(n + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(m) for m in batches[t]])
+        dev_in.append((torch.from_numpy(blob).cuda(), torch.from_numpy(off).cuda()))
+        dev_out.append((torch.zeros((n, keys[t].z_bytes), dtype=torch.uint8, device="cuda"), torch.zeros((n, keys[t].h_bytes), dtype=torch.uint8, device="cuda"),
+                        torch.zeros((n, 32), dtype=torch.uint8, device="cuda"), torch.zeros(n, dtype=torch.int32, device="cuda")))
+    torch.cuda.synchronize()
+
+    def dev_worker(t):
+        try:
+            torch.cuda.set_device(0)
+            with torch.cuda.stream(streams[t]):
+                for _ in range(3):
+                    keys[t].sign_dev(dev_in[t][0], dev_in[t][1], n, *dev_out[t])
+            streams[t].synchronize()
+        except Exception as ex:   # noqa: BLE001
+            errs.append(ex)
+    th = [threading.Thread(target=dev_worker, args=(t,)) for t in range(T)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs
+    for t in range(T):
+        for name, a, b in zip(("z", "h", "c", "att"), lone[t], dev_out[t]):
+            assert np.array_equal(a, b.cpu().numpy()), (t, name, "device path in flight")
+    assert lone_rounds >= 1
+    for k in keys:
+        k.close()
