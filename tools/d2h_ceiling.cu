@@ -10,7 +10,7 @@
 // Modes: threads (one process, one host thread per GPU - the shape of dil_pool) or procs (one process per GPU,
 // fork before CUDA is touched - the shape of torchrun).  Subsets N = 1, 2, 4, ... up to --gpus.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/bin/d2h_ceiling tools/d2h_ceiling.cu -lpthread
-//   tools/bin/d2h_ceiling [--gpus 8] [--rows 65536] [--reps 8] [--mode threads|procs|both]
+//   tools/bin/d2h_ceiling [--gpus 8] [--rows 65536] [--reps 8] [--mode threads|procs|both] [--wc 0|1] [--min-n 1]
 #include <cuda_runtime.h>
 #include <sys/mman.h>
 #include <sys/wait.h>
@@ -75,6 +75,8 @@ static void barrier(Shared* sh, int phase, int n) {
 }
 
 // one GPU's work: for every (subset, variant) phase this GPU takes part in, wait on the barrier, run, record its time
+static int g_wc = 0, g_min_n = 1;   // --wc 1: write-combined pinned memory (not snooped by the CPU caches); --min-n: skip smaller subsets
+
 static void worker(int dev, int max_gpus, uint32_t rows, int reps, Shared* sh) {
     CK(cudaSetDevice(dev));
     const size_t bytes = (size_t)rows * ROW, zbytes = (size_t)rows * ZROW;
@@ -82,7 +84,7 @@ static void worker(int dev, int max_gpus, uint32_t rows, int reps, Shared* sh) {
     uint32_t* dlist;
     CK(cudaMalloc(&dsrc, bytes));
     CK(cudaMemset(dsrc, 0x5a, bytes));
-    CK(cudaHostAlloc(&hdst, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+    CK(cudaHostAlloc(&hdst, bytes, cudaHostAllocMapped | cudaHostAllocPortable | (g_wc ? cudaHostAllocWriteCombined : 0)));
     memset(hdst, 0, bytes);
     CK(cudaHostGetDevicePointer(&hdst_dev, hdst, 0));
     std::vector<uint32_t> list(rows);
@@ -95,7 +97,7 @@ static void worker(int dev, int max_gpus, uint32_t rows, int reps, Shared* sh) {
     int phase = 0;
     for (int n = 1; n <= max_gpus; n *= 2) {
         for (int v = 0; v < NV; v++, phase++) {
-            if (dev >= n) continue;
+            if (dev >= n || n < g_min_n) continue;
             const Variant& V = VARIANTS[v];
             auto run = [&](int r) {
                 for (int i = 0; i < r; i++) {
@@ -142,6 +144,8 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--rows")) rows = atoi(argv[i + 1]);
         else if (!strcmp(argv[i], "--reps")) reps = atoi(argv[i + 1]);
         else if (!strcmp(argv[i], "--mode")) mode = argv[i + 1];
+        else if (!strcmp(argv[i], "--wc")) g_wc = atoi(argv[i + 1]);
+        else if (!strcmp(argv[i], "--min-n")) g_min_n = atoi(argv[i + 1]);
     }
     auto fresh = []() {
         void* p = mmap(nullptr, sizeof(Shared), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
@@ -152,6 +156,7 @@ int main(int argc, char** argv) {
     };
     printf("d2h_ceiling: %u rows x %u B = %.1f MB per GPU per repetition, %d repetitions, up to %d GPUs, %ld host CPUs\n", rows, ROW,
            rows * (double)ROW / 1e6, reps, gpus, sysconf(_SC_NPROCESSORS_ONLN));
+    printf("host buffers: %s pinned memory\n", g_wc ? "WRITE-COMBINED" : "ordinary (cacheable)");
     if (mode == "procs" || mode == "both") {
         // fork BEFORE any CUDA call: each child creates its own context, as torchrun ranks do
         printf("mode procs (one process per GPU):\n");
