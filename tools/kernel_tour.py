@@ -58,4 +58,16 @@ pool.load_key(2, K["rho"][0], K["k"][0], K["tr"][0], K["s1"][0], K["s2"][0], K["
 pz, ph, pc, pa = pool.sign(msgs)
 assert np.array_equal(z, pz) and np.array_equal(att, pa)
 pool.close()
+# three batches in flight on three handles of the same key (host path with pinned outputs: own streams, drain kernel, blocking waits)
+import threading
+sks = [d.SignKey(eng, 2, K["rho"][0], K["k"][0], K["tr"][0], K["s1"][0], K["s2"][0], K["t0"][0]) for _ in range(3)]
+res = [None] * 3
+def _worker(t):
+    torch.cuda.set_device(0)
+    for _ in range(2):
+        res[t] = [np.array(a) for a in sks[t].sign(msgs, pinned=True)]
+th = [threading.Thread(target=_worker, args=(t,)) for t in range(3)]
+[x.start() for x in th]; [x.join() for x in th]
+for r in res:
+    assert np.array_equal(z, r[0]) and np.array_equal(h, r[1]) and np.array_equal(c, r[2]) and np.array_equal(att, r[3])
 print("tour ok", eng.launch_count)
