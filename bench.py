@@ -561,6 +561,38 @@ def cfg5_sweep(c, max_log2):
             "rows": rows}
 
 
+def keygen_record(c, keccak_peak, n=65536):
+    """SURVEY.md 8f row N4 under the same clock: batched key generation (combined_top.v mode 0, tb_keygen_top.v:145-275) from
+    32-byte seeds, device-resident (dil_keygen_batch_dev) at every level; the first 100 seeds of the level-2 batch are the KAT
+    seeds and must reproduce the KAT keys.  Keccak work per key: 1 (seed) + (k + l) eta-sampler polynomials (>= 1-2 permutations
+    each) + 5 k l (ExpandA) + tr (SHAKE-256 over rho || t1: 10 / 15 / 20 permutations)."""
+    import numpy as np
+    import oracle_lib as ol
+    torch, eng = c.torch, c.eng
+    out = {"workload": f"{n} keys per GPU from 32-byte seeds, device-resident", "levels": {}}
+    for level in (2, 3, 5):
+        k, l = LEVEL_DIMS[level]
+        K = ol.kat(level)
+        gen = torch.Generator(device="cpu").manual_seed(SEED + 40 + level + 16 * c.rank)
+        seeds = torch.randint(0, 256, (n, 32), dtype=torch.uint8, generator=gen)
+        seeds[:100] = torch.from_numpy(np.ascontiguousarray(K["z"][:100]))   # z_*.txt holds the keygen seeds xi
+        d_seeds = seeds.to(c.dev)
+        keys = eng.keygen_dev(level, d_seeds)
+        torch.cuda.synchronize()
+        kat_ok = None
+        if True:
+            kat_ok = all(bool(np.array_equal(keys[f][:100].cpu().numpy(), K[f][:100])) for f in ("rho", "k", "tr", "s1", "s2", "t1", "t0"))
+            if not kat_ok:
+                raise RuntimeError(f"bench: keygen level {level} does not reproduce the KAT keys")
+        ms = c.time_ms(lambda: eng.keygen_dev(level, d_seeds), 5, warm=1)
+        perms = 1 + 2 * (k + l) + 5 * k * l + (32 + k * 320) // 136 + 1
+        out["levels"][str(level)] = {"keys_per_s": c.world * n / (ms * 1e-3), "ms": ms, "kat_keys_reproduced": kat_ok,
+                                     "keccak_f_per_key_approx": perms,
+                                     "keccak_frac_of_measured_peak": n * perms / (ms * 1e-3) / keccak_peak}
+        del keys, d_seeds
+    return out
+
+
 def run_engine(args):
     import numpy as np
     c = Ctx()
@@ -756,7 +788,7 @@ def run_engine(args):
     configs = None
     if not args.no_configs:
         t_cfg = time.perf_counter()
-        configs = {"kat_length_messages": kat_length_record(c, key, B), "cfg3": cfg3_record(c, keccak_peak),
+        configs = {"kat_length_messages": kat_length_record(c, key, B), "keygen": keygen_record(c, keccak_peak), "cfg3": cfg3_record(c, keccak_peak),
                    "cfg4": cfg4_record(c, keccak_peak), "cfg5": cfg5_sweep(c, args.sweep_max_log2)}
         configs["wall_s"] = time.perf_counter() - t_cfg
 

@@ -90,14 +90,27 @@ __global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L, WARPS)) matv
     // CTA that starts late finds the counter exhausted and leaves).  Without a counter the distribution is
     // the static warp-stride one.
     if (work_ctr != nullptr) {
-        uint32_t claim = 0;
-        if (lane == 0) claim = atomicAdd(work_ctr, 1u);
-        uint32_t item = __shfl_sync(0xffffffffu, claim, 0);
+        // items are claimed TWO ahead, so that the next item's inputs can be pulled into L2 (register-free prefetches) while
+        // the current one is transformed
+        uint32_t claim = 0, next = 0;
+        if (lane == 0) {
+            next = atomicAdd(work_ctr, 2u);
+            claim = next + 1;
+        }
+        uint32_t item = __shfl_sync(0xffffffffu, next, 0);
+        next = __shfl_sync(0xffffffffu, claim, 0);
         while (item < batch) {
             if (lane == 0) claim = atomicAdd(work_ctr, 1u);
+            if (next < batch) {
+                const char* vl = reinterpret_cast<const char*>(v + (size_t)next * L * N) + 128 * lane;
+#pragma unroll
+                for (int q = 0; q < (L * N * 4 + 4095) / 4096; q++)
+                    if (4096 * q + 128 * lane < L * N * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(vl + 4096 * q));
+            }
             item_core<K, L, NTT_IN, INTT_OUT, false, W1>(w + (size_t)item * K * N, v + (size_t)item * L * N, a_sm, scr, lane, nullptr,
                                                          W1 ? w1p + (size_t)item * W1_ROW : nullptr);
-            item = __shfl_sync(0xffffffffu, claim, 0);
+            item = next;
+            next = __shfl_sync(0xffffffffu, claim, 0);
         }
     } else {
         for (uint32_t item = blockIdx.x * WARPS + warp; item < batch; item += gridDim.x * WARPS)

@@ -648,6 +648,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sign_tail_sparse_kernel(
         }
     };
 
+    // (Claiming two slots ahead and pulling the next slot's c / w into L2 with prefetches was measured 4 % SLOWER here: per-slot work
+    // varies tenfold and the late rounds have only 5-9 slots per warp, so every slot a warp holds back costs balance.)
     uint32_t claim = 0;
     if (lane == 0) claim = atomicAdd(work_ctr, 1u);
     for (uint32_t a = __shfl_sync(0xffffffffu, claim, 0); a < n_slots; a = __shfl_sync(0xffffffffu, claim, 0)) {
@@ -674,6 +676,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) sign_tail_sparse_kernel(
         // HighBits(w) != 0 flag for the survivors
         bool bad = false;
         int32_t* wa = w + (size_t)a * K * N;
+        {   // rows 1 .. K-1 of w and the first polynomial of y are on their way into L2 while row 0 is checked (no registers needed)
+            constexpr int LINES = (K - 1) * 8 + 8;
+#pragma unroll
+            for (int q = 0; q < (LINES + 31) / 32; q++) {
+                const int ln = 32 * q + lane;
+                if (ln < (K - 1) * 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(wa + N) + 128 * ln));
+                else if (ln < LINES) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(y + (size_t)a * L * N) + 128 * (ln - (K - 1) * 8)));
+            }
+        }
 #pragma unroll 1
         for (int i = 0; i < K && !bad; i++) {
             int4* wp = reinterpret_cast<int4*>(wa + i * N) + 2 * lane;
