@@ -68,7 +68,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=65536, help="signatures per GPU per step (weak scaling)")
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--in-flight", type=int, default=4,
-                    help="sign batches in flight per GPU in the timed loops (one key handle, stream and host thread each); 1 = strictly one at a time")
+                    help="sign batches in flight per GPU in the timed loops (one key handle and stream each); 1 = strictly one at a time")
+    ap.add_argument("--driver", default="async", choices=["async", "threads"],
+                    help="how the batches in flight are driven: one host thread with dil_sign_batch_*_begin / dil_sign_batch_finish (default) "
+                         "or one host thread per batch in flight with the synchronous calls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg3 / cfg4 / cfg5 sub-records")
     ap.add_argument("--sweep-max-log2", type=int, default=22)
@@ -636,6 +639,22 @@ def run_engine(args):
         ctxs.append((kx, torch.empty_like(z), torch.empty_like(h), torch.empty_like(ct), torch.zeros_like(att), torch.cuda.Stream()))
 
     def run_pipelined(n_steps, start_ev=None):
+        if args.driver == "async":
+            # ONE host thread: step i is begun on context i mod T as soon as that context's previous step has been finished
+            if start_ev is not None:
+                for cx_ in ctxs:
+                    cx_[5].wait_event(start_ev)
+            for i in range(n_steps):
+                kx, zx, hx, cx, ax, st = ctxs[i % T]
+                if i >= T:
+                    kx.finish()
+                with torch.cuda.stream(st):
+                    kx.sign_dev_begin(msgs, offs, B, zx, hx, cx, ax)
+            for i in range(max(0, n_steps - T), n_steps):
+                ctxs[i % T][0].finish()
+            for cx_ in ctxs:
+                torch.cuda.current_stream().wait_stream(cx_[5])
+            return
         errs = []
 
         def worker(wi):
@@ -753,6 +772,15 @@ def run_engine(args):
             for _ in range(n_steps):
                 e2e_call(0)
             return
+        if args.driver == "async":
+            for i in range(n_steps):
+                which = i % in_flight
+                if i >= in_flight:
+                    ctxs[which][0].finish()
+                ctxs[which][0].sign_host_begin(msgs_host, offs_host, B, *bufs[which])
+            for i in range(max(0, n_steps - in_flight), n_steps):
+                ctxs[i % in_flight][0].finish()
+            return
         errs = []
 
         def worker(which):
@@ -807,7 +835,9 @@ def run_engine(args):
             "config": {"workload": workload_name(level, B), "level": level, "k": k, "l": l, "batch_per_gpu": B,
                        "key": "reference KAT vector 0 (tests/golden)", "mean_attempts": mean_attempts,
                        "batches_in_flight": T,
-                       "batches_in_flight_note": ("every step is one full batch; step i runs on key handle / stream / host thread i mod T, all K steps "
+                       "batches_in_flight_driver": ("one host thread: dil_sign_batch_dev_begin / dil_sign_batch_finish" if args.driver == "async"
+                                                    else "one host thread per batch in flight: dil_sign_batch_dev"),
+                       "batches_in_flight_note": ("every step is one full batch; step i runs on key handle / stream i mod T, all K steps "
                                                   "start and finish inside the timed region; `one_batch_at_a_time` is the strictly serial figure"),
                        "rejection_rounds": rounds,
                        "attempt_slots_per_step": slots, "host_syncs_per_step": "1 (the rejection loop runs on the device; rounds are enqueued ahead)",
@@ -846,9 +876,10 @@ def run_engine(args):
                           "hbm_frac": B * (k + l) * 1024 / (core_ms * 1e-3) / 1e9 / peak, "ncu_limiter": ncu_limiter("signcore")},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * MSG_BYTES + (B + 1) * 8,
                     "d2h_bytes_per_step": B * (sig_bytes + 4), "steps": e2e_steps,
-                    "api": "dil_sign_batch_host (C ABI): pinned host messages in, z/h/c~/attempts back in host memory",
+                    "api": ("dil_sign_batch_host_begin / dil_sign_batch_finish (C ABI, one host thread)" if args.driver == "async" and T > 1 else
+                            "dil_sign_batch_host (C ABI)") + ": pinned host messages in, z/h/c~/attempts back in host memory",
                     "batches_in_flight": T, "one_call_at_a_time": e2e_res[1],
-                    "timing": "host wall clock around the synchronous calls (one host thread, key handle and pinned buffer set per batch in flight), max over ranks",
+                    "timing": "host wall clock around the calls (one key handle and pinned buffer set per batch in flight), max over ranks",
                     "matches_device_path": e2e_ok,
                     "host_ceiling": ({"aggregate_gb_per_s": ceiling, "signatures_per_s": ceiling * 1e9 / (sig_bytes + 4),
                                       "e2e_frac_of_ceiling": e2e_val * (sig_bytes + 4) / (ceiling * 1e9),

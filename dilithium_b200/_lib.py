@@ -52,6 +52,9 @@ SIGNATURES = {
     "dil_sign_key_destroy": (c_int, [c_void, c_void]),
     "dil_sign_batch_host": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void]),
     "dil_sign_batch_dev": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void, c_void]),
+    "dil_sign_batch_dev_begin": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void, c_void]),
+    "dil_sign_batch_host_begin": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void]),
+    "dil_sign_batch_finish": (c_int, [c_void, c_void]),
     "dil_sign_multi_host": (c_int, [c_void, c_int] + [c_void] * 8 + [c_size] + [c_void] * 4),
     "dil_sign_multi_dev": (c_int, [c_void, c_int] + [c_void] * 8 + [c_size] + [c_void] * 5),
     "dil_sign_last_rounds": (ctypes.c_uint32, [c_void]),

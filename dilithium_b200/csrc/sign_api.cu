@@ -59,6 +59,7 @@ struct dil_sign_key {
     size_t msgs_cap = 0, out_cap = 0;
     uint32_t last_rounds = 0;
     uint64_t last_slots = 0;
+    void* pend = nullptr;        // Pending*: the batch between *_begin and dil_sign_batch_finish (one per handle)
     dil_sign_tuning tune{};      // zero = defaults
     // one key per signature (dil_sign_multi_*): per-item key material and the unfused core's intermediates
     int32_t *a_items = nullptr, *key_items = nullptr, *yh = nullptr, *wh = nullptr;
@@ -260,11 +261,152 @@ struct MultiKeys {
     const uint8_t *tr, *key;
 };
 
-// the round loop; all pointers are device pointers
+// ---- the round loop of a batch under one key, split in two so that a caller can keep several batches in flight from ONE
+// host thread: rounds_begin enqueues the expected number of rounds (the loop itself runs on the device) and returns;
+// rounds_finish waits, looks at the round state and enqueues more rounds until nothing is left.
+struct Pending {
+    dil::SignBufs b{};
+    Spec sp{};
+    size_t n = 0;
+    uint32_t cap_slots = 0, enq = 0, seen = 0, seen_at = 0;
+    std::vector<double> traj;
+    cudaStream_t st = nullptr;
+    bool has_drain = false, host = false, loaded = false;
+    DrainTarget drain{};
+    uint64_t launches = 0;
+};
+
+dil::SignBufs sign_bufs(const dil_sign_key* k, uint8_t* d_zp, uint8_t* d_h, uint8_t* d_ct, uint32_t* d_att, bool track_done) {
+    dil::SignBufs b{};
+    b.ctl = k->ctl; b.active[0] = k->active[0]; b.active[1] = k->active[1]; b.done_list = k->done_list;
+    b.mu = k->mu_d; b.rhop = k->rhop; b.kappa = k->kappa; b.y = k->y; b.w = k->w; b.w1p = k->w1p; b.c = k->c;
+    b.ct_slot = k->ct_slot; b.h_slot = k->h_slot; b.accepted = k->accepted;
+    b.zp = d_zp; b.h_out = d_h; b.ct_out = reinterpret_cast<uint64_t*>(d_ct); b.attempts = d_att;
+    b.track_done = track_done;
+    return b;
+}
+
+// enqueue `burst` more rounds of the pending batch (grid sizes are hints derived from the expected trajectory), then
+// the publication of the round state into mapped host memory
+int rounds_enqueue(dil_engine* e, dil_sign_key* k, Pending& p, int burst) {
+    const LevelParams& P = k->P;
+    const uint32_t T = p.sp.target, M = p.sp.max;
+    cudaStream_t st = p.st;
+    for (int i = 0; i < burst; i++, p.enq++) {
+        uint32_t ci = p.seen;   // hint: items of this round
+        if (p.enq > p.seen_at) {
+            const size_t ti = p.enq < p.traj.size() ? p.enq : p.traj.size() - 1, ts = p.seen_at < p.traj.size() ? p.seen_at : p.traj.size() - 1;
+            const double ratio = p.traj[ts] > 0 ? p.traj[ti] / p.traj[ts] : 1.0;
+            const double guess = (double)p.seen * ratio * 1.25 + 512.0;
+            if (guess < (double)p.seen) ci = (uint32_t)guess;
+        }
+        const uint64_t cs64 = ci >= T ? ci : ((uint64_t)ci * M < p.cap_slots ? (uint64_t)ci * M : p.cap_slots);
+        const uint32_t cs = (uint32_t)(cs64 < ci ? ci : cs64);   // hint: slots of this round
+        if (k->tune.fused_mask) {
+            CK(dil::launch_mask_core(P.level, p.b, k->a_hat, cs, e->sm_count, st, k->tune.mask_producers));
+            p.launches += 1;
+        } else {
+            CK(dil::launch_expand_mask(P.level, p.b, cs, st));
+            CK(dil::launch_signcore(k->w, k->a_hat, k->y, P.k, P.l, cs, e->sm_count, st, &k->ctl->ctr_core,
+                                    reinterpret_cast<uint8_t*>(k->w1p), &k->ctl->n_slots));
+            p.launches += 2;
+        }
+        CK(dil::launch_challenge(P.level, p.b, cs, st));
+        CK(dil::launch_sign_tail(P.level, p.b, k->key_hat, k->key_small, cs, e->sm_count, st));
+        // only a first round of >= spec_target items is known to run without speculation; later rounds decide on the device
+        if (!(p.enq == 0 && p.n >= T)) { CK(dil::launch_resolve(P.level, p.b, ci < T ? ci : T, st)); p.launches++; }
+        CK(dil::launch_plan(k->ctl, p.enq, st));
+        p.launches += 3;
+        if (p.has_drain) {
+            CK(cudaEventRecord(k->round_ev, st));
+            CK(cudaStreamWaitEvent(p.drain.stream, k->round_ev, 0));
+            CK(dil::launch_drain(p.drain.z, p.drain.h, p.drain.ct, p.drain.att, p.b, p.enq, (uint32_t)(P.l * P.z_bytes),
+                                 (uint32_t)(P.omega + P.k), p.drain.stream));
+            p.launches++;
+        }
+    }
+    CK(dil::launch_publish_ctl(k->ctl_host_dev, k->ctl, st));
+    return DIL_OK;
+}
+
+void pending_drop(dil_engine* e, dil_sign_key* k) {
+    if (!k->pend) return;
+    --e->sign_in_flight;
+    delete static_cast<Pending*>(k->pend);
+    k->pend = nullptr;
+}
+
+int rounds_begin(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uint64_t* d_off, size_t n, uint8_t* d_zp, uint8_t* d_h,
+                 uint8_t* d_ct, uint32_t* d_att, cudaStream_t st, const DrainTarget* drain) {
+    if (k->pend) return fail_msg(e, DIL_ERR_ARG, "sign: this key handle already has a batch in flight (dil_sign_batch_finish it first)");
+    int rc = ensure_ws(e, k, n);
+    if (rc) return rc;
+    // the previous batch's last drains still read the done list and the round state: let them finish first
+    if (drain) CK(cudaStreamWaitEvent(st, drain->idle, 0));
+    Pending* p = new (std::nothrow) Pending();
+    if (!p) return DIL_ERR_ALLOC;
+    k->pend = p;
+    const int load = ++e->sign_in_flight;
+    p->loaded = load > 1;
+    p->sp = spec_for(k, load);
+    p->n = n;
+    p->st = st;
+    p->cap_slots = (uint32_t)slots_for(p->sp, n);
+    p->b = sign_bufs(k, d_zp, d_h, d_ct, d_att, drain != nullptr);
+    p->has_drain = drain != nullptr;
+    if (drain) p->drain = *drain;
+    p->seen = (uint32_t)n;
+    p->traj = expected_trajectory(k, p->sp, n);
+    auto bail = [&](int code) { pending_drop(e, k); return code; };
+    cudaError_t er = dil::launch_sign_begin(p->b, (uint32_t)n, p->cap_slots, p->sp.target, p->sp.max, st);
+    if (er == cudaSuccess) er = dil::launch_sign_init(k->mu_d, k->rhop, k->kappa, k->seeds, k->seeds + 32, 0, d_msgs, d_off, (uint32_t)n, st);
+    if (er != cudaSuccess) return bail(fail(e, er, "sign: first launches"));
+    p->launches = 2;
+    rc = rounds_enqueue(e, k, *p, (int)p->traj.size() + 1);
+    if (rc) return bail(rc);
+    return DIL_OK;
+}
+
+// may_sleep: the synchronous calls (one host thread per batch in flight) sleep on a blocking event under load; the asynchronous
+// pair is driven by one thread for many batches, which should see completions as early as possible, so it spins
+int rounds_finish(dil_engine* e, dil_sign_key* k, bool may_sleep) {
+    Pending* p = static_cast<Pending*>(k->pend);
+    if (!p) return fail_msg(e, DIL_ERR_ARG, "sign: no batch in flight on this key handle");
+    volatile uint32_t* hc = k->ctl_host;
+    int rc = DIL_OK;
+    for (;;) {
+        cudaError_t er = wait_stream(k, p->st, may_sleep && (p->loaded || e->sign_in_flight.load() > 1));
+        if (er != cudaSuccess) { rc = fail(e, er, "sign: waiting for the rounds"); break; }
+        p->seen = hc[0];
+        p->seen_at = p->enq;
+        if (p->seen == 0) break;
+        if (p->enq > 4000) { rc = fail_msg(e, DIL_ERR_CUDA, "sign: rejection loop did not terminate"); break; }
+        rc = rounds_enqueue(e, k, *p, 2);
+        if (rc) break;
+    }
+    if (rc == DIL_OK && p->has_drain) {
+        cudaError_t er = cudaEventRecord(p->drain.idle, p->drain.stream);
+        if (er != cudaSuccess) rc = fail(e, er, "sign drain event");
+    }
+    e->launches += p->launches;
+    if (rc == DIL_OK) {
+        k->last_rounds = hc[8];
+        k->last_slots = hc[9];
+    }
+    pending_drop(e, k);
+    return rc;
+}
+
+// the round loop, one call (profiling and one-key-per-signature batches observe every round); all pointers are device pointers
 int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uint64_t* d_off, size_t n, uint8_t* d_zp,
                 uint8_t* d_h, uint8_t* d_ct, uint32_t* d_att, cudaStream_t st, const DrainTarget* drain = nullptr,
                 const MultiKeys* mk = nullptr) {
     const LevelParams& P = k->P;
+    if (!k->profile && mk == nullptr) {   // the ordinary batch: begin + finish
+        int rcb = rounds_begin(e, k, d_msgs, d_off, n, d_zp, d_h, d_ct, d_att, st, drain);
+        return rcb ? rcb : rounds_finish(e, k, true);
+    }
+    if (k->pend) return fail_msg(e, DIL_ERR_ARG, "sign: this key handle already has a batch in flight (dil_sign_batch_finish it first)");
     int rc = ensure_ws(e, k, n);
     if (rc) return rc;
     // the previous batch's last drains still read the done list and the round state: let them finish first
@@ -495,6 +637,7 @@ int dil_sign_key_create(dil_engine_t* e, dil_sign_key_t** out, int level, const 
 int dil_sign_key_destroy(dil_engine_t* e, dil_sign_key_t* k) {
     if (!k) return DIL_OK;
     DeviceGuard dg(k->device);
+    if (k->pend && e) dil_sign_batch_finish(e, k);   // a batch begun and never finished: let it run out before its buffers go
     const LevelParams& P = k->P;
     free_ws(k);
     wipe_free(k->key_hat, (size_t)(P.l + 2 * P.k) * 1024);
@@ -522,6 +665,7 @@ int dil_sign_key_set_tuning(dil_sign_key_t* k, const dil_sign_tuning* t) {
     if (!k) return DIL_ERR_ARG;
     if (t && t->spec_max > 32) return DIL_ERR_ARG;
     std::lock_guard<std::mutex> g(k->mu);
+    if (k->pend) return DIL_ERR_ARG;   // not between *_begin and dil_sign_batch_finish
     k->tune = t ? *t : dil_sign_tuning{};
     return DIL_OK;
 }
@@ -547,6 +691,7 @@ int dil_sign_batch_dev(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* d_msgs
     std::lock_guard<std::mutex> g(k->mu);
     DeviceGuard dg(e->device);
     if (!dg.ok) return DIL_ERR_CUDA;
+    if (k->pend) return fail_msg(e, DIL_ERR_ARG, "sign: this key handle already has a batch in flight (dil_sign_batch_finish it first)");
     // very large batches are signed in 2^20-message pieces so that the per-attempt workspace (about
     // 9.5 / 13 / 17 KB per message at levels 2 / 3 / 5) stays bounded
     const size_t chunk = k->tune.dev_chunk ? k->tune.dev_chunk : ((size_t)1 << 20);
@@ -561,21 +706,17 @@ int dil_sign_batch_dev(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* d_msgs
     return DIL_OK;
 }
 
-int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs, const uint64_t* offsets, size_t n,
-                        uint8_t* z, uint8_t* h, uint8_t* ctilde, uint32_t* attempts) {
-    if (!e || !k) return DIL_ERR_ARG;
-    if (n == 0) return DIL_OK;
-    if (!msgs || !offsets || !z || !h || !ctilde || n > 0x07FFFFFFu) return DIL_ERR_ARG;
-    if (!offsets_ok(offsets, n)) return DIL_ERR_ARG;
-    std::lock_guard<std::mutex> g(k->mu);
-    DeviceGuard dg(e->device);
-    if (!dg.ok) return DIL_ERR_CUDA;
+}  // extern "C"
+
+namespace {
+
+// host path, common part: the handle's own streams, device staging for the messages and the packed outputs, H2D of the inputs
+int host_stage(dil_engine* e, dil_sign_key* k, const uint8_t* msgs, const uint64_t* offsets, size_t n) {
     const LevelParams& P = k->P;
     if (!k->st_own) {
         CK(cudaStreamCreateWithFlags(&k->st_own, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&k->cs_own, cudaStreamNonBlocking));
     }
-    cudaStream_t st = k->st_own;
     const size_t mbytes = offsets[n] > 0 ? offsets[n] : 1;
     const size_t zb = (size_t)P.l * P.z_bytes, hb = (size_t)P.omega + P.k;
     if (mbytes > k->msgs_cap) {
@@ -600,29 +741,118 @@ int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs,
         CK(dmalloc(&k->att_d, n));
         k->out_cap = n;
     }
-    CK(cudaMemcpyAsync(k->msgs_d, msgs, offsets[n], cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(k->off_d, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    cudaStream_t cs = k->cs_own;
-    // Streaming path: when every output buffer is pinned host memory the device can address (cudaHostAlloc /
-    // cudaHostRegister; torch's pinned tensors are), finished signatures leave round by round (DrainTarget)
-    // and the transfer hides behind the remaining rounds.  Pageable buffers take the chunked copy path below.
+    CK(cudaMemcpyAsync(k->msgs_d, msgs, offsets[n], cudaMemcpyHostToDevice, k->st_own));
+    CK(cudaMemcpyAsync(k->off_d, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, k->st_own));
+    return DIL_OK;
+}
+
+// Streaming path: when every output buffer is pinned host memory the device can address (cudaHostAlloc /
+// cudaHostRegister; torch's pinned tensors are), finished signatures leave round by round (DrainTarget)
+// and the transfer hides behind the remaining rounds.  Returns false for pageable (or misaligned) buffers.
+bool host_drain_target(const dil_sign_key* k, uint8_t* z, uint8_t* h, uint8_t* ctilde, uint32_t* attempts, DrainTarget& dt) {
+    if (k->tune.host_copy_path) return false;
+    auto dev_alias = [&](const void* p, size_t align) -> void* {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+        if (reinterpret_cast<uintptr_t>(a.devicePointer) & (align - 1)) return nullptr;
+        return a.devicePointer;
+    };
+    dt.z = static_cast<uint8_t*>(dev_alias(z, 16));
+    dt.h = static_cast<uint8_t*>(dev_alias(h, 1));
+    dt.ct = static_cast<uint8_t*>(dev_alias(ctilde, 16));
+    dt.att = attempts ? static_cast<uint32_t*>(dev_alias(attempts, 4)) : nullptr;
+    dt.stream = k->cs_own;
+    return dt.z && dt.h && dt.ct && (!attempts || dt.att);
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- asynchronous pair: several batches in flight from ONE host thread (one batch per key handle) ----
+int dil_sign_batch_dev_begin(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* d_msgs, const uint64_t* d_offsets, size_t n,
+                             uint8_t* d_z, uint8_t* d_h, uint8_t* d_ctilde, uint32_t* d_attempts, void* stream) {
+    if (!e || !k) return DIL_ERR_ARG;
+    if (!d_msgs || !d_offsets || !d_z || !d_h || !d_ctilde || !d_attempts || n == 0 || n > 0x07FFFFFFu) return DIL_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_ctilde) & 7u) || (reinterpret_cast<uintptr_t>(d_z) & 15u)) return DIL_ERR_ARG;
+    std::lock_guard<std::mutex> g(k->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    const size_t chunk = k->tune.dev_chunk ? k->tune.dev_chunk : ((size_t)1 << 20);
+    if (n > chunk + chunk / 4 || k->profile)
+        return fail_msg(e, DIL_ERR_ARG, "dil_sign_batch_dev_begin: at most 1.25 x dev_chunk messages per asynchronous batch, profiling off");
+    return rounds_begin(e, k, d_msgs, d_offsets, n, d_z, d_h, d_ctilde, d_attempts, (cudaStream_t)stream, nullptr);
+}
+
+int dil_sign_batch_host_begin(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs, const uint64_t* offsets, size_t n,
+                              uint8_t* z, uint8_t* h, uint8_t* ctilde, uint32_t* attempts) {
+    if (!e || !k) return DIL_ERR_ARG;
+    if (!msgs || !offsets || !z || !h || !ctilde || n == 0 || n > 0x07FFFFFFu) return DIL_ERR_ARG;
+    if (!offsets_ok(offsets, n)) return DIL_ERR_ARG;
+    std::lock_guard<std::mutex> g(k->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    if (k->pend) return fail_msg(e, DIL_ERR_ARG, "sign: this key handle already has a batch in flight (dil_sign_batch_finish it first)");
+    const size_t CHUNK = k->tune.host_chunk ? k->tune.host_chunk : 262144;
+    if (n > CHUNK + CHUNK / 4 || k->profile)
+        return fail_msg(e, DIL_ERR_ARG, "dil_sign_batch_host_begin: at most 1.25 x host_chunk messages per asynchronous batch, profiling off");
+    int rc = host_stage(e, k, msgs, offsets, n);
+    if (rc) return rc;
+    DrainTarget dt;
+    if (!host_drain_target(k, z, h, ctilde, attempts, dt))
+        return fail_msg(e, DIL_ERR_ARG, "dil_sign_batch_host_begin: z, h, ctilde (and attempts) must be pinned host memory the device can "
+                                        "address (cudaHostAlloc / cudaHostRegister), z and ctilde 16-byte aligned");
+    CK(cudaEventCreateWithFlags(&dt.idle, cudaEventDisableTiming));
+    cudaError_t er = cudaEventRecord(dt.idle, dt.stream);
+    rc = er == cudaSuccess ? DIL_OK : fail(e, er, "sign drain event");
+    if (rc == DIL_OK) rc = rounds_begin(e, k, k->msgs_d, k->off_d, n, k->zp_d, k->h_d, k->ct_d, k->att_d, k->st_own, &dt);
+    if (rc != DIL_OK) {
+        cudaEventDestroy(dt.idle);
+        return rc;
+    }
+    static_cast<Pending*>(k->pend)->host = true;
+    return DIL_OK;
+}
+
+int dil_sign_batch_finish(dil_engine_t* e, dil_sign_key_t* k) {
+    if (!e || !k) return DIL_ERR_ARG;
+    std::lock_guard<std::mutex> g(k->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    Pending* p = static_cast<Pending*>(k->pend);
+    if (!p) return fail_msg(e, DIL_ERR_ARG, "sign: no batch in flight on this key handle");
+    const bool host = p->host, loaded = p->loaded;
+    const DrainTarget dt = p->drain;
+    int rc = rounds_finish(e, k, false);
+    if (host) {   // the last drains: every signature is in the caller's buffers when this returns
+        cudaError_t e1 = wait_stream(k, dt.stream, false);
+        (void)loaded;
+        cudaEventDestroy(dt.idle);
+        if (rc == DIL_OK && e1 != cudaSuccess) rc = fail(e, e1, "sign drain sync");
+    }
+    return rc;
+}
+
+int dil_sign_batch_host(dil_engine_t* e, dil_sign_key_t* k, const uint8_t* msgs, const uint64_t* offsets, size_t n,
+                        uint8_t* z, uint8_t* h, uint8_t* ctilde, uint32_t* attempts) {
+    if (!e || !k) return DIL_ERR_ARG;
+    if (n == 0) return DIL_OK;
+    if (!msgs || !offsets || !z || !h || !ctilde || n > 0x07FFFFFFu) return DIL_ERR_ARG;
+    if (!offsets_ok(offsets, n)) return DIL_ERR_ARG;
+    std::lock_guard<std::mutex> g(k->mu);
+    DeviceGuard dg(e->device);
+    if (!dg.ok) return DIL_ERR_CUDA;
+    if (k->pend) return fail_msg(e, DIL_ERR_ARG, "sign: this key handle already has a batch in flight (dil_sign_batch_finish it first)");
+    const LevelParams& P = k->P;
+    int rcs = host_stage(e, k, msgs, offsets, n);
+    if (rcs) return rcs;
+    cudaStream_t st = k->st_own, cs = k->cs_own;
+    const size_t zb = (size_t)P.l * P.z_bytes, hb = (size_t)P.omega + P.k;
     {
-        const bool want = !k->tune.host_copy_path;
         const size_t CHUNK = k->tune.host_chunk ? k->tune.host_chunk : 262144;
         DrainTarget dt;
-        auto dev_alias = [&](const void* p, size_t align) -> void* {
-            cudaPointerAttributes a{};
-            if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-            if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
-            if (reinterpret_cast<uintptr_t>(a.devicePointer) & (align - 1)) return nullptr;
-            return a.devicePointer;
-        };
-        dt.z = static_cast<uint8_t*>(dev_alias(z, 16));
-        dt.h = static_cast<uint8_t*>(dev_alias(h, 1));
-        dt.ct = static_cast<uint8_t*>(dev_alias(ctilde, 16));
-        dt.att = attempts ? static_cast<uint32_t*>(dev_alias(attempts, 4)) : nullptr;
-        if (want && dt.z && dt.h && dt.ct && (!attempts || dt.att)) {
-            dt.stream = cs;
+        if (host_drain_target(k, z, h, ctilde, attempts, dt)) {
             CK(cudaEventCreateWithFlags(&dt.idle, cudaEventDisableTiming));
             cudaError_t er = cudaEventRecord(dt.idle, cs);
             int rc = er == cudaSuccess ? DIL_OK : fail(e, er, "sign drain event");

@@ -420,6 +420,35 @@ class SignKey:
         self.engine._check(rc, "dil_sign_batch_dev")
 
 
+def _sign_dev_begin(self, d_msgs, d_offsets, n, d_z, d_h, d_c, d_att):
+    """Asynchronous device-resident signing (dil_sign_batch_dev_begin): enqueues the batch on torch's current stream and returns;
+    finish() completes it.  One batch per key handle at a time."""
+    rc = self.engine._lib.dil_sign_batch_dev_begin(self.engine._h, self._h, ctypes.c_void_p(d_msgs.data_ptr()),
+                                                   ctypes.c_void_p(d_offsets.data_ptr()), n, ctypes.c_void_p(d_z.data_ptr()),
+                                                   ctypes.c_void_p(d_h.data_ptr()), ctypes.c_void_p(d_c.data_ptr()),
+                                                   ctypes.c_void_p(d_att.data_ptr()), self.engine._stream())
+    self.engine._check(rc, "dil_sign_batch_dev_begin")
+
+
+def _sign_host_begin(self, msgs_t, offsets_t, n, z_t, h_t, c_t, att_t):
+    """Asynchronous host-pointer signing (dil_sign_batch_host_begin): pinned torch tensors (or anything with data_ptr()) for the
+    messages, offsets and outputs; they must stay alive until finish()."""
+    P = ctypes.c_void_p
+    rc = self.engine._lib.dil_sign_batch_host_begin(self.engine._h, self._h, P(msgs_t.data_ptr()), P(offsets_t.data_ptr()), n,
+                                                    P(z_t.data_ptr()), P(h_t.data_ptr()), P(c_t.data_ptr()), P(att_t.data_ptr()))
+    self.engine._check(rc, "dil_sign_batch_host_begin")
+
+
+def _sign_finish(self):
+    """Complete the batch begun with sign_dev_begin / sign_host_begin (dil_sign_batch_finish)."""
+    self.engine._check(self.engine._lib.dil_sign_batch_finish(self.engine._h, self._h), "dil_sign_batch_finish")
+
+
+SignKey.sign_dev_begin = _sign_dev_begin
+SignKey.sign_host_begin = _sign_host_begin
+SignKey.finish = _sign_finish
+
+
 class VerifyKey:
     """Expanded public key on the device (rho, t1 as in the KAT files / tb_verify_top.v:144-240)."""
 

@@ -135,8 +135,9 @@ int dil_sign_key_create(dil_engine_t *e, dil_sign_key_t **out, int level, const 
 int dil_sign_key_destroy(dil_engine_t *e, dil_sign_key_t *k);
 /* Streaming use: a key handle signs one batch at a time (calls on one handle serialise).  To keep several batches in
  * flight on one GPU - the next batch signs while the small last rejection rounds of the previous one leave SMs idle -
- * create two to four handles of the same key and call from one host thread per handle (dil_sign_batch_host uses streams
- * owned by the handle; dil_sign_batch_dev the stream it is given).  Measured on one B200, Dilithium-2, 65 536-message
+ * create two to four handles of the same key and either call from one host thread per handle (dil_sign_batch_host uses streams
+ * owned by the handle; dil_sign_batch_dev the stream it is given) or drive them all from one thread with the asynchronous
+ * *_begin / dil_sign_batch_finish pair below.  Measured on one B200, Dilithium-2, 65 536-message
  * batches: 12.1 M signs/s with one batch at a time, 13.9 M with two and 14.6 M with four in flight.
  * host pointers.  When z, h, ctilde (and attempts, if given) are all pinned host memory the device can address
  * (cudaHostAlloc / cudaHostRegister; z and ctilde 16-byte aligned), finished signatures are streamed into them
@@ -148,6 +149,18 @@ int dil_sign_batch_host(dil_engine_t *e, dil_sign_key_t *k, const uint8_t *msgs,
  * expected number of rounds at once and synchronises the stream once at the end (again only if items are still active). */
 int dil_sign_batch_dev(dil_engine_t *e, dil_sign_key_t *k, const uint8_t *d_msgs, const uint64_t *d_offsets, size_t n,
                        uint8_t *d_z, uint8_t *d_h, uint8_t *d_ctilde, uint32_t *d_attempts, void *stream);
+/* Asynchronous pair: several batches in flight from ONE host thread.  *_begin enqueues the batch (the rejection loop runs on the
+ * device) and returns at once; dil_sign_batch_finish waits for it, enqueues further rounds if messages are still unsigned, and
+ * returns the batch's status - only then are the outputs complete.  A key handle carries one batch at a time (a second *_begin,
+ * a synchronous call or dil_sign_key_set_tuning on a busy handle returns DIL_ERR_ARG); use one handle of the same key per batch in
+ * flight.  Limits: at most 1.25 x dev_chunk (2^20) messages for _dev_begin and 1.25 x host_chunk (2^18) for _host_begin; _host_begin
+ * needs pinned, device-addressable output buffers (the streaming path) and msgs / offsets must stay valid until the finish.
+ * dil_sign_batch_dev / _host are exactly begin + finish for batches within those limits. */
+int dil_sign_batch_dev_begin(dil_engine_t *e, dil_sign_key_t *k, const uint8_t *d_msgs, const uint64_t *d_offsets, size_t n,
+                             uint8_t *d_z, uint8_t *d_h, uint8_t *d_ctilde, uint32_t *d_attempts, void *stream);
+int dil_sign_batch_host_begin(dil_engine_t *e, dil_sign_key_t *k, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                              uint8_t *z, uint8_t *h, uint8_t *ctilde, uint32_t *attempts);
+int dil_sign_batch_finish(dil_engine_t *e, dil_sign_key_t *k);
 uint32_t dil_sign_last_rounds(const dil_sign_key_t *k);   /* rejection rounds of the last batch */
 uint64_t dil_sign_last_slots(const dil_sign_key_t *k);    /* signing attempts (slots) the last batch executed, speculative ones included */
 /* Per-key tuning of the batch scheduler; zero fields keep the defaults.  Results never depend on these. */

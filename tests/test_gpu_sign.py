@@ -227,3 +227,61 @@ def test_sign_batches_in_flight(eng, oracle):
     assert lone_rounds >= 1
     for k in keys:
         k.close()
+
+
+def test_sign_async_begin_finish(eng, oracle):
+    """dil_sign_batch_{dev,host}_begin + dil_sign_batch_finish: one host thread keeps a batch in flight on each of three key
+    handles (different messages each), several times over; results equal the synchronous calls bit for bit, a busy handle
+    refuses a second batch, and a begun batch that is never finished is completed by dil_sign_key_destroy."""
+    import torch
+    import dilithium_b200 as d
+    level, n, T = 3, 2500, 3
+    K = ol.kat(level)
+    parts = [K[f][9] for f in ("rho", "k", "tr", "s1", "s2", "t0")]
+    keys = [d.SignKey(eng, level, *parts) for _ in range(T)]
+    batches = [[(t * n + i).to_bytes(4, "little") * (1 + (i + 2 * t) % 6) for i in range(n)] for t in range(T)]
+    ref = [[np.array(a) for a in keys[0].sign(b)] for b in batches]
+    zo, ho, co, a = oracle.sign(level, *parts, batches[2][17])
+    assert np.array_equal(ref[2][0][17], zo) and np.array_equal(ref[2][1][17], ho) and np.array_equal(ref[2][2][17], co) and ref[2][3][17] == a
+    dev_in, dev_out, host_in, host_out = [], [], [], []
+    for t in range(T):
+        blob = np.frombuffer(b"".join(batches[t]), dtype=np.uint8).copy()
+        off = np.zeros(n + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(m) for m in batches[t]])
+        host_in.append((torch.from_numpy(blob).pin_memory(), torch.from_numpy(off).pin_memory()))
+        dev_in.append((host_in[t][0].cuda(), host_in[t][1].cuda()))
+        shapes = ((n, keys[t].z_bytes), (n, keys[t].h_bytes), (n, 32))
+        dev_out.append([torch.zeros(s, dtype=torch.uint8, device="cuda") for s in shapes] + [torch.zeros(n, dtype=torch.int32, device="cuda")])
+        host_out.append([torch.zeros(s, dtype=torch.uint8).pin_memory() for s in shapes] + [torch.zeros(n, dtype=torch.int32).pin_memory()])
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(T)]
+    for rep in range(3):                    # device path: begin all, then finish all, from this one thread
+        for t in range(T):
+            with torch.cuda.stream(streams[t]):
+                keys[t].sign_dev_begin(dev_in[t][0], dev_in[t][1], n, *dev_out[t])
+        with pytest.raises(RuntimeError):   # a busy handle refuses a second batch
+            keys[0].sign_dev(dev_in[0][0], dev_in[0][1], n, *dev_out[0])
+        for t in range(T):
+            keys[t].finish()
+    for t in range(T):
+        for name, r, g in zip(("z", "h", "c", "att"), ref[t], dev_out[t]):
+            assert np.array_equal(r, g.cpu().numpy()), (t, name, "async device path")
+    for rep in range(3):                    # host path: pinned messages in, signatures streamed into pinned buffers
+        for t in range(T):
+            keys[t].sign_host_begin(host_in[t][0], host_in[t][1], n, *host_out[t])
+        for t in reversed(range(T)):
+            keys[t].finish()
+    for t in range(T):
+        for name, r, g in zip(("z", "h", "c", "att"), ref[t], host_out[t]):
+            assert np.array_equal(r, g.numpy()), (t, name, "async host path")
+    with pytest.raises(RuntimeError):       # nothing in flight
+        keys[1].finish()
+    pageable = [torch.zeros((n, keys[0].z_bytes), dtype=torch.uint8), torch.zeros((n, keys[0].h_bytes), dtype=torch.uint8),
+                torch.zeros((n, 32), dtype=torch.uint8), torch.zeros(n, dtype=torch.int32)]
+    with pytest.raises(RuntimeError):       # the asynchronous host path needs pinned outputs
+        keys[1].sign_host_begin(host_in[1][0], host_in[1][1], n, *pageable)
+    keys[2].sign_dev_begin(dev_in[2][0], dev_in[2][1], n, *dev_out[2])   # never finished: destroy completes it
+    for k in keys:
+        k.close()
+    torch.cuda.synchronize()
+    assert np.array_equal(ref[2][0], dev_out[2][0].cpu().numpy())
