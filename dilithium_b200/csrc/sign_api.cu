@@ -420,12 +420,7 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
     }
 #define PROF_BEGIN(cls) do { if (prof) CK(cudaEventRecord(k->ev[2 * (cls)], st)); } while (0)
 #define PROF_END(cls) do { if (prof) CK(cudaEventRecord(k->ev[2 * (cls) + 1], st)); } while (0)
-    dil::SignBufs b{};
-    b.ctl = k->ctl; b.active[0] = k->active[0]; b.active[1] = k->active[1]; b.done_list = k->done_list;
-    b.mu = k->mu_d; b.rhop = k->rhop; b.kappa = k->kappa; b.y = k->y; b.w = k->w; b.w1p = k->w1p; b.c = k->c;
-    b.ct_slot = k->ct_slot; b.h_slot = k->h_slot; b.accepted = k->accepted;
-    b.zp = d_zp; b.h_out = d_h; b.ct_out = reinterpret_cast<uint64_t*>(d_ct); b.attempts = d_att;
-    b.track_done = drain != nullptr;
+    const dil::SignBufs b = sign_bufs(k, d_zp, d_h, d_ct, d_att, drain != nullptr);
     InFlight load(e->sign_in_flight);
     const Spec sp = spec_for(k, load.seen);
     const uint32_t cap_slots = (uint32_t)slots_for(sp, n);
@@ -442,10 +437,10 @@ int sign_rounds(dil_engine* e, dil_sign_key* k, const uint8_t* d_msgs, const uin
         k->prof_ms[0] += ms;
         k->prof_slots[0] += n;
     }
-    // Rounds are enqueued in bursts without waiting for their outcome; a round that finds no active items costs
-    // a handful of empty launches.  The host reads the round state (posted write into mapped memory) once per burst.
-    // Grid sizes are hints (every kernel strides or claims work dynamically, so any grid is correct): the expected
-    // number of active items plus a margin, never more than the last count the host has seen.
+    // This variant observes EVERY round (profiling reads its events, the one-key-per-signature core sizes its stand-alone
+    // kernels on the host); the ordinary batch (rounds_begin / rounds_finish above) enqueues its rounds in bursts without
+    // waiting for their outcome.  Grid sizes are hints (every kernel strides or claims work dynamically, so any grid is
+    // correct): the expected number of active items plus a margin, never more than the last count the host has seen.
     const std::vector<double> traj = expected_trajectory(k, sp, n);
     const uint32_t T = sp.target, M = sp.max;
     uint32_t enq = 0, seen = (uint32_t)n, seen_at = 0;   // last observed item count and the round it belongs to
