@@ -1650,18 +1650,58 @@ __global__ void __launch_bounds__(256) s_pack_kernel(uint8_t* __restrict__ sp, c
     for (int i = 0; i < W; i++) d[i] = (uint8_t)(o >> (8 * i));
 }
 
-// tr = SHAKE256(rho || t1_packed)[0:32] per item
+// tr = SHAKE256(rho || t1_packed)[0:32] per item: one Keccak state per thread, but the 1312 / 1952 / 2592 input bytes of the
+// warp's 32 items are fetched COOPERATIVELY, one 136-byte rate block of every item at a time (contiguous 136-byte runs,
+// 8-byte loads) into a shared-memory tile from which each thread absorbs its own row.  (Every thread walking its own
+// record with private loads ran at 44 % of the hash rate: 1.42 ms per 131 072 level-5 keys.)  Needs 8-byte aligned
+// inputs and t1_bytes % 8 == 0 (true for the packed t1 of every level); otherwise the per-thread path below is used.
+constexpr int TR_ROW = 18;   // 64-bit words per staged row (17 rate lanes + 1: skews the banks)
 __global__ void __launch_bounds__(128) tr_batch_kernel(uint8_t* __restrict__ tr, const uint8_t* __restrict__ rho,
                                                        const uint8_t* __restrict__ t1p, uint32_t t1_bytes, uint32_t n) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const uint8_t* r = rho + (size_t)t * 32;
-    const uint8_t* p = t1p + (size_t)t * t1_bytes;
+    __shared__ uint64_t tile[4 * 32 * TR_ROW];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t wbase = (blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+    if (wbase >= n) return;
+    const uint32_t t = wbase + lane;
+    const bool coop = (((reinterpret_cast<uintptr_t>(rho) | reinterpret_cast<uintptr_t>(t1p)) & 7u) == 0) && (t1_bytes % 8u == 0);   // uniform
     uint64_t A[25];
-    shake256_absorb_lanes(A, 32 + t1_bytes, [&](size_t idx) -> uint64_t {
-        if (idx < 4) return load_lane_bytes(r, idx * 8, 32);
-        return load_lane_bytes(p, (idx - 4) * 8, t1_bytes);
-    });
+    if (coop) {
+        uint64_t* wt = tile + warp * 32 * TR_ROW;
+        const uint32_t total = 32 + t1_bytes, nfull = total / 136, rem_lanes = (total - nfull * 136) / 8;
+#pragma unroll
+        for (int i = 0; i < 25; i++) A[i] = 0;
+        for (uint32_t blk = 0; blk <= nfull; blk++) {
+            const uint32_t lanes_here = blk < nfull ? 17u : rem_lanes;
+            // stream word s of an item: words 0..3 are rho, the rest t1
+            for (uint32_t idx = lane; idx < 32 * lanes_here; idx += 32) {
+                const uint32_t row = idx / lanes_here, w = idx % lanes_here, sw = blk * 17 + w;
+                const uint32_t item = wbase + row < n ? wbase + row : n - 1;
+                wt[row * TR_ROW + w] = sw < 4 ? reinterpret_cast<const uint64_t*>(rho)[(size_t)item * 4 + sw]
+                                              : reinterpret_cast<const uint64_t*>(t1p + (size_t)item * t1_bytes)[sw - 4];
+            }
+            __syncwarp();
+            const uint64_t* my = wt + lane * TR_ROW;
+#pragma unroll
+            for (int i = 0; i < 17; i++)
+                if ((uint32_t)i < lanes_here) A[i] ^= my[i];
+            if (blk == nfull) {
+#pragma unroll
+                for (int i = 0; i < 17; i++)
+                    if ((uint32_t)i == rem_lanes) A[i] ^= 0x1FULL;
+                A[16] ^= 0x80ULL << 56;
+            }
+            keccak_f1600(A);
+            __syncwarp();
+        }
+    } else if (t < n) {
+        const uint8_t* r = rho + (size_t)t * 32;
+        const uint8_t* p = t1p + (size_t)t * t1_bytes;
+        shake256_absorb_lanes(A, 32 + t1_bytes, [&](size_t idx) -> uint64_t {
+            if (idx < 4) return load_lane_bytes(r, idx * 8, 32);
+            return load_lane_bytes(p, (idx - 4) * 8, t1_bytes);
+        });
+    }
+    if (t >= n) return;
     uint64_t* o = reinterpret_cast<uint64_t*>(tr) + (size_t)t * 4;
 #pragma unroll
     for (int i = 0; i < 4; i++) o[i] = A[i];
