@@ -13,9 +13,9 @@ for stem in ("rho", "k", "tr", "s1", "s2", "t0"):
     open(f"/tmp/kat/{stem}_2.txt", "w").write(K[stem][0].tobytes().hex().upper() + "\n")
 PY
 # one process, dil_pool_* over g GPUs, 1 / 2 / 4 batches in flight
-for g in 1 2 4 8; do
+for g in ${POOL_GPUS:-1 2 4 8}; do
   [ $g -le $G ] || continue
-  for t in 1 2 4; do examples/pool_sign /tmp/kat 2 65536 8 $g $t; done
+  for t in ${POOL_IN_FLIGHT:-1 2 4}; do examples/pool_sign /tmp/kat 2 65536 8 $g $t; done
 done > gpurun_out/${tag}_pool_sign.jsonl 2>&1
 cat gpurun_out/${tag}_pool_sign.jsonl
 # one process per GPU (the driver's launch line)
