@@ -143,6 +143,8 @@ __global__ void __launch_bounds__(128) expand_mask_kernel(int32_t* __restrict__ 
     }
     __syncwarp();   // staging area is reused by the next chunk
     }
+    // the masks are secret (y together with z reveals s1): nothing of them stays behind in shared memory
+    for (int i = lane; i < 32 * ROW / 16; i += 32) reinterpret_cast<uint4*>(stage)[i] = make_uint4(0, 0, 0, 0);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1586,6 +1588,10 @@ __global__ void __launch_bounds__(128) eta_sample_kernel(int32_t* __restrict__ s
         dst[0] = make_int4((int8_t)(b.x), (int8_t)(b.x >> 8), (int8_t)(b.x >> 16), (int8_t)(b.x >> 24));
         dst[1] = make_int4((int8_t)(b.y), (int8_t)(b.y >> 8), (int8_t)(b.y >> 16), (int8_t)(b.y >> 24));
     }
+    __syncwarp();
+    // s1 / s2 are secret: nothing of them stays behind in shared memory
+#pragma unroll
+    for (int i = 0; i < ETA_ROW / 16; i++) reinterpret_cast<uint4*>(row)[i] = make_uint4(0, 0, 0, 0);
 }
 
 // t = t + s2 (canonical); Power2Round (uncenter_coeff.v:54-55); pack t1 (10 bit) and 2^12 - t0 (13 bit).
