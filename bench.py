@@ -863,6 +863,13 @@ def run_engine(args):
                          "avg_launch_ms": dom_ms / prof_rounds, "peak_source": peak_src,
                          "ncu_limiter": ncu_limiter(dominant),
                          "compute_roofline": keccak_roofline(dominant, level, dom_units, dom_ms, keccak_peak / 1e9, keccak_src)},
+            "roofline_step": {"what": "all kernel classes of the timed steps together: algorithmic HBM bytes per attempt slot x slots per step / step time",
+                              "algorithmic_bytes_per_slot": sum(cb[n] for n in ("expand_mask", "signcore", "challenge", "tail")),
+                              "slots_per_step": slots, "ms_per_step": ms_step,
+                              "achieved": sum(cb[n] for n in ("expand_mask", "signcore", "challenge", "tail")) * slots / (ms_step * 1e-3) / 1e9,
+                              "peak": peak, "unit": "GB/s",
+                              "frac": sum(cb[n] for n in ("expand_mask", "signcore", "challenge", "tail")) * slots / (ms_step * 1e-3) / 1e9 / peak,
+                              "note": "the step is bound by the integer ALU pipe (Keccak) and the multiplier pipe (transforms), not by HBM (DESIGN.md 8)"},
             "keccak_peak": {"measured_g_per_s": keccak_peak / 1e9, "source": keccak_src, "sass_mix_per_round": kmix, "sm_mhz_during": kclock,
                             "alu_pipe_model_g_per_s": keccak_model / 1e9 if keccak_model else None,
                             "alu_pipe_model": "sm_count x 4 sub-partitions x clock / 2 cycles per ALU warp instruction x 32 threads / "

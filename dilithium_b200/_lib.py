@@ -77,6 +77,8 @@ SIGNATURES = {
     "dil_pool_sign_key_create": (c_int, [c_void, ctypes.POINTER(c_void), c_int, c_void, c_void, c_void, c_void, c_void, c_void]),
     "dil_pool_sign_key_destroy": (c_int, [c_void, c_void]),
     "dil_pool_sign_batch_host": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void]),
+    "dil_pool_sign_batch_host_begin": (c_int, [c_void, c_void, c_void, c_void, c_size, c_void, c_void, c_void, c_void]),
+    "dil_pool_sign_batch_finish": (c_int, [c_void, c_void]),
     "dil_diag_item_rows_threshold": (c_int, [c_size]),
     "dil_diag_keccak_dev": (c_int, [c_void, c_void, c_uint, c_uint, c_void]),
     "dil_invntt_tomont_dev": (c_int, [c_void, c_void, c_void, c_size, c_void]),

@@ -21,6 +21,10 @@ struct dil_pool {
 struct dil_pool_sign_key {
     int level = 0;
     std::vector<dil_sign_key_t*> keys;   // one expanded key per engine
+    // the batch between dil_pool_sign_batch_host_begin and dil_pool_sign_batch_finish: which engines carry a shard, and the
+    // shards' rebased offset arrays (they must outlive the asynchronous H2D copies)
+    std::vector<char> busy;
+    std::vector<std::vector<uint64_t>> offs;
 };
 
 namespace {
@@ -94,6 +98,63 @@ int dil_pool_sign_key_destroy(dil_pool_t* p, dil_pool_sign_key_t* k) {
     for (size_t i = 0; i < k->keys.size(); i++) dil_sign_key_destroy(p && i < p->engines.size() ? p->engines[i] : nullptr, k->keys[i]);
     delete k;
     return DIL_OK;
+}
+
+// Asynchronous pair over the pool: every engine begins its shard (dil_sign_batch_host_begin; the enqueueing runs on one short-lived
+// host thread per engine so that the GPUs start together), the call returns, and dil_pool_sign_batch_finish completes all shards.
+// One batch per pool key at a time; use one pool key per batch in flight.  Same limits as dil_sign_batch_host_begin per shard
+// (pinned, device-addressable output buffers; at most 1.25 x host_chunk messages per GPU).
+int dil_pool_sign_batch_host_begin(dil_pool_t* p, dil_pool_sign_key_t* k, const uint8_t* msgs, const uint64_t* offsets, size_t n,
+                                   uint8_t* z, uint8_t* h, uint8_t* ctilde, uint32_t* attempts) {
+    if (!p || !k || k->keys.size() != p->engines.size()) return DIL_ERR_ARG;
+    if (!msgs || !offsets || !z || !h || !ctilde || n == 0) return DIL_ERR_ARG;
+    for (char b : k->busy)
+        if (b) return DIL_ERR_ARG;   // a batch is already in flight on this pool key
+    size_t zb = 0, hb = 0;
+    if (dil_sign_sizes(k->level, &zb, &hb) != DIL_OK) return DIL_ERR_ARG;
+    const size_t G = p->engines.size();
+    if (offsets[0] != 0) return DIL_ERR_ARG;
+    for (size_t i = 0; i < n; i++)
+        if (offsets[i + 1] < offsets[i]) return DIL_ERR_ARG;
+    k->busy.assign(G, 0);
+    k->offs.assign(G, {});
+    for (size_t g = 0; g < G; g++) {
+        size_t lo, hi;
+        shard(n, G, g, &lo, &hi);
+        if (hi == lo) continue;
+        k->offs[g].resize(hi - lo + 1);
+        for (size_t i = lo; i <= hi; i++) k->offs[g][i - lo] = offsets[i] - offsets[lo];
+    }
+    std::vector<int> rcs(G, DIL_OK);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; g++) {
+        size_t lo, hi;
+        shard(n, G, g, &lo, &hi);
+        if (hi == lo) continue;
+        th.emplace_back([=, &rcs] {
+            rcs[g] = dil_sign_batch_host_begin(p->engines[g], k->keys[g], msgs + offsets[lo], k->offs[g].data(), hi - lo, z + lo * zb,
+                                               h + lo * hb, ctilde + lo * 32, attempts ? attempts + lo : nullptr);
+            k->busy[g] = rcs[g] == DIL_OK;
+        });
+    }
+    for (auto& t : th) t.join();
+    int rc = DIL_OK;
+    for (int r : rcs)
+        if (r != DIL_OK) rc = r;
+    if (rc != DIL_OK) dil_pool_sign_batch_finish(p, k);   // let the shards that did start run out
+    return rc;
+}
+
+int dil_pool_sign_batch_finish(dil_pool_t* p, dil_pool_sign_key_t* k) {
+    if (!p || !k || k->keys.size() != p->engines.size()) return DIL_ERR_ARG;
+    int rc = DIL_OK;
+    for (size_t g = 0; g < k->busy.size(); g++) {
+        if (!k->busy[g]) continue;
+        const int r = dil_sign_batch_finish(p->engines[g], k->keys[g]);
+        if (r != DIL_OK) rc = r;
+        k->busy[g] = 0;
+    }
+    return rc;
 }
 
 int dil_pool_sign_batch_host(dil_pool_t* p, dil_pool_sign_key_t* k, const uint8_t* msgs, const uint64_t* offsets, size_t n,

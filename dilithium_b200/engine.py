@@ -539,6 +539,18 @@ class Pool:
         if rc != 0:
             raise DilithiumError(f"dil_pool_sign_batch_host failed: {self._lib.dil_status_string(rc).decode()}")
 
+    def sign_into_begin(self, msgs_ptr, offsets_ptr, n, z_ptr, h_ptr, c_ptr, att_ptr):
+        """Asynchronous form (dil_pool_sign_batch_host_begin): pinned portable output buffers; finish() completes the batch."""
+        P = ctypes.c_void_p
+        rc = self._lib.dil_pool_sign_batch_host_begin(self._h, self._key, P(msgs_ptr), P(offsets_ptr), n, P(z_ptr), P(h_ptr), P(c_ptr), P(att_ptr))
+        if rc != 0:
+            raise DilithiumError(f"dil_pool_sign_batch_host_begin failed: {self._lib.dil_status_string(rc).decode()}")
+
+    def finish(self):
+        rc = self._lib.dil_pool_sign_batch_finish(self._h, self._key)
+        if rc != 0:
+            raise DilithiumError(f"dil_pool_sign_batch_finish failed: {self._lib.dil_status_string(rc).decode()}")
+
     def sign(self, msgs):
         n = len(msgs)
         k, l = LEVEL_DIMS[self.level]

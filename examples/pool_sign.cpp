@@ -4,8 +4,9 @@
 // reference's KAT files) from pinned host memory into pinned host memory, checks that the pool's signatures equal the
 // ones a single engine produces for a sample shard, and prints one JSON line with the end-to-end rate.
 //
-// `in_flight` batches are signed at the same time (one pool key, one set of output buffers and one host thread per batch in
-// flight): the next batch signs while the last rejection rounds of the previous one leave SMs idle and its last signatures drain.
+// `in_flight` batches are signed at the same time (one pool key and one set of output buffers per batch in flight, all driven by
+// this one thread through dil_pool_sign_batch_host_begin / dil_pool_sign_batch_finish): the next batch signs while the last
+// rejection rounds of the previous one leave SMs idle and its last signatures drain.
 //
 //   usage: pool_sign <KAT dir> [level=2] [n_per_gpu=65536] [steps=5] [gpus=all] [in_flight=2]
 #include <cuda_runtime.h>
@@ -17,7 +18,6 @@
 #include <cstring>
 #include <fstream>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "dilithium_b200.h"
@@ -87,19 +87,19 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i <= n; i++) off[i] = i * mlen;
     for (int t = 0; t < T; t++)   // warm-up (workspaces, kernel attributes)
         CK(dil_pool_sign_batch_host(pool, pks[t], msgs, off, n, zs[t], hs[t], cts[t], atts[t]));
-    std::vector<int> rcs(T, DIL_OK);
+    // ONE host thread keeps T batches in flight: step s is begun on pool key s mod T as soon as that key's previous batch is finished
     auto t0c = std::chrono::steady_clock::now();
-    {
-        std::vector<std::thread> th;
-        for (int t = 0; t < T; t++)
-            th.emplace_back([&, t] {
-                for (int s = t; s < steps && rcs[t] == DIL_OK; s += T)
-                    rcs[t] = dil_pool_sign_batch_host(pool, pks[t], msgs, off, n, zs[t], hs[t], cts[t], atts[t]);
-            });
-        for (auto& w : th) w.join();
+    if (T == 1) {
+        for (int s = 0; s < steps; s++) CK(dil_pool_sign_batch_host(pool, pks[0], msgs, off, n, zs[0], hs[0], cts[0], atts[0]));
+    } else {
+        for (int s = 0; s < steps; s++) {
+            const int t = s % T;
+            if (s >= T) CK(dil_pool_sign_batch_finish(pool, pks[t]));
+            CK(dil_pool_sign_batch_host_begin(pool, pks[t], msgs, off, n, zs[t], hs[t], cts[t], atts[t]));
+        }
+        for (int s = steps > T ? steps - T : 0; s < steps; s++) CK(dil_pool_sign_batch_finish(pool, pks[s % T]));
     }
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0c).count();
-    for (int t = 0; t < T; t++) CK(rcs[t]);
     bool sets_equal = true;
     for (int t = 1; t < T && t < steps; t++)
         sets_equal = sets_equal && !std::memcmp(zs[t], z, n * zb) && !std::memcmp(hs[t], h, n * hb) && !std::memcmp(cts[t], ct, n * 32);

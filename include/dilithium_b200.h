@@ -239,6 +239,11 @@ int dil_pool_sign_key_create(dil_pool_t *p, dil_pool_sign_key_t **out, int level
 int dil_pool_sign_key_destroy(dil_pool_t *p, dil_pool_sign_key_t *k);
 int dil_pool_sign_batch_host(dil_pool_t *p, dil_pool_sign_key_t *k, const uint8_t *msgs, const uint64_t *offsets, size_t n,
                              uint8_t *z, uint8_t *h, uint8_t *ctilde, uint32_t *attempts);
+/* asynchronous pair over the pool: every engine begins its shard, dil_pool_sign_batch_finish completes them all (one batch per
+   pool key at a time; same limits per shard as dil_sign_batch_host_begin: pinned device-addressable outputs, <= 1.25 x 2^18 per GPU) */
+int dil_pool_sign_batch_host_begin(dil_pool_t *p, dil_pool_sign_key_t *k, const uint8_t *msgs, const uint64_t *offsets, size_t n,
+                                   uint8_t *z, uint8_t *h, uint8_t *ctilde, uint32_t *attempts);
+int dil_pool_sign_batch_finish(dil_pool_t *p, dil_pool_sign_key_t *k);
 
 /* ---- diagnostics ----
  * Pure Keccak-f[1600] rate of the device: sm_count * ctas_per_sm CTAs of 128 threads, every thread runs perms_per_thread

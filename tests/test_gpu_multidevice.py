@@ -70,6 +70,15 @@ def test_pool_signs_like_one_engine(oracle):
         pool.sign_into(blob.ctypes.data, off.ctypes.data, n, zt.data_ptr(), ht.data_ptr(), ct.data_ptr(), at.data_ptr())
         assert np.array_equal(zt.numpy(), ref[0]) and np.array_equal(ht.numpy(), ref[1]) and np.array_equal(ct.numpy(), ref[2])
         assert np.array_equal(at.numpy().view(np.uint32), ref[3])
+        # the asynchronous pair over the pool (dil_pool_sign_batch_host_begin / dil_pool_sign_batch_finish), twice over
+        for _ in range(2):
+            zt.zero_(); ht.zero_(); ct.zero_(); at.zero_()
+            pool.sign_into_begin(blob.ctypes.data, off.ctypes.data, n, zt.data_ptr(), ht.data_ptr(), ct.data_ptr(), at.data_ptr())
+            with pytest.raises(RuntimeError):   # one batch per pool key at a time
+                pool.sign_into_begin(blob.ctypes.data, off.ctypes.data, n, zt.data_ptr(), ht.data_ptr(), ct.data_ptr(), at.data_ptr())
+            pool.finish()
+            assert np.array_equal(zt.numpy(), ref[0]) and np.array_equal(ht.numpy(), ref[1]) and np.array_equal(ct.numpy(), ref[2])
+            assert np.array_equal(at.numpy().view(np.uint32), ref[3])
         pool.close()
     for m in (0, 2501, n - 1):
         zo, ho, co, a = oracle.sign(level, *kk, msgs[m])
