@@ -16,15 +16,18 @@ arithmetic inside is the engine's hot path; the stand-alone NTT kernel and the f
 Multi-GPU: one process per GPU (torchrun), every rank signs its own 65 536-message shard (weak
 scaling); the only collective is ONE NCCL broadcast of the key material from rank 0.
 
-`value`    signs/s over all GPUs, messages already resident in HBM, CUDA-event timed, max over ranks.
-`e2e`      the same through dil_sign_batch_host: pinned host messages in, signatures back on the host
-           (finished signatures are drained to the host round by round while later rounds still sign);
-           `e2e.host_ceiling` relates it to the measured host-memory ceiling of the box (profiles/).
+`value`    signs/s over all GPUs for K steps, every step one 65 536-message batch per GPU with its messages resident in HBM,
+           T = 4 batches in flight per GPU (one key handle and stream per batch in flight, driven by ONE host thread through
+           dil_sign_batch_dev_begin / dil_sign_batch_finish; all K steps start and finish between the two CUDA events), max
+           over ranks.  `one_batch_at_a_time` is the same K steps strictly serial (--in-flight 1 makes it the headline).
+`e2e`      the same through dil_sign_batch_host[_begin]: pinned host messages in, signatures back on the host
+           (finished signatures are drained to the host round by round while later rounds still sign), T batches in flight,
+           `e2e.one_call_at_a_time` next to it; `e2e.host_ceiling` relates it to the measured host-memory ceiling of the box.
 `roofline` the kernel class with the largest share of the step's device time (CUDA events around every
            launch in a separate profiled step): HBM fraction from algorithmic bytes as the contract asks,
            plus `compute_roofline`: Keccak-f/s against the pure-Keccak rate MEASURED IN THIS RUN
            (dil_diag_keccak_dev) because that class is bound by the integer ALU pipe, not by HBM.
-`configs`  the other BASELINE configurations under the same clock: cfg3 (Dilithium-3, 262 144 items: fused
+`configs`  key generation (row N4) and the other BASELINE configurations under the same clock: cfg3 (Dilithium-3, 262 144 items: fused
            ExpandA core with shared and per-item rho, full signing), cfg4 (Dilithium-5 verification, one GPU's
            131 072-signature shard, a key per signature, 100 KAT tuples injected and asserted), cfg5 (batch sweep
            2^10 .. 2^22 x levels 2/3/5, sharded over the ranks).  --no-configs skips them.
