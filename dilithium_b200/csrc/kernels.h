@@ -106,13 +106,15 @@ cudaError_t launch_drain(uint8_t* hz, uint8_t* hh, uint8_t* hct, uint32_t* hatt,
                          uint32_t hb, cudaStream_t st);
 cudaError_t launch_publish_ctl(uint32_t* host_dst_dev, const RoundCtl* ctl, cudaStream_t st);
 // ---- verify pipeline ----
+// w1p / hmask non-null: the core applies the hints itself and emits the packed w1' = UseHint(h, w); w is then not written
 cudaError_t launch_verify_core(int32_t* w, const int32_t* a_ext, const int32_t* v, int level, size_t batch, int sm_count,
-                               cudaStream_t st);
+                               cudaStream_t st, uint8_t* w1p = nullptr, const uint32_t* hmask = nullptr);
 cudaError_t launch_verify_mu(uint64_t* mu, const uint8_t* tr, const uint8_t* msgs, const uint64_t* offsets, uint32_t n,
                              uint32_t tr_stride, cudaStream_t st);
 cudaError_t launch_unpack_t1neg(int32_t* out, const uint8_t* t1p, size_t n_polys, cudaStream_t st);
 cudaError_t launch_verify_core_item(int32_t* w, const uint8_t* rho, const int32_t* v, const int32_t* extra, int level,
-                                    size_t batch, cudaStream_t st);
+                                    size_t batch, cudaStream_t st, uint8_t* w1p = nullptr, const uint32_t* hmask = nullptr,
+                                    bool* fused = nullptr);
 cudaError_t launch_tr(uint64_t* tr, const uint8_t* rho, const uint8_t* t1p, uint32_t t1_bytes, cudaStream_t st);
 cudaError_t launch_unpack_z(int level, int32_t* v, uint32_t* bad, const uint8_t* zp, uint32_t n, cudaStream_t st);
 cudaError_t launch_verify_prep(int level, int32_t* v, uint32_t* hmask, uint32_t* bad, const uint8_t* h, const uint64_t* ctilde,

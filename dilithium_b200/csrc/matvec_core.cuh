@@ -23,8 +23,10 @@ template <int K, int LA, bool INTT_OUT, bool EXTRA, bool W1, bool PRESCALED = tr
 __device__ __forceinline__ void item_rows(int32_t* __restrict__ w_item, const uint32_t (&yh)[LA + (EXTRA ? 1 : 0)][8],
                                           const uint32_t* __restrict__ a_sm, uint32_t* __restrict__ scr, int lane,
                                           const int32_t* __restrict__ extra_item, uint8_t* __restrict__ w1_item, int i_begin,
-                                          int i_end, int a_first_row = 0) {
+                                          int i_end, int a_first_row = 0, const uint32_t* __restrict__ hint_item = nullptr) {
     // a_first_row: the matrix row held first in a_sm (kernels that stream A through shared memory a few rows at a time)
+    // hint_item (W1 only; verification): k x 8 words of hint bits, bit b of word r of row i <-> coefficient 32 r + b.  The packed
+    // output is then w1' = UseHint(h, w) (usehint.v:134-155) instead of HighBits(w), and w itself is not stored at all.
     constexpr int L = LA + (EXTRA ? 1 : 0);
 #pragma unroll 1
     for (int i = i_begin; i < i_end; i++) {
@@ -62,16 +64,29 @@ __device__ __forceinline__ void item_rows(int32_t* __restrict__ w_item, const ui
             }
             ntt_inv_warp<PRESCALED>(x, scr, itw, lane);
             __syncwarp();
-            int32_t* o = w_item + i * N + lane;
+            if (!(W1 && hint_item != nullptr)) {
+                int32_t* o = w_item + i * N + lane;
 #pragma unroll
-            for (int r = 0; r < 8; r++) o[32 * r] = (int32_t)x[r];
+                for (int r = 0; r < 8; r++) o[32 * r] = (int32_t)x[r];
+            }
             if constexpr (W1) {
                 static_assert(INTT_OUT, "w1 is defined on the time-domain w");
                 constexpr int32_t G2 = K == 4 ? (Q_I - 1) / 88 : (Q_I - 1) / 32;
                 // this lane holds coefficients lane + 32 r: stage HighBits as bytes, re-read 8 consecutive ones
                 uint8_t* sb = reinterpret_cast<uint8_t*>(scr);
+                if (hint_item != nullptr) {   // uniform
+                    constexpr int32_t M = (Q_I - 1) / (2 * G2);   // 44 or 16
 #pragma unroll
-                for (int r = 0; r < 8; r++) sb[32 * r + lane] = (uint8_t)highbits<G2>(x[r]);
+                    for (int r = 0; r < 8; r++) {
+                        int32_t a1, a0;
+                        decompose<G2>((int32_t)x[r], a1, a0);
+                        if ((__ldg(hint_item + i * 8 + r) >> lane) & 1u) a1 = a0 > 0 ? (a1 + 1 == M ? 0 : a1 + 1) : (a1 == 0 ? M - 1 : a1 - 1);
+                        sb[32 * r + lane] = (uint8_t)a1;
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 8; r++) sb[32 * r + lane] = (uint8_t)highbits<G2>(x[r]);
+                }
                 __syncwarp();
                 const uint2 q = reinterpret_cast<const uint2*>(sb)[lane];
                 if constexpr (G2 == (Q_I - 1) / 32) {
@@ -143,7 +158,7 @@ __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const in
                                           const uint32_t* __restrict__ a_sm, uint32_t* __restrict__ scr, int lane,
                                           const int32_t* __restrict__ extra_item = nullptr,
                                           uint8_t* __restrict__ w1_item = nullptr, uint32_t* __restrict__ yh_sm = nullptr,
-                                          int part = 0) {
+                                          int part = 0, const uint32_t* __restrict__ hint_item = nullptr) {
     constexpr int L = LA + (EXTRA ? 1 : 0);   // number of input polynomials
     uint32_t yh[L][8];  // NTT-domain inputs in layout C
     if constexpr (NTT_IN && SPLIT) {
@@ -177,7 +192,7 @@ __device__ __forceinline__ void item_core(int32_t* __restrict__ w_item, const in
         item_inputs<L, NTT_IN>(yh, v_item, scr, lane);
     }
     const int i_begin = SPLIT ? part * (K / 2) : 0, i_end = SPLIT ? (part + 1) * (K / 2) : K;
-    item_rows<K, LA, INTT_OUT, EXTRA, W1, PRESCALED>(w_item, yh, a_sm, scr, lane, extra_item, w1_item, i_begin, i_end);
+    item_rows<K, LA, INTT_OUT, EXTRA, W1, PRESCALED>(w_item, yh, a_sm, scr, lane, extra_item, w1_item, i_begin, i_end, 0, hint_item);
 }
 
 #endif  // __CUDACC__

@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L, WARPS)) matv
                                                                    const int32_t* __restrict__ v, uint32_t batch,
                                                                    uint32_t* __restrict__ work_ctr,
                                                                    uint8_t* __restrict__ w1p = nullptr,
-                                                                   const uint32_t* __restrict__ batch_dev = nullptr) {
+                                                                   const uint32_t* __restrict__ batch_dev = nullptr,
+                                                                   const uint32_t* __restrict__ hmask = nullptr) {
+    // hmask != nullptr (verification, W1): the packed output is w1' = UseHint(h, w) and w is not stored (matvec_core.cuh)
     if (batch_dev != nullptr) batch = *batch_dev;   // round loop of batched signing: the size lives on the device
     constexpr int W1_ROW = K * (K == 4 ? 192 : 128);   // packed w1 bytes per item
     extern __shared__ __align__(16) uint32_t smem_u32v[];
@@ -115,7 +117,8 @@ __global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L, WARPS)) matv
     } else {
         for (uint32_t item = blockIdx.x * WARPS + warp; item < batch; item += gridDim.x * WARPS)
             item_core<K, L, NTT_IN, INTT_OUT, false, W1>(w + (size_t)item * K * N, v + (size_t)item * L * N, a_sm, scr, lane, nullptr,
-                                                         W1 ? w1p + (size_t)item * W1_ROW : nullptr);
+                                                         W1 ? w1p + (size_t)item * W1_ROW : nullptr, nullptr, 0,
+                                                         W1 && hmask != nullptr ? hmask + (size_t)item * K * 8 : nullptr);
     }
 }
 
@@ -134,11 +137,15 @@ constexpr size_t item_smem_bytes() {
     return (size_t)(G * K * L * A_STRIDE + NW * SCRATCH_WORDS + (item_split<K, L, G, NTT_IN>() ? (L + (EXTRA ? 1 : 0)) * N : 0)) * 4;
 }
 
-template <int K, int L, int G, bool NTT_IN, bool INTT_OUT, bool EXTRA = false>
+template <int K, int L, int G, bool NTT_IN, bool INTT_OUT, bool EXTRA = false, bool W1 = false>
 __global__ void __launch_bounds__(((G * K * L + 31) / 32) * 32) matvec_item_kernel(int32_t* __restrict__ w,
                                                                                  const uint8_t* __restrict__ rho,
                                                                                  const int32_t* __restrict__ v, uint32_t batch,
-                                                                                 const int32_t* __restrict__ extra = nullptr) {
+                                                                                 const int32_t* __restrict__ extra = nullptr,
+                                                                                 uint8_t* __restrict__ w1p = nullptr,
+                                                                                 const uint32_t* __restrict__ hmask = nullptr) {
+    // W1 (per-key verification): the output is the packed w1' = UseHint(h, w) of every item, w is not stored
+    constexpr int W1_ROW = K * (K == 4 ? 192 : 128);
     extern __shared__ __align__(16) uint32_t smem_u32v[];
     constexpr int NW = (G * K * L + 31) / 32;
     constexpr bool SPLIT = item_split<K, L, G, NTT_IN>();         // two warps share one item's core
@@ -158,16 +165,18 @@ __global__ void __launch_bounds__(((G * K * L + 31) / 32) * 32) matvec_item_kern
     const int warp = t >> 5, lane = t & 31;
     if constexpr (SPLIT) {
         if (item0 < batch)   // uniform for the CTA: both warps enter (the core synchronises the CTA once)
-            item_core<K, L, NTT_IN, INTT_OUT, EXTRA, false, true, false>(w + item0 * K * N, v + item0 * (L + (EXTRA ? 1 : 0)) * N, a_sm,
+            item_core<K, L, NTT_IN, INTT_OUT, EXTRA, W1, true, false>(w + item0 * K * N, v + item0 * (L + (EXTRA ? 1 : 0)) * N, a_sm,
                                                                  scr_all + warp * SCRATCH_WORDS, lane,
-                                                                 EXTRA ? extra + item0 * K * N : nullptr, nullptr, yh_sm, warp);
+                                                                 EXTRA ? extra + item0 * K * N : nullptr, W1 ? w1p + item0 * W1_ROW : nullptr,
+                                                                 yh_sm, warp, W1 ? hmask + item0 * K * 8 : nullptr);
     } else {
     for (int g = warp; g < G; g += NW) {
         const size_t item = item0 + g;
         if (item < batch)
-            item_core<K, L, NTT_IN, INTT_OUT, EXTRA, false, false, false>(w + item * K * N, v + item * (L + (EXTRA ? 1 : 0)) * N,
+            item_core<K, L, NTT_IN, INTT_OUT, EXTRA, W1, false, false>(w + item * K * N, v + item * (L + (EXTRA ? 1 : 0)) * N,
                                                      a_sm + g * K * L * A_STRIDE, scr_all + warp * SCRATCH_WORDS, lane,
-                                                     EXTRA ? extra + item * K * N : nullptr);
+                                                     EXTRA ? extra + item * K * N : nullptr, W1 ? w1p + item * W1_ROW : nullptr, nullptr, 0,
+                                                     W1 ? hmask + item * K * 8 : nullptr);
     }
     }
 }
@@ -246,7 +255,7 @@ constexpr size_t shared_smem_bytes(int warps) {
 template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT, int MAX_CTAS = 8, bool W1 = false>
 static cudaError_t launch_shared_t(int32_t* w, const int32_t* a_hat, const uint8_t* rho, const int32_t* v, size_t batch,
                                    int sm_count, cudaStream_t st, uint32_t* work_ctr = nullptr, uint8_t* w1p = nullptr,
-                                   const uint32_t* batch_dev = nullptr) {
+                                   const uint32_t* batch_dev = nullptr, const uint32_t* hmask = nullptr) {
     auto kern = matvec_shared_kernel<K, L, WARPS, EXPAND, NTT_IN, INTT_OUT, W1>;
     constexpr size_t smem = shared_smem_bytes<K, L>(WARPS);
     static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
@@ -258,7 +267,7 @@ static cudaError_t launch_shared_t(int32_t* w, const int32_t* a_hat, const uint8
     size_t want = (batch + WARPS - 1) / WARPS;
     size_t cap = (size_t)sm_count * ctas_per_sm;
     unsigned grid = (unsigned)(want < cap ? want : cap);
-    kern<<<grid, WARPS * 32, smem, st>>>(w, a_hat, rho, v, (uint32_t)batch, work_ctr, w1p, batch_dev);
+    kern<<<grid, WARPS * 32, smem, st>>>(w, a_hat, rho, v, (uint32_t)batch, work_ctr, w1p, batch_dev, hmask);
     return cudaGetLastError();
 }
 
@@ -283,7 +292,7 @@ static cudaError_t launch_item_t(int32_t* w, const uint8_t* rho, const int32_t* 
     static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
     if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(smem), configured); e != cudaSuccess) return e;
     constexpr int threads = NW * 32;
-    kern<<<(unsigned)((batch + G - 1) / G), threads, smem, st>>>(w, rho, v, (uint32_t)batch, nullptr);
+    kern<<<(unsigned)((batch + G - 1) / G), threads, smem, st>>>(w, rho, v, (uint32_t)batch, nullptr, nullptr, nullptr);
     return cudaGetLastError();
 }
 
@@ -342,18 +351,27 @@ cudaError_t launch_signcore(int32_t* w, const int32_t* a_hat, const int32_t* y, 
 // verification core with per-item public keys: A from rho[item] on chip, extra column t1neg_hat[item] from HBM
 template <int K, int L>
 static cudaError_t launch_verify_item_t(int32_t* w, const uint8_t* rho, const int32_t* v, const int32_t* extra, size_t batch,
-                                        cudaStream_t st) {
+                                        cudaStream_t st, uint8_t* w1p, const uint32_t* hmask) {
     constexpr int G = item_group<K, L>();
     constexpr int NW = (G * K * L + 31) / 32;
-    auto kern = matvec_item_kernel<K, L, G, true, true, true>;
     constexpr size_t smem = item_smem_bytes<K, L, G, true, true>();
-    static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
+    static std::atomic<uint64_t> configured{0}, configured_w1{0};   // one bit per device: the attribute is per device
+    if (w1p != nullptr && hmask != nullptr) {   // fused UseHint + w1 packing: w is not written
+        auto kern = matvec_item_kernel<K, L, G, true, true, true, true>;
+        if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(smem), configured_w1); e != cudaSuccess) return e;
+        kern<<<(unsigned)((batch + G - 1) / G), NW * 32, smem, st>>>(w, rho, v, (uint32_t)batch, extra, w1p, hmask);
+        return cudaGetLastError();
+    }
+    auto kern = matvec_item_kernel<K, L, G, true, true, true>;
     if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(smem), configured); e != cudaSuccess) return e;
-    kern<<<(unsigned)((batch + G - 1) / G), NW * 32, smem, st>>>(w, rho, v, (uint32_t)batch, extra);
+    kern<<<(unsigned)((batch + G - 1) / G), NW * 32, smem, st>>>(w, rho, v, (uint32_t)batch, extra, nullptr, nullptr);
     return cudaGetLastError();
 }
+// w1p / hmask non-null: the core also applies the hints and emits the packed w1' (no usehint_pack pass, w is not written);
+// *fused tells the caller whether that happened (the row-streamed A/B kernel keeps the separate pass)
 cudaError_t launch_verify_core_item(int32_t* w, const uint8_t* rho, const int32_t* v, const int32_t* extra, int level,
-                                    size_t batch, cudaStream_t st) {
+                                    size_t batch, cudaStream_t st, uint8_t* w1p, const uint32_t* hmask, bool* fused) {
+    if (fused) *fused = false;
     if (batch == 0) return cudaSuccess;
     if (batch >= g_item_rows_min.load()) {   // row-streamed kernel (8 items per CTA); tiny batches keep one CTA per item
         int dev = 0, sms = 148;
@@ -365,18 +383,27 @@ cudaError_t launch_verify_core_item(int32_t* w, const uint8_t* rho, const int32_
         }
         return cudaErrorInvalidValue;
     }
+    if (fused) *fused = w1p != nullptr && hmask != nullptr;
     switch (level) {
-        case 2: return launch_verify_item_t<4, 4>(w, rho, v, extra, batch, st);
-        case 3: return launch_verify_item_t<6, 5>(w, rho, v, extra, batch, st);
-        case 5: return launch_verify_item_t<8, 7>(w, rho, v, extra, batch, st);
+        case 2: return launch_verify_item_t<4, 4>(w, rho, v, extra, batch, st, w1p, hmask);
+        case 3: return launch_verify_item_t<6, 5>(w, rho, v, extra, batch, st, w1p, hmask);
+        case 5: return launch_verify_item_t<8, 7>(w, rho, v, extra, batch, st, w1p, hmask);
     }
     return cudaErrorInvalidValue;
 }
 
 // verification core: k x (l+1) matrix [A_hat | -t1_hat*2^13], inputs [z_0..z_{l-1}, c] in the time domain
 cudaError_t launch_verify_core(int32_t* w, const int32_t* a_ext, const int32_t* v, int level, size_t batch, int sm_count,
-                               cudaStream_t st) {
+                               cudaStream_t st, uint8_t* w1p, const uint32_t* hmask) {
     if (batch == 0) return cudaSuccess;
+    if (w1p != nullptr && hmask != nullptr) {   // fused UseHint + w1 packing: w is not written
+        switch (level) {
+            case 2: return launch_shared_t<4, 5, 8, false, true, true, 8, true>(w, a_ext, nullptr, v, batch, sm_count, st, nullptr, w1p, nullptr, hmask);
+            case 3: return launch_shared_t<6, 6, 8, false, true, true, 8, true>(w, a_ext, nullptr, v, batch, sm_count, st, nullptr, w1p, nullptr, hmask);
+            case 5: return launch_shared_t<8, 8, 8, false, true, true, 8, true>(w, a_ext, nullptr, v, batch, sm_count, st, nullptr, w1p, nullptr, hmask);
+        }
+        return cudaErrorInvalidValue;
+    }
     switch (level) {
         case 2: return launch_shared_t<4, 5, 8, false, true, true>(w, a_ext, nullptr, v, batch, sm_count, st);
         case 3: return launch_shared_t<6, 6, 8, false, true, true>(w, a_ext, nullptr, v, batch, sm_count, st);

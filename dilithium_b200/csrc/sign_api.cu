@@ -1151,11 +1151,19 @@ int verify_run(dil_engine* e, dil_verify_key* k, const uint8_t* d_msgs, const ui
     CK(dil::launch_verify_mu(k->mu_d, k->seeds, d_msgs, d_off, nn, 0, st));
     CK(dil::launch_unpack_z(P.level, k->v, k->bad, d_z, nn, st));
     CK(dil::launch_verify_prep(P.level, k->v, k->hmask, k->bad, d_h, reinterpret_cast<const uint64_t*>(d_ct), nn, st));
-    CK(dil::launch_verify_core(k->w, k->a_ext, k->v, P.level, n, e->sm_count, st));
-    CK(dil::launch_usehint_pack(P.level, reinterpret_cast<uint32_t*>(k->w1p), k->w, k->hmask, nn, st));
+    // Levels 2 and 3: the core applies the hints and packs w1' = UseHint(h, w') itself - no separate pass, w' never reaches HBM
+    // (+12 % verifications/s).  Level 5: the 8 x 8 core runs one 8-warp CTA per SM and is latency-bound; the extra work per row
+    // costs it more than the pass saves (55.6 vs 65.8 M/s measured), so it keeps the separate usehint_pack pass.
+    if (P.level != 5) {
+        CK(dil::launch_verify_core(k->w, k->a_ext, k->v, P.level, n, e->sm_count, st, reinterpret_cast<uint8_t*>(k->w1p), k->hmask));
+    } else {
+        CK(dil::launch_verify_core(k->w, k->a_ext, k->v, P.level, n, e->sm_count, st));
+        CK(dil::launch_usehint_pack(P.level, reinterpret_cast<uint32_t*>(k->w1p), k->w, k->hmask, nn, st));
+        e->launches += 1;
+    }
     CK(dil::launch_verify_hash(P.level, d_ok, k->mu_d, k->w1p, reinterpret_cast<const uint64_t*>(d_ct), k->bad, nn, st));
     CK(cudaEventRecord(k->ws_done, st));
-    e->launches += 6;
+    e->launches += 5;
     return DIL_OK;
 }
 }  // namespace
@@ -1497,6 +1505,8 @@ cudaError_t verify_multi_run(dil_engine* e, const LevelParams& P, uint8_t* work,
     A(dil::launch_verify_prep(P.level, P32(m.v), PU32(m.hm), PU32(m.bad), d_h, reinterpret_cast<const uint64_t*>(d_ct), nn, st));
     A(dil::launch_unpack_t1neg(P32(m.t1n), d_t1p, n * K, st));
     A(dil::launch_ntt_fwd(P32(m.t1n), P32(m.t1n), n * K, e->sm_count, st));
+    // per-key verification keeps the separate UseHint pass: its core is Keccak-bound, one warp (two at level 5) per item, and
+    // the fused variant (matvec_item_kernel<..., W1>, kept for A/B) measured 2 % slower at level 5
     A(dil::launch_verify_core_item(P32(m.w), d_rho, P32(m.v), P32(m.t1n), P.level, n, st));
     A(dil::launch_usehint_pack(P.level, PU32(m.w1p), P32(m.w), PU32(m.hm), nn, st));
     A(dil::launch_verify_hash(P.level, d_ok, PU64(m.mu), PU64(m.w1p), reinterpret_cast<const uint64_t*>(d_ct), PU32(m.bad), nn, st));
