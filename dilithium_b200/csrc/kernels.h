@@ -106,9 +106,12 @@ cudaError_t launch_drain(uint8_t* hz, uint8_t* hh, uint8_t* hct, uint32_t* hatt,
                          uint32_t hb, cudaStream_t st);
 cudaError_t launch_publish_ctl(uint32_t* host_dst_dev, const RoundCtl* ctl, cudaStream_t st);
 // ---- verify pipeline ----
-// w1p / hmask non-null: the core applies the hints itself and emits the packed w1' = UseHint(h, w); w is then not written
+// w1p / hmask non-null: the core applies the hints itself and emits the packed w1' = UseHint(h, w); w is then not written.
+// zp / bad_flags non-null as well (levels 2 and 3): z is read from the packed signature (4-byte aligned) inside the core, with
+// the ||z|| check; v then only has to hold the challenge polynomial (last of the l + 1 polynomials of an item record)
 cudaError_t launch_verify_core(int32_t* w, const int32_t* a_ext, const int32_t* v, int level, size_t batch, int sm_count,
-                               cudaStream_t st, uint8_t* w1p = nullptr, const uint32_t* hmask = nullptr);
+                               cudaStream_t st, uint8_t* w1p = nullptr, const uint32_t* hmask = nullptr, const uint8_t* zp = nullptr,
+                               uint32_t* bad_flags = nullptr);
 cudaError_t launch_verify_mu(uint64_t* mu, const uint8_t* tr, const uint8_t* msgs, const uint64_t* offsets, uint32_t n,
                              uint32_t tr_stride, cudaStream_t st);
 cudaError_t launch_unpack_t1neg(int32_t* out, const uint8_t* t1p, size_t n_polys, cudaStream_t st);

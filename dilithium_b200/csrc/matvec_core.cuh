@@ -142,6 +142,48 @@ __device__ __forceinline__ void item_inputs(uint32_t (&yh)[L][8], const int32_t*
     }
 }
 
+// Verification inputs straight from the signature: the item's LZ polynomials of z are read from their packed form
+// (gamma1 - z in ZBITS = 18 / 20 bits per coefficient, encoder.v:96-133 / decoder.v:89-143) - no unpack pass, no 4 KiB per
+// polynomial of int32 in HBM - and the challenge polynomial c (int32, time domain, from verify_prep) is the last input.
+// Every coefficient is a bit field inside two aligned 32-bit words (one funnel shift); the ||z|| < gamma1 - beta check of
+// the unpack pass happens here.  Returns (warp-uniform) whether the item violates the bound.
+template <int LZ, int ZBITS, int BETA>
+__device__ __forceinline__ bool item_inputs_zpacked(uint32_t (&yh)[LZ + 1][8], const uint8_t* __restrict__ z_item,
+                                                    const int32_t* __restrict__ c_item, uint32_t* __restrict__ scr, int lane) {
+    constexpr int ROWB = 32 * ZBITS;              // packed bytes per polynomial: 576 / 640
+    constexpr int32_t G1 = 1 << (ZBITS - 1);
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < LZ; j++) {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(z_item + j * ROWB);
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int bit = (lane + 32 * r) * ZBITS, byte = bit >> 3, aw = byte >> 2, sh = (byte & 3) * 8 + (bit & 7);
+            const uint32_t w0 = __ldg(p + aw), w1 = (4 * aw + 4 < ROWB) ? __ldg(p + aw + 1) : 0u;
+            const int32_t zc = G1 - (int32_t)(__funnelshift_r(w0, w1, sh) & ((1u << ZBITS) - 1));
+            bad |= (zc >= G1 - BETA) || (zc <= -(G1 - BETA));
+            yh[j][r] = (uint32_t)zc;              // signed representative: lifted inside the first butterfly
+        }
+    }
+    {
+        const int32_t* p = c_item + lane;
+#pragma unroll
+        for (int r = 0; r < 8; r++) yh[LZ][r] = (uint32_t)p[32 * r];
+    }
+    FwdTw ftw;
+    {
+        const TwTable* tab = &TW_FWD;
+        asm volatile("" : "+l"(tab));
+        load_fwd_tw(ftw, tab, lane);
+    }
+#pragma unroll
+    for (int j = 0; j < LZ + 1; j++) {
+        ntt_fwd_warp(yh[j], scr, ftw, lane);
+        __syncwarp();
+    }
+    return __any_sync(0xffffffffu, bad);
+}
+
 // ---- per-item core, executed by one warp ----
 // v_item: l polys (global), w_item: k polys (global), a_sm: k*l polys in shared memory (stride A_STRIDE)
 // EXTRA = true (verification with per-item public keys): v_item holds L+1 polynomials, and the last one is

@@ -47,15 +47,19 @@ cudaError_t launch_expand_a(int32_t* a_hat, const uint8_t* rho, size_t n_rho, in
 // integer-multiply pipe, not by latency.)
 constexpr int shared_min_ctas(int k, int l, int warps = 8) { return warps > 8 ? 1 : (k * l <= 56 ? 2 : 1); }
 
-template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT, bool W1 = false>
+template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT, bool W1 = false, int ZBITS = 0, int BETA = 0>
 __global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L, WARPS)) matvec_shared_kernel(int32_t* __restrict__ w, const int32_t* __restrict__ a_hat,
                                                                    const uint8_t* __restrict__ rho,
                                                                    const int32_t* __restrict__ v, uint32_t batch,
                                                                    uint32_t* __restrict__ work_ctr,
                                                                    uint8_t* __restrict__ w1p = nullptr,
                                                                    const uint32_t* __restrict__ batch_dev = nullptr,
-                                                                   const uint32_t* __restrict__ hmask = nullptr) {
+                                                                   const uint32_t* __restrict__ hmask = nullptr,
+                                                                   const uint8_t* __restrict__ zp = nullptr,
+                                                                   uint32_t* __restrict__ bad_flags = nullptr) {
     // hmask != nullptr (verification, W1): the packed output is w1' = UseHint(h, w) and w is not stored (matvec_core.cuh)
+    // ZBITS > 0 (verification): the first L - 1 inputs are read from the packed z of the signature (zp), only the challenge
+    // polynomial comes from v; items violating ||z|| < gamma1 - beta are flagged in bad_flags
     if (batch_dev != nullptr) batch = *batch_dev;   // round loop of batched signing: the size lives on the device
     constexpr int W1_ROW = K * (K == 4 ? 192 : 128);   // packed w1 bytes per item
     extern __shared__ __align__(16) uint32_t smem_u32v[];
@@ -115,10 +119,22 @@ __global__ void __launch_bounds__(WARPS * 32, shared_min_ctas(K, L, WARPS)) matv
             next = __shfl_sync(0xffffffffu, claim, 0);
         }
     } else {
-        for (uint32_t item = blockIdx.x * WARPS + warp; item < batch; item += gridDim.x * WARPS)
-            item_core<K, L, NTT_IN, INTT_OUT, false, W1>(w + (size_t)item * K * N, v + (size_t)item * L * N, a_sm, scr, lane, nullptr,
-                                                         W1 ? w1p + (size_t)item * W1_ROW : nullptr, nullptr, 0,
-                                                         W1 && hmask != nullptr ? hmask + (size_t)item * K * 8 : nullptr);
+        for (uint32_t item = blockIdx.x * WARPS + warp; item < batch; item += gridDim.x * WARPS) {
+            if constexpr (ZBITS > 0) {
+                static_assert(NTT_IN && INTT_OUT && !EXPAND, "packed-z inputs belong to the verification core");
+                uint32_t yh[L][8];
+                const bool bad = item_inputs_zpacked<L - 1, ZBITS, BETA>(yh, zp + (size_t)item * (L - 1) * (32 * ZBITS),
+                                                                         v + (size_t)item * L * N + (L - 1) * N, scr, lane);
+                if (bad && lane == 0) bad_flags[item] = 1;
+                item_rows<K, L, INTT_OUT, false, W1>(w + (size_t)item * K * N, yh, a_sm, scr, lane, nullptr,
+                                                     W1 ? w1p + (size_t)item * W1_ROW : nullptr, 0, K, 0,
+                                                     W1 && hmask != nullptr ? hmask + (size_t)item * K * 8 : nullptr);
+            } else {
+                item_core<K, L, NTT_IN, INTT_OUT, false, W1>(w + (size_t)item * K * N, v + (size_t)item * L * N, a_sm, scr, lane, nullptr,
+                                                             W1 ? w1p + (size_t)item * W1_ROW : nullptr, nullptr, 0,
+                                                             W1 && hmask != nullptr ? hmask + (size_t)item * K * 8 : nullptr);
+            }
+        }
     }
 }
 
@@ -252,11 +268,12 @@ constexpr size_t shared_smem_bytes(int warps) {
     return (size_t)(K * L * A_STRIDE + warps * SCRATCH_WORDS) * 4;
 }
 
-template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT, int MAX_CTAS = 8, bool W1 = false>
+template <int K, int L, int WARPS, bool EXPAND, bool NTT_IN, bool INTT_OUT, int MAX_CTAS = 8, bool W1 = false, int ZBITS = 0, int BETA = 0>
 static cudaError_t launch_shared_t(int32_t* w, const int32_t* a_hat, const uint8_t* rho, const int32_t* v, size_t batch,
                                    int sm_count, cudaStream_t st, uint32_t* work_ctr = nullptr, uint8_t* w1p = nullptr,
-                                   const uint32_t* batch_dev = nullptr, const uint32_t* hmask = nullptr) {
-    auto kern = matvec_shared_kernel<K, L, WARPS, EXPAND, NTT_IN, INTT_OUT, W1>;
+                                   const uint32_t* batch_dev = nullptr, const uint32_t* hmask = nullptr, const uint8_t* zp = nullptr,
+                                   uint32_t* bad_flags = nullptr) {
+    auto kern = matvec_shared_kernel<K, L, WARPS, EXPAND, NTT_IN, INTT_OUT, W1, ZBITS, BETA>;
     constexpr size_t smem = shared_smem_bytes<K, L>(WARPS);
     static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per device
     if (cudaError_t e = ensure_dyn_smem(kern, (size_t)(smem), configured); e != cudaSuccess) return e;
@@ -267,7 +284,7 @@ static cudaError_t launch_shared_t(int32_t* w, const int32_t* a_hat, const uint8
     size_t want = (batch + WARPS - 1) / WARPS;
     size_t cap = (size_t)sm_count * ctas_per_sm;
     unsigned grid = (unsigned)(want < cap ? want : cap);
-    kern<<<grid, WARPS * 32, smem, st>>>(w, a_hat, rho, v, (uint32_t)batch, work_ctr, w1p, batch_dev, hmask);
+    kern<<<grid, WARPS * 32, smem, st>>>(w, a_hat, rho, v, (uint32_t)batch, work_ctr, w1p, batch_dev, hmask, zp, bad_flags);
     return cudaGetLastError();
 }
 
@@ -394,8 +411,15 @@ cudaError_t launch_verify_core_item(int32_t* w, const uint8_t* rho, const int32_
 
 // verification core: k x (l+1) matrix [A_hat | -t1_hat*2^13], inputs [z_0..z_{l-1}, c] in the time domain
 cudaError_t launch_verify_core(int32_t* w, const int32_t* a_ext, const int32_t* v, int level, size_t batch, int sm_count,
-                               cudaStream_t st, uint8_t* w1p, const uint32_t* hmask) {
+                               cudaStream_t st, uint8_t* w1p, const uint32_t* hmask, const uint8_t* zp, uint32_t* bad_flags) {
     if (batch == 0) return cudaSuccess;
+    if (w1p != nullptr && hmask != nullptr && zp != nullptr && bad_flags != nullptr) {   // packed z in, packed w1' out (levels 2, 3)
+        switch (level) {
+            case 2: return launch_shared_t<4, 5, 8, false, true, true, 8, true, 18, 78>(w, a_ext, nullptr, v, batch, sm_count, st, nullptr, w1p, nullptr, hmask, zp, bad_flags);
+            case 3: return launch_shared_t<6, 6, 8, false, true, true, 8, true, 20, 196>(w, a_ext, nullptr, v, batch, sm_count, st, nullptr, w1p, nullptr, hmask, zp, bad_flags);
+        }
+        return cudaErrorInvalidValue;
+    }
     if (w1p != nullptr && hmask != nullptr) {   // fused UseHint + w1 packing: w is not written
         switch (level) {
             case 2: return launch_shared_t<4, 5, 8, false, true, true, 8, true>(w, a_ext, nullptr, v, batch, sm_count, st, nullptr, w1p, nullptr, hmask);

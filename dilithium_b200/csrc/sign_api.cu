@@ -1149,21 +1149,23 @@ int verify_run(dil_engine* e, dil_verify_key* k, const uint8_t* d_msgs, const ui
     else CK(cudaStreamWaitEvent(st, k->ws_done, 0));   // the previous batch may still be running on another stream
     CK(cudaMemsetAsync(k->bad, 0, n * 4, st));
     CK(dil::launch_verify_mu(k->mu_d, k->seeds, d_msgs, d_off, nn, 0, st));
-    CK(dil::launch_unpack_z(P.level, k->v, k->bad, d_z, nn, st));
-    CK(dil::launch_verify_prep(P.level, k->v, k->hmask, k->bad, d_h, reinterpret_cast<const uint64_t*>(d_ct), nn, st));
-    // Levels 2 and 3: the core applies the hints and packs w1' = UseHint(h, w') itself - no separate pass, w' never reaches HBM
-    // (+12 % verifications/s).  Level 5: the 8 x 8 core runs one 8-warp CTA per SM and is latency-bound; the extra work per row
-    // costs it more than the pass saves (55.6 vs 65.8 M/s measured), so it keeps the separate usehint_pack pass.
+    // Levels 2 and 3: the core reads z straight from the packed signature (with the ||z|| check) and applies the hints and packs
+    // w1' = UseHint(h, w') itself - no unpack pass, no UseHint pass, neither z as int32 nor w' ever reaches HBM.  Level 5: the
+    // 8 x 8 core (one CTA per SM, 167-183 registers) is latency-bound; the extra work per row costs it more than the passes save
+    // (fused UseHint: 55.6 vs 65.8 M/s measured), so it keeps the separate unpack_z / usehint_pack passes.
     if (P.level != 5) {
-        CK(dil::launch_verify_core(k->w, k->a_ext, k->v, P.level, n, e->sm_count, st, reinterpret_cast<uint8_t*>(k->w1p), k->hmask));
+        CK(dil::launch_verify_prep(P.level, k->v, k->hmask, k->bad, d_h, reinterpret_cast<const uint64_t*>(d_ct), nn, st));
+        CK(dil::launch_verify_core(k->w, k->a_ext, k->v, P.level, n, e->sm_count, st, reinterpret_cast<uint8_t*>(k->w1p), k->hmask, d_z, k->bad));
     } else {
+        CK(dil::launch_unpack_z(P.level, k->v, k->bad, d_z, nn, st));
+        CK(dil::launch_verify_prep(P.level, k->v, k->hmask, k->bad, d_h, reinterpret_cast<const uint64_t*>(d_ct), nn, st));
         CK(dil::launch_verify_core(k->w, k->a_ext, k->v, P.level, n, e->sm_count, st));
         CK(dil::launch_usehint_pack(P.level, reinterpret_cast<uint32_t*>(k->w1p), k->w, k->hmask, nn, st));
-        e->launches += 1;
+        e->launches += 2;
     }
     CK(dil::launch_verify_hash(P.level, d_ok, k->mu_d, k->w1p, reinterpret_cast<const uint64_t*>(d_ct), k->bad, nn, st));
     CK(cudaEventRecord(k->ws_done, st));
-    e->launches += 5;
+    e->launches += 4;
     return DIL_OK;
 }
 }  // namespace
