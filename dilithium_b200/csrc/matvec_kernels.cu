@@ -431,7 +431,7 @@ cudaError_t launch_verify_core(int32_t* w, const int32_t* a_ext, const int32_t* 
     switch (level) {
         case 2: return launch_shared_t<4, 5, 8, false, true, true>(w, a_ext, nullptr, v, batch, sm_count, st);
         case 3: return launch_shared_t<6, 6, 8, false, true, true>(w, a_ext, nullptr, v, batch, sm_count, st);
-        case 5: return launch_shared_t<8, 8, 12, false, true, true>(w, a_ext, nullptr, v, batch, sm_count, st);
+        case 5: return launch_shared_t<8, 8, 16, false, true, true>(w, a_ext, nullptr, v, batch, sm_count, st);
     }
     return cudaErrorInvalidValue;
 }

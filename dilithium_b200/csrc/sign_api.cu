@@ -1151,7 +1151,7 @@ int verify_run(dil_engine* e, dil_verify_key* k, const uint8_t* d_msgs, const ui
     CK(dil::launch_verify_mu(k->mu_d, k->seeds, d_msgs, d_off, nn, 0, st));
     // Levels 2 and 3: the core reads z straight from the packed signature (with the ||z|| check) and applies the hints and packs
     // w1' = UseHint(h, w') itself - no unpack pass, no UseHint pass, neither z as int32 nor w' ever reaches HBM.  Level 5: the
-    // 8 x 8 core (one CTA per SM, 167-183 registers) is latency-bound; the extra work per row costs it more than the passes save
+    // 8 x 8 core (one CTA per SM) gains nothing from it: the extra work per row costs it as much as the passes save
     // (fused UseHint: 55.6 vs 65.8 M/s with 8 warps per SM; everything fused with 12 warps: 70.4 vs 72.7 M/s at 2^20), so it keeps the
     // separate unpack_z / usehint_pack passes.
     if (P.level != 5) {
