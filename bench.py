@@ -69,7 +69,7 @@ def parse():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--level", type=int, default=2, choices=[2, 3, 5])
     ap.add_argument("--batch", type=int, default=65536, help="signatures per GPU per step (weak scaling)")
-    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--in-flight", type=int, default=4,
                     help="sign batches in flight per GPU in the timed loops (one key handle and stream each); 1 = strictly one at a time")
     ap.add_argument("--driver", default="async", choices=["async", "threads"],
