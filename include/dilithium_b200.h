@@ -154,7 +154,8 @@ int dil_sign_batch_dev(dil_engine_t *e, dil_sign_key_t *k, const uint8_t *d_msgs
  * returns the batch's status - only then are the outputs complete.  A key handle carries one batch at a time (a second *_begin,
  * a synchronous call or dil_sign_key_set_tuning on a busy handle returns DIL_ERR_ARG); use one handle of the same key per batch in
  * flight.  Limits: at most 1.25 x dev_chunk (2^20) messages for _dev_begin and 1.25 x host_chunk (2^18) for _host_begin; _host_begin
- * needs pinned, device-addressable output buffers (the streaming path) and msgs / offsets must stay valid until the finish.
+ * needs pinned, device-addressable output buffers (the streaming path); every buffer passed to *_begin (and the stream given to
+ * _dev_begin) must stay valid until the finish.  dil_sign_key_destroy completes a batch that was begun and never finished.
  * dil_sign_batch_dev / _host are exactly begin + finish for batches within those limits. */
 int dil_sign_batch_dev_begin(dil_engine_t *e, dil_sign_key_t *k, const uint8_t *d_msgs, const uint64_t *d_offsets, size_t n,
                              uint8_t *d_z, uint8_t *d_h, uint8_t *d_ctilde, uint32_t *d_attempts, void *stream);
